@@ -1,0 +1,119 @@
+"""Host-side state container: Python mirror of the reference's CLOUDSC2_ARRAY_STATE
+(src/common/module/cloudsc2_array_state_mod.F90:28-203) on top of the C host helpers.
+
+Arrays are NumPy, C-order ``(NBLOCKS, KLEV, NPROMA)`` == Fortran ``(NPROMA, KLEV, NBLOCKS)``,
+so ``arr.ctypes.data`` is exactly the pointer the Fortran host would pass through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+
+SRC_2D = ("pt", "pq", "pap", "plu", "plude", "pmfu", "pmfd", "pa", "psupsat")
+
+
+def default_params(lregcl: bool = False) -> _abi.Params:
+    """Constants of SURVEY Appendix E via cloudsc2_default_params (include/cloudsc2_host.h)."""
+    lib = _abi.load_library()
+    p = _abi.Params()
+    lib.cloudsc2_default_params(C.byref(p))
+    p.lregcl = int(bool(lregcl))
+    return p
+
+
+@dataclass
+class SourceColumns:
+    """Un-expanded columns in the input.h5 layout: every field C-order (NDIM, KLEV, KLON)."""
+    klon: int
+    klev: int
+    ptsphy: float
+    ceta: np.ndarray
+    f: dict = field(default_factory=dict)   # name -> ndarray
+
+    def subset(self, cols) -> "SourceColumns":
+        cols = np.asarray(cols)
+        g = {k: np.ascontiguousarray(v[..., cols]) for k, v in self.f.items()}
+        return SourceColumns(len(cols), self.klev, self.ptsphy, self.ceta.copy(), g)
+
+
+def synth_source(seed: int = 0, klon: int = 100, klev: int = 137,
+                 params: _abi.Params | None = None) -> SourceColumns:
+    """Seeded synthetic stand-in for config-files/input.h5 (absent from the reference)."""
+    lib = _abi.load_library()
+    p = params if params is not None else default_params()
+    s = _abi.Source()
+    rc = lib.cloudsc2_source_synth(C.byref(s), seed, klon, klev, C.byref(p))
+    if rc:
+        raise RuntimeError(f"cloudsc2_source_synth failed rc={rc}")
+    try:
+        def arr(ptr, shape):
+            return np.ctypeslib.as_array(ptr, shape=shape).copy()
+        f = {n: arr(getattr(s, n), (klev, klon)) for n in SRC_2D}
+        f["paph"] = arr(s.paph, (klev + 1, klon))
+        f["pclv"] = arr(s.pclv, (_abi.NCLV, klev, klon))
+        f["tend_cml"] = arr(s.tend_cml, (_abi.NSTATE, klev, klon))
+        out = SourceColumns(klon, klev, float(s.ptsphy), arr(s.ceta, (klev,)), f)
+    finally:
+        lib.cloudsc2_source_free(C.byref(s))
+    return out
+
+
+def nblocks(ngptot: int, nproma: int) -> int:
+    return ngptot // nproma + min(ngptot % nproma, 1)
+
+
+def expand(src: np.ndarray, nproma: int, ngptot: int) -> np.ndarray:
+    """expand_mod.F90:270-335 through cloudsc2_expand_host.  src (..., NLEV, NLON)."""
+    lib = _abi.load_library()
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    nlon, nlev = src.shape[-1], src.shape[-2]
+    ndim = int(np.prod(src.shape[:-2])) if src.ndim > 2 else 1
+    nb = nblocks(ngptot, nproma)
+    shape = (nb,) + (tuple(src.shape[:-2]) if src.ndim > 2 else ()) + (nlev, nproma)
+    dst = np.empty(shape, dtype=np.float64)
+    lib.cloudsc2_expand_host(src.ctypes.data_as(_abi.c_double_p), nlon, nlev, ndim,
+                             dst.ctypes.data_as(_abi.c_double_p), nproma, ngptot)
+    return dst
+
+
+class ArrayState:
+    """Blocked arrays of one problem (mirror of CLOUDSC2_ARRAY_STATE%LOAD)."""
+
+    def __init__(self, src: SourceColumns, nproma: int, ngptot: int):
+        self.nproma, self.klev, self.ngptot = nproma, src.klev, ngptot
+        self.nblocks = nblocks(ngptot, nproma)
+        self.ptsphy = src.ptsphy
+        self.ceta = np.ascontiguousarray(src.ceta)
+        a = {}
+        for n in ("pt", "pq", "pap", "paph", "plu", "plude", "pmfu", "pmfd", "psupsat", "pa",
+                  "pclv"):
+            a[n] = expand(src.f[n], nproma, ngptot)
+        a["b_cml"] = expand(src.f["tend_cml"], nproma, ngptot)
+        nb, kl = self.nblocks, self.klev
+        a["b_loc"] = np.zeros((nb, _abi.NSTATE, kl, nproma))
+        a["pcovptot"] = np.zeros((nb, kl, nproma))
+        for n in ("pfplsl", "pfplsn", "pfhpsl", "pfhpsn"):
+            a[n] = np.zeros((nb, kl + 1, nproma))
+        self.a = a
+
+    def fields(self) -> _abi.Fields:
+        f = _abi.Fields()
+        for n in _abi.FIELD_IN + _abi.FIELD_OUT:
+            setattr(f, n, self.a[n].ctypes.data)
+        return f
+
+    def reset_outputs(self, fill: float = 0.0):
+        for n in ("b_loc", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn"):
+            self.a[n].fill(fill)
+
+    # views named as the reference's outputs
+    def outputs(self) -> dict:
+        a = self.a
+        return {"tend_loc_t": a["b_loc"][:, 0], "tend_loc_q": a["b_loc"][:, 2],
+                "tend_loc_l": a["b_loc"][:, 3], "tend_loc_i": a["b_loc"][:, 4],
+                "pa": a["pa"], "pfplsl": a["pfplsl"], "pfplsn": a["pfplsn"],
+                "pfhpsl": a["pfhpsl"], "pfhpsn": a["pfhpsn"], "pcovptot": a["pcovptot"]}

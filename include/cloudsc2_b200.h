@@ -1,0 +1,174 @@
+/*
+ * cloudsc2_b200.h -- C ABI of the B200-native CLOUDSC2 NL / TL / AD column physics.
+ *
+ * This is the drop-in boundary between the (unchanged) Fortran host of
+ * ecmwf-ifs/dwarf-p-cloudsc2-tl-ad and the CUDA (sm_100a) implementation.  Every entry
+ * point replaces one reference interface, cited as (file:line relative to the
+ * reference's src/ directory).  Plain C types only: pointers, ints, doubles.
+ *
+ * Conventions
+ *  - Working precision is FP64 (reference: common/module/parkind1.F90:40-44, JPRB).
+ *  - Arrays keep the reference's blocked, column-major layout: a field declared
+ *    X(NPROMA,KLEV,NBLOCKS) in Fortran is a double* to its first element; element
+ *    (jl,jk,ibl) (0-based) lives at  ((ibl*KLEV + jk)*NPROMA + jl).  Half-level fields
+ *    (PAPH, PFPLSL, PFPLSN, PFHPSL, PFHPSN) have KLEV+1 levels.
+ *    PCLV is (NPROMA,KLEV,NCLV=5,NBLOCKS); the tendency states are the AOSOA buffers
+ *    B_CML / B_LOC (NPROMA,KLEV,3+NCLV=8,NBLOCKS) with slabs T=0, A=1, Q=2, CLD=3..7
+ *    (common/module/cloudsc2_array_state_mod.F90:129-151).
+ *  - NBLOCKS = ceil(NGPTOT/NPROMA); columns ICEND+1..NPROMA of the last block are never
+ *    computed (cloudsc2_nl/cloudsc_driver_mod.F90:82-84).
+ *  - Every function returns 0 on success, non-zero on error; the text of the last error
+ *    is returned by cloudsc2_gpu_last_error().  There is NO CPU fallback: without a
+ *    CUDA device every compute entry point fails.  (Reference error convention:
+ *    ABOR1 -> abort(), common/module/abor1.F90:10-14; the Fortran shim maps non-zero to ABOR1.)
+ *  - "_dev" variants take device pointers (same layout) and enqueue on the library's
+ *    stream (or a caller stream given as void* cudaStream_t); the others take host
+ *    pointers and perform the H2D / D2H copies inside the call.
+ */
+#ifndef CLOUDSC2_B200_H
+#define CLOUDSC2_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLOUDSC2_NCLV 5      /* yoecldp.F90:86-91 : NCLV, NCLDQL=1, NCLDQI=2 (1-based) */
+#define CLOUDSC2_NSTATE 8    /* 3 + NCLV slabs of a STATE_TYPE buffer                  */
+
+/* Constants that reach the kernels.  Replaces the module variables of
+ * common/module/yomcst.F90:167-177, yoethf.F90:79-99, yoecldp.F90:242-370,
+ * yoephli.F90:79-97, yomncl.F90:26, yophnc.F90 -- read from input.h5 by the Fortran host
+ * and passed by value.  All physics constants are run-time data, never compiled in. */
+typedef struct cloudsc2_params {
+  /* YOMCST */
+  double rg, rd, rcpd, retv, rlvtt, rlstt, rlmlt, rtt;
+  /* YOETHF */
+  double r2es, r3les, r3ies, r4les, r4ies, r5les, r5ies, r5alvcp, r5alscp;
+  double ralvdcp, ralsdcp, rtwat, rtice, rtwat_rtice_r, rvtmp2;
+  /* YRECLDP */
+  double rclcrit, rkconv, rlmin, rpecons;
+  /* YREPHLI */
+  double rlptrc;
+  /* switches: YREPHLI%LPHYLIN, YRPHNC%LEVAPLS2, YRNCL%LREGCL, driver LDRAIN1D */
+  int lphylin, levapls2, lregcl, ldrain1d;
+} cloudsc2_params;
+
+/* Blocked host/device arrays of one problem; mirrors the argument list of
+ * CLOUDSC_DRIVER (cloudsc2_nl/cloudsc_driver_mod.F90:22-30), same names. */
+typedef struct cloudsc2_fields {
+  /* inputs */
+  const double *pt, *pq, *pap, *paph, *plu, *plude, *pmfu, *pmfd, *psupsat;
+  const double *pclv;   /* (NPROMA,KLEV,5,NBLOCKS), species 0=QL 1=QI used           */
+  const double *b_cml;  /* TENDENCY_CML buffer (NPROMA,KLEV,8,NBLOCKS)               */
+  /* outputs */
+  double *b_loc;        /* TENDENCY_LOC buffer (NPROMA,KLEV,8,NBLOCKS): slabs 0,2,3,4 written, 7 zeroed */
+  double *pa;           /* cloud fraction, passed as PCLC (driver_mod.F90:105)       */
+  double *pcovptot, *pfplsl, *pfplsn, *pfhpsl, *pfhpsn;
+} cloudsc2_fields;
+
+/* The 16 increment (TL input / AD output) and 10 increment (TL output / AD input) arrays of
+ * CLOUDSC2TL / CLOUDSC2AD (cloudsc2_tl/cloudsc2tl.F90:10-24, cloudsc2_ad/cloudsc2ad.F90:10-24).
+ * All plain (NPROMA,KLEV[+1],NBLOCKS) arrays. */
+typedef struct cloudsc2_incr_in {   /* perturbations of the 16 inputs  */
+  double *paph, *pap, *pq, *pqs, *pt, *pl, *pi, *plude, *plu, *pmfu, *pmfd;
+  double *gtent, *gtenq, *gtenl, *gteni, *psupsat;
+} cloudsc2_incr_in;
+typedef struct cloudsc2_incr_out {  /* perturbations of the 10 outputs */
+  double *tent, *tenq, *tenl, *teni, *pclc, *pfplsl, *pfplsn, *pfhpsl, *pfhpsn, *pcovptot;
+} cloudsc2_incr_out;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+
+/* Select CUDA device `device`, upload the constants and the CETA(KLEV) vector
+ * (cloudsc2_nl/dwarf_cloudsc.F90:100-102; YRECLD%CETA) and create the stream.
+ * Replaces the implicit module state used by CLOUDSC2/TL/AD (cloudsc2.F90:104-111,222-224). */
+int cloudsc2_gpu_init(const cloudsc2_params *params, int klev, const double *ceta, int device);
+int cloudsc2_gpu_finalize(void);
+const char *cloudsc2_gpu_last_error(void);
+/* 1 if a usable CUDA device is visible, else 0 (never falls back to CPU). */
+int cloudsc2_gpu_available(void);
+/* number of kernels launched by this library since init (bench.py: gpu_launches). */
+long long cloudsc2_gpu_launch_count(void);
+
+/* ---- nonlinear: replaces the block loop of CLOUDSC_DRIVER -------------------------- */
+
+/* Host-pointer entry: cloudsc2_nl/cloudsc_driver_mod.F90:82-111 (zero PCOVPTOT and
+ * TENDENCY_LOC%CLD(:,:,NCLV), SATUR, CLOUDSC2 for every block).  elapsed_kernel_s /
+ * elapsed_total_s (may be NULL) return CUDA-event times of the kernel alone and of
+ * copies+kernel. */
+int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy,
+                    const cloudsc2_fields *host, double *elapsed_kernel_s, double *elapsed_total_s);
+/* Device-pointer entry, asynchronous on `stream` (NULL = library stream).  If pqs is non-NULL
+ * it is used as PQS(NPROMA,KLEV,NBLOCKS) instead of the fused SATUR (CLOUDSC2 call-only
+ * semantics, cloudsc2.F90:10-18). */
+int cloudsc2_gpu_nl_dev(int nproma, int klev, int ngptot, double ptsphy,
+                        const cloudsc2_fields *dev, const double *pqs, void *stream);
+
+/* ---- tangent linear / adjoint on full fields ---------------------------------------- */
+
+/* CLOUDSC2TL (cloudsc2_tl/cloudsc2tl.F90:10-24) preceded by SATUR for the trajectory PQS
+ * (cloudsc_driver_tl_mod.F90:135-136).  Trajectory outputs are written to dev->b_loc, pa,
+ * fluxes as the reference does (:1079-1111); increments in `din` -> `dout`. */
+int cloudsc2_gpu_tl_dev(int nproma, int klev, int ngptot, double ptsphy,
+                        const cloudsc2_fields *dev, const cloudsc2_incr_in *din,
+                        const cloudsc2_incr_out *dout, void *stream);
+/* CLOUDSC2AD (cloudsc2_ad/cloudsc2ad.F90:10-24): input adjoints in `din` are ACCUMULATED
+ * (psupsat assigned, :1733), output adjoints in `dout` are consumed and zeroed. */
+int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy,
+                        const cloudsc2_fields *dev, const cloudsc2_incr_in *din,
+                        const cloudsc2_incr_out *dout, void *stream);
+/* Host-pointer convenience wrappers (copies inside the call). */
+int cloudsc2_gpu_tl(int nproma, int klev, int ngptot, double ptsphy,
+                    const cloudsc2_fields *host, const cloudsc2_incr_in *din,
+                    const cloudsc2_incr_out *dout);
+int cloudsc2_gpu_ad(int nproma, int klev, int ngptot, double ptsphy,
+                    const cloudsc2_fields *host, const cloudsc2_incr_in *din,
+                    const cloudsc2_incr_out *dout);
+
+/* ---- self tests: replace the block loops of CLOUDSC_DRIVER_TL / CLOUDSC_DRIVER_AD ---- */
+
+/* Taylor test (cloudsc2_tl/cloudsc_driver_tl_mod.F90:126-254): per block 1 NL + 1 TL + 10
+ * perturbed NL, ERROR_NORM (:21-31) over 10 fields, max over blocks.  znormg[10] receives the
+ * ratios BEFORE the |1-r| redefinition (:278).  ratios_blk (may be NULL) receives the
+ * per-block values ZNORM/ZCOUNT, layout [nblocks][10].  Returns 3 if a block is degenerate
+ * (ZNORM==0 or ZCOUNT==0; reference STOPs, :247-249). Host pointers. */
+int cloudsc2_gpu_tl_taylor(int nproma, int klev, int ngptot, double ptsphy,
+                           const cloudsc2_fields *host, double znormg[10], double *ratios_blk);
+int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
+                               const cloudsc2_fields *dev, double znormg[10], double *ratios_blk);
+/* Adjoint (dot-product) test (cloudsc2_ad/cloudsc_driver_ad_mod.F90:108-271): dx = 0.01 x
+ * (ZSUPSAT=0), y = TL dx, N1 = <y,y>, dx* = AD y, N2 = <dx, dx*>,
+ * N3 = |N1-N2|/eps/N2; *znormg = max N3.  norms_col (may be NULL): [ngptot][3] = N1,N2,N3. */
+int cloudsc2_gpu_ad_test(int nproma, int klev, int ngptot, double ptsphy,
+                         const cloudsc2_fields *host, double *znormg, double *norms_col);
+int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
+                             const cloudsc2_fields *dev, double *znormg, double *norms_col);
+
+/* Verdict logic of the reference drivers, host-side, pure functions.
+ * cloudsc_driver_tl_mod.F90:273-311: returns the penalty (>=0 passed iff <=5), or
+ * -13 for "err 13" (ISTART==0 or >4); -(ITEST) never used otherwise. */
+int cloudsc2_taylor_verdict(const double znormg[10], int *istart_out);
+/* cloudsc_driver_ad_mod.F90:286-294: 1 = TEST OK (znormg < 10000). */
+int cloudsc2_adjoint_verdict(double znormg);
+
+/* ---- device-side expansion (next row 8f-1) ---------------------------------------------- */
+
+/* Replicate `nlon` source columns cyclically into a blocked array, zero-padding the tail
+ * (common/module/expand_mod.F90:270-302): column g (0-based) <- source column g mod nlon.
+ * src is (nlon, nlev, ndim) column-major = the input.h5 layout; dst is
+ * (nproma, nlev, ndim, nblocks).  Both device pointers. */
+int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim,
+                            double *dst, int nproma, int ngptot, void *stream);
+
+/* ---- device memory helpers for non-torch hosts ------------------------------------------ */
+int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes);
+int cloudsc2_gpu_free(void *ptr);
+int cloudsc2_gpu_memcpy_h2d(void *dst, const void *src, unsigned long long bytes);
+int cloudsc2_gpu_memcpy_d2h(void *dst, const void *src, unsigned long long bytes);
+int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes);
+int cloudsc2_gpu_sync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUDSC2_B200_H */

@@ -1,0 +1,79 @@
+/*
+ * cloudsc2_host.h -- host-side helpers of the B200 CLOUDSC2 library (C ABI, no CUDA needed).
+ *
+ * These mirror the pieces of the reference's Fortran host that sit directly either side of the
+ * hot path: the synthetic stand-in for config-files/input.h5 (absent from the reference
+ * checkout), the 100 -> NGPTOT column expansion, the blocked-array container, and a minimal
+ * reader for the contiguous HDF5 files the reference ships.  Reference interfaces are cited
+ * as file:line relative to the reference's src/ directory.
+ */
+#ifndef CLOUDSC2_HOST_H
+#define CLOUDSC2_HOST_H
+#include "cloudsc2_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* IFS-standard constants consistent with yoethf.F90:57-69 and with config-files/reference.h5
+ * (SURVEY Appendix E).  ASSUMPTION: input.h5 is absent, these are not read from the reference.
+ * Switches are set as the NL program sets them (cloudsc2_nl/dwarf_cloudsc.F90:105-107). */
+void cloudsc2_default_params(cloudsc2_params *p);
+
+/* Un-expanded source columns in the layout of input.h5: every field is
+ * (KLON,KLEV[,NDIM]) column-major, i.e. C-order (NDIM,KLEV,KLON), KLON contiguous. */
+typedef struct cloudsc2_source {
+  int klon, klev;
+  double ptsphy;
+  double *pt, *pq, *pap, *paph /*klev+1*/, *plu, *plude, *pmfu, *pmfd, *pa, *psupsat;
+  double *pclv;          /* (KLON,KLEV,5)                                                */
+  double *tend_cml;      /* (KLON,KLEV,8): slabs T,A,Q,CLD(5) like B_CML of one block    */
+  double *ceta;          /* (KLEV) = PAP(1,JK)/PAPH(1,KLEV+1), dwarf_cloudsc.F90:100-102 */
+} cloudsc2_source;
+
+/* Allocate and fill `klon` physically plausible, all-active columns (seeded, deterministic).
+ * Stand-in for CLOUDSC2_ARRAY_STATE%LOAD's reads of input.h5
+ * (common/module/cloudsc2_array_state_mod.F90:153-203). */
+int cloudsc2_source_synth(cloudsc2_source *s, unsigned long long seed, int klon, int klev,
+                          const cloudsc2_params *p);
+void cloudsc2_source_free(cloudsc2_source *s);
+
+/* Host expansion, common/module/expand_mod.F90:270-335 (EXPAND_R2/R3): column g (0-based) of
+ * the blocked field <- source column g mod nlon; tail of last block zero.  The reference reads
+ * out of bounds when a block starts at a multiple of nlon other than nlon itself
+ * (expand_mod.F90:283); that is not replicated. */
+void cloudsc2_expand_host(const double *src, int nlon, int nlev, int ndim, double *dst,
+                          int nproma, int ngptot);
+
+/* Blocked arrays of one problem, owned by the library (malloc).  Mirrors the allocatable
+ * members of CLOUDSC2_ARRAY_STATE (cloudsc2_array_state_mod.F90:28-60). */
+typedef struct cloudsc2_state {
+  int nproma, klev, ngptot, nblocks;
+  cloudsc2_fields f;     /* all pointers owned by this struct */
+} cloudsc2_state;
+/* LOAD: allocate, expand inputs from `s`, zero outputs (FIELD_INIT :100-127; B_LOC is
+ * allocated but not zeroed by the reference :129-151 -- we zero it for determinism). */
+int cloudsc2_state_load(cloudsc2_state *st, const cloudsc2_source *s, int nproma, int ngptot);
+void cloudsc2_state_free(cloudsc2_state *st);
+int cloudsc2_nblocks(int ngptot, int nproma);
+
+/* Minimal HDF5 reader: superblock v0, contiguous little-endian f8/i4 datasets in the root group
+ * -- what config-files/reference.h5 (and the missing input.h5) use.  Replaces the calls the
+ * host makes into libhdf5 (common/module/hdf5_file_mod.F90:135-164) for these files only.
+ * Returns number of elements read into out (up to max_elems), <0 on error / not found. */
+long long cloudsc2_h5_read_f8(const char *path, const char *dataset, double *out,
+                              long long max_elems, int dims_out[4], int *ndims_out);
+long long cloudsc2_h5_read_i4(const char *path, const char *dataset, int *out,
+                              long long max_elems);
+
+/* Validation statistics of one field, common/module/validate_mod.F90:165-211,263-296
+ * (L1 sense): out[0]=min(field) out[1]=max(field) out[2]=max|err| out[3]=sum|err|
+ * out[4]=sum|ref| ; relative error % as the reference prints it = see cloudsc2_error_rel. */
+void cloudsc2_validate_host(const double *ref, const double *field, int nproma, int nlev,
+                            int ngptot, double out[5]);
+double cloudsc2_error_rel(const double stats[5], int *flag_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
