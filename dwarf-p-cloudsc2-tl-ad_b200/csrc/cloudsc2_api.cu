@@ -1,0 +1,692 @@
+// cloudsc2_api.cu -- the C ABI of include/cloudsc2_b200.h: context, memory plumbing, and the
+// host-side orchestration that replaces the reference's three block-loop drivers.
+// No CPU fallback anywhere: every compute entry point fails if CUDA is not usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "cloudsc2_launch.h"
+
+namespace {
+
+char g_err[1024] = "";
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(100 + (int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(100 + (int)e, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  double *d() const { return static_cast<double *>(p); }
+};
+
+constexpr int kStreams = 3;
+
+struct Ctx {
+  bool init = false;
+  int device = 0;
+  cloudsc2_params prm;
+  int klev = 0;
+  double ceta[CSC2_KLEV_MAX];
+  double zscalm[CSC2_KLEV_MAX];
+  int kwin0 = 0, kwin1 = -1;
+  cudaStream_t stream = nullptr;
+  cudaStream_t pipe[kStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long launches = 0;
+  DevBuf in, out, work, work2, res;   // staging for the host-pointer entry points + scratch
+};
+Ctx g;
+
+int require_init() {
+  if (!g.init) return fail(2, "cloudsc2_gpu_init has not been called");
+  return 0;
+}
+
+KConst make_kconst(double ptsphy) {
+  KConst c;
+  std::memset(&c, 0, sizeof(c));
+  const cloudsc2_params &p = g.prm;
+  c.rg = p.rg; c.rd = p.rd; c.rcpd = p.rcpd; c.retv = p.retv; c.rlvtt = p.rlvtt;
+  c.rlstt = p.rlstt; c.rlmlt = p.rlmlt; c.rtt = p.rtt; c.r2es = p.r2es; c.r3les = p.r3les;
+  c.r3ies = p.r3ies; c.r4les = p.r4les; c.r4ies = p.r4ies; c.r5les = p.r5les; c.r5ies = p.r5ies;
+  c.r5alvcp = p.r5alvcp; c.r5alscp = p.r5alscp; c.ralvdcp = p.ralvdcp; c.ralsdcp = p.ralsdcp;
+  c.rtwat = p.rtwat; c.rtice = p.rtice; c.rtwat_rtice_r = p.rtwat_rtice_r; c.rvtmp2 = p.rvtmp2;
+  c.rclcrit = p.rclcrit; c.rkconv = p.rkconv; c.rlmin = p.rlmin; c.rlptrc = p.rlptrc;
+  // cloudsc2.F90:235-244 / cloudsc2tl.F90:321-333
+  c.ptsphy = ptsphy;
+  c.zckcodtl = 2.0 * p.rkconv * ptsphy;
+  c.zckcodti = 5.0 * p.rkconv * ptsphy;
+  c.zckcodtla = c.zckcodtl / 100.0;
+  c.zckcodtia = c.zckcodti / 100.0;
+  c.zcons2 = 1.0 / (ptsphy * p.rg);
+  c.zcons3 = p.rlvtt / p.rcpd;
+  c.zmeltp2 = p.rtt + 2.0;
+  c.zqtmst = 1.0 / ptsphy;
+  c.rlcrit_inv = 1.0 / (p.rclcrit * 2.0);
+  c.rcpd_inv = 1.0 / p.rcpd;
+  c.lregcl = p.lregcl;
+  c.klev = g.klev;
+  c.kwin0 = g.kwin0;
+  c.kwin1 = g.kwin1;
+  std::memcpy(c.ceta, g.ceta, sizeof(double) * g.klev);
+  std::memcpy(c.zscalm, g.zscalm, sizeof(double) * g.klev);
+  return c;
+}
+
+int check_dims(int nproma, int klev, int ngptot) {
+  if (nproma <= 0 || ngptot <= 0) return fail(3, "bad dimensions nproma=%d ngptot=%d", nproma, ngptot);
+  if (klev != g.klev) return fail(3, "klev=%d differs from the klev=%d given to cloudsc2_gpu_init", klev, g.klev);
+  return 0;
+}
+inline int nblocks_of(int ngptot, int nproma) { return ngptot / nproma + std::min(ngptot % nproma, 1); }
+
+// TrajIn / TrajOut views of a cloudsc2_fields struct of DEVICE pointers in the reference layout.
+void views_from_fields(const cloudsc2_fields &f, int nproma, int klev, TrajIn &in, TrajOut &out) {
+  const long long n2 = (long long)nproma * klev;
+  in.paph = f.paph; in.pap = f.pap; in.pq = f.pq; in.pt = f.pt;
+  in.pl = f.pclv;            // PCLV(:,:,NCLDQL,IBL)
+  in.pi = f.pclv + n2;       // PCLV(:,:,NCLDQI,IBL)
+  in.plude = f.plude; in.plu = f.plu; in.pmfu = f.pmfu; in.pmfd = f.pmfd;
+  in.gt = f.b_cml;           // TENDENCY_CML%T
+  in.gq = f.b_cml + 2 * n2;  // %Q
+  in.gl = f.b_cml + 3 * n2;  // %CLD(:,:,NCLDQL)
+  in.gi = f.b_cml + 4 * n2;  // %CLD(:,:,NCLDQI)
+  in.psupsat = f.psupsat;
+  in.pqs = nullptr;
+  in.bs_cld = CLOUDSC2_NCLV * n2;
+  in.bs_cml = CLOUDSC2_NSTATE * n2;
+  out.tent = f.b_loc; out.tenq = f.b_loc + 2 * n2; out.tenl = f.b_loc + 3 * n2;
+  out.teni = f.b_loc + 4 * n2; out.loc_last = f.b_loc + 7 * n2;
+  out.pclc = f.pa; out.pfplsl = f.pfplsl; out.pfplsn = f.pfplsn; out.pfhpsl = f.pfhpsl;
+  out.pfhpsn = f.pfhpsn; out.pcovptot = f.pcovptot;
+  out.bs_loc = CLOUDSC2_NSTATE * n2;
+}
+
+int check_fields(const cloudsc2_fields *f) {
+  if (!f) return fail(3, "fields pointer is NULL");
+  const void *ptrs[] = {f->pt, f->pq, f->pap, f->paph, f->plu, f->plude, f->pmfu, f->pmfd, f->psupsat,
+                        f->pclv, f->b_cml, f->b_loc, f->pa, f->pcovptot, f->pfplsl, f->pfplsn,
+                        f->pfhpsl, f->pfhpsn};
+  for (const void *p : ptrs)
+    if (!p) return fail(3, "a field pointer in cloudsc2_fields is NULL");
+  return 0;
+}
+
+// Device copy of a whole problem in the reference layout (used by the host-pointer wrappers of
+// the TL / AD / test entry points, which are correctness paths, not throughput paths).
+struct DevProblem {
+  cloudsc2_fields f;
+  size_t n2b, n2hb;   // doubles per plain array / per half-level array
+};
+int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int nblocks, DevProblem &dp) {
+  const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
+  dp.n2b = n2 * nblocks;
+  dp.n2hb = n2h * nblocks;
+  const size_t in_d = 8 * dp.n2b + dp.n2hb + CLOUDSC2_NCLV * dp.n2b + CLOUDSC2_NSTATE * dp.n2b;
+  const size_t out_d = CLOUDSC2_NSTATE * dp.n2b + 2 * dp.n2b + 4 * dp.n2hb;
+  if (int rc = g.in.reserve(in_d * sizeof(double))) return rc;
+  if (int rc = g.out.reserve(out_d * sizeof(double))) return rc;
+  double *p = g.in.d();
+  auto up = [&](const double *src, size_t n, const double *&dst) -> cudaError_t {
+    dst = p;
+    cudaError_t e = cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+    p += n;
+    return e;
+  };
+  CK(up(h->pt, dp.n2b, dp.f.pt)); CK(up(h->pq, dp.n2b, dp.f.pq)); CK(up(h->pap, dp.n2b, dp.f.pap));
+  CK(up(h->paph, dp.n2hb, dp.f.paph)); CK(up(h->plu, dp.n2b, dp.f.plu));
+  CK(up(h->plude, dp.n2b, dp.f.plude)); CK(up(h->pmfu, dp.n2b, dp.f.pmfu));
+  CK(up(h->pmfd, dp.n2b, dp.f.pmfd)); CK(up(h->psupsat, dp.n2b, dp.f.psupsat));
+  CK(up(h->pclv, CLOUDSC2_NCLV * dp.n2b, dp.f.pclv));
+  CK(up(h->b_cml, CLOUDSC2_NSTATE * dp.n2b, dp.f.b_cml));
+  double *q = g.out.d();
+  dp.f.b_loc = q; q += CLOUDSC2_NSTATE * dp.n2b;
+  dp.f.pa = q; q += dp.n2b;
+  dp.f.pcovptot = q; q += dp.n2b;
+  dp.f.pfplsl = q; q += dp.n2hb; dp.f.pfplsn = q; q += dp.n2hb;
+  dp.f.pfhpsl = q; q += dp.n2hb; dp.f.pfhpsn = q; q += dp.n2hb;
+  // outputs start from the caller's values (tail columns and untouched slabs keep them)
+  CK(cudaMemcpyAsync(dp.f.b_loc, h->b_loc, CLOUDSC2_NSTATE * dp.n2b * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(dp.f.pa, h->pa, dp.n2b * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(dp.f.pcovptot, h->pcovptot, dp.n2b * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(dp.f.pfplsl, h->pfplsl, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(dp.f.pfplsn, h->pfplsn, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(dp.f.pfhpsl, h->pfhpsl, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(dp.f.pfhpsn, h->pfhpsn, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  return 0;
+}
+int download_outputs(const cloudsc2_fields *h, const DevProblem &dp) {
+  CK(cudaMemcpyAsync(h->b_loc, dp.f.b_loc, CLOUDSC2_NSTATE * dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(h->pa, dp.f.pa, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(h->pcovptot, dp.f.pcovptot, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(h->pfplsl, dp.f.pfplsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(h->pfplsn, dp.f.pfplsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(h->pfhpsl, dp.f.pfhpsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(h->pfhpsn, dp.f.pfhpsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+inline long long pad_cols(long long n) { return (n + 127) / 128 * 128; }
+
+}  // namespace
+
+extern "C" {
+
+const char *cloudsc2_gpu_last_error(void) { return g_err; }
+
+int cloudsc2_gpu_available(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0 ? 1 : 0;
+}
+
+long long cloudsc2_gpu_launch_count(void) { return g.launches; }
+
+int cloudsc2_gpu_init(const cloudsc2_params *params, int klev, const double *ceta, int device) {
+  if (!params || !ceta) return fail(3, "cloudsc2_gpu_init: NULL argument");
+  if (klev < 2 || klev > CSC2_KLEV_MAX) return fail(3, "klev=%d outside [2,%d]", klev, CSC2_KLEV_MAX);
+  // Only the configuration the three dwarf programs run is implemented on the device
+  // (cloudsc2_{nl,tl,ad}/dwarf_cloudsc.F90:105-107; LDRAIN1D = .FALSE. in every driver).
+  if (!params->lphylin) return fail(4, "LPHYLIN=.FALSE. is not supported (the dwarf forces .TRUE.)");
+  if (params->levapls2 || params->ldrain1d)
+    return fail(4, "LEVAPLS2/LDRAIN1D=.TRUE. (precipitation evaporation) is not supported");
+  if (!cloudsc2_gpu_available()) return fail(5, "no CUDA device available (there is no CPU fallback)");
+  if (g.init) cloudsc2_gpu_finalize();
+  CK(cudaSetDevice(device));
+  g.device = device;
+  g.prm = *params;
+  g.klev = klev;
+  std::memcpy(g.ceta, ceta, sizeof(double) * klev);
+  g.kwin0 = 0; g.kwin1 = -1;
+  bool any = false;
+  for (int jk = 0; jk < klev - 1; ++jk) {        // DO JK=1,KLEV-1 (cloudsc2.F90:318)
+    if (ceta[jk] > 0.1 && ceta[jk] < 0.4) {
+      if (!any) g.kwin0 = jk;
+      g.kwin1 = jk;
+      any = true;
+    }
+  }
+  for (int jk = 0; jk < klev; ++jk)              // cloudsc2.F90:266, ZSCAL = 0.9 (:172)
+    g.zscalm[jk] = 0.9 * std::pow(std::max(ceta[jk] - 0.2, 1.e-12), 0.2);
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < kStreams; ++i) CK(cudaStreamCreateWithFlags(&g.pipe[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&g.ev[i]));
+  g.launches = 0;
+  g.init = true;
+  return 0;
+}
+
+int cloudsc2_gpu_finalize(void) {
+  if (!g.init) return 0;
+  cudaSetDevice(g.device);
+  cudaDeviceSynchronize();
+  g.in.release(); g.out.release(); g.work.release(); g.work2.release(); g.res.release();
+  if (g.stream) cudaStreamDestroy(g.stream);
+  for (int i = 0; i < kStreams; ++i) if (g.pipe[i]) cudaStreamDestroy(g.pipe[i]);
+  for (int i = 0; i < 4; ++i) if (g.ev[i]) cudaEventDestroy(g.ev[i]);
+  g.stream = nullptr;
+  for (int i = 0; i < kStreams; ++i) g.pipe[i] = nullptr;
+  for (int i = 0; i < 4; ++i) g.ev[i] = nullptr;
+  g.init = false;
+  return 0;
+}
+
+/* ---- memory helpers ------------------------------------------------------------------ */
+int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes) {
+  if (int rc = require_init()) return rc;
+  CK(cudaMalloc(ptr, bytes));
+  return 0;
+}
+int cloudsc2_gpu_free(void *ptr) { CK(cudaFree(ptr)); return 0; }
+int cloudsc2_gpu_memcpy_h2d(void *dst, const void *src, unsigned long long bytes) {
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+int cloudsc2_gpu_memcpy_d2h(void *dst, const void *src, unsigned long long bytes) {
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes) {
+  CK(cudaMemset(dst, value, bytes));
+  return 0;
+}
+int cloudsc2_gpu_sync(void) {
+  if (int rc = require_init()) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  for (int i = 0; i < kStreams; ++i) CK(cudaStreamSynchronize(g.pipe[i]));
+  return 0;
+}
+
+/* ---- nonlinear ----------------------------------------------------------------------- */
+
+int cloudsc2_gpu_nl_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,
+                        const double *pqs, void *stream) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(dev)) return rc;
+  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  TrajIn in; TrajOut out;
+  views_from_fields(*dev, nproma, klev, in, out);
+  in.pqs = pqs;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  CK(csc2_launch_nl(make_kconst(ptsphy), geo, in, out, s));
+  g.launches += 1;
+  return 0;
+}
+
+// Host-pointer NL: the drop-in for the block loop of CLOUDSC_DRIVER.  Blocks are processed in
+// chunks on three streams so that H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1
+// overlap (PCIe is full duplex); only the slabs the kernel touches cross the bus
+// (PCLV 2 of 5 species, B_CML 4 of 8 slabs, B_LOC 5 of 8 slabs).
+int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                    double *elapsed_kernel_s, double *elapsed_total_s) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(h)) return rc;
+  const int nblocks = nblocks_of(ngptot, nproma);
+  const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
+  const size_t D = sizeof(double);
+  // compact device layout: [8 plain | paph | cld(2) | cml(4)] and [loc(5) | pa | pcov | 4 flux]
+  const size_t in_blk = 8 * n2 + n2h + 2 * n2 + 4 * n2;
+  const size_t out_blk = 5 * n2 + 2 * n2 + 4 * n2h;
+  if (int rc = g.in.reserve(in_blk * nblocks * D)) return rc;
+  if (int rc = g.out.reserve(out_blk * nblocks * D)) return rc;
+  double *di = g.in.d(), *dout = g.out.d();
+  const size_t nb = nblocks;
+  double *d_pt = di, *d_pq = d_pt + n2 * nb, *d_pap = d_pq + n2 * nb, *d_plu = d_pap + n2 * nb,
+         *d_plude = d_plu + n2 * nb, *d_pmfu = d_plude + n2 * nb, *d_pmfd = d_pmfu + n2 * nb,
+         *d_psupsat = d_pmfd + n2 * nb, *d_paph = d_psupsat + n2 * nb, *d_cld = d_paph + n2h * nb,
+         *d_cml = d_cld + 2 * n2 * nb;
+  double *d_loc = dout, *d_pa = d_loc + 5 * n2 * nb, *d_pcov = d_pa + n2 * nb,
+         *d_fl = d_pcov + n2 * nb, *d_fn = d_fl + n2h * nb, *d_hl = d_fn + n2h * nb,
+         *d_hn = d_hl + n2h * nb;
+
+  // chunking: ~48 MB of input per chunk, at least 1 block, at most 64 chunks
+  size_t blocks_per_chunk = std::max<size_t>(1, (48u << 20) / (in_blk * D));
+  size_t nchunks = (nb + blocks_per_chunk - 1) / blocks_per_chunk;
+  if (nchunks > 64) { nchunks = 64; blocks_per_chunk = (nb + 63) / 64; nchunks = (nb + blocks_per_chunk - 1) / blocks_per_chunk; }
+  const KConst kc = make_kconst(ptsphy);
+
+  std::vector<cudaEvent_t> k0(nchunks), k1(nchunks);
+  for (size_t i = 0; i < nchunks; ++i) { CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i])); }
+  CK(cudaEventRecord(g.ev[0], g.stream));
+  for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(g.pipe[i], g.ev[0], 0));
+
+  for (size_t ic = 0; ic < nchunks; ++ic) {
+    cudaStream_t s = g.pipe[ic % kStreams];
+    const size_t b0 = ic * blocks_per_chunk, cb = std::min(blocks_per_chunk, nb - b0);
+    auto h2d = [&](double *dst, const double *src, size_t per_blk) {
+      return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyHostToDevice, s);
+    };
+    CK(h2d(d_pt, h->pt, n2)); CK(h2d(d_pq, h->pq, n2)); CK(h2d(d_pap, h->pap, n2));
+    CK(h2d(d_plu, h->plu, n2)); CK(h2d(d_plude, h->plude, n2)); CK(h2d(d_pmfu, h->pmfu, n2));
+    CK(h2d(d_pmfd, h->pmfd, n2)); CK(h2d(d_psupsat, h->psupsat, n2)); CK(h2d(d_paph, h->paph, n2h));
+    // PCLV species QL,QI (slabs 0-1 of 5)
+    CK(cudaMemcpy2DAsync(d_cld + 2 * n2 * b0, 2 * n2 * D, h->pclv + 5 * n2 * b0, 5 * n2 * D, 2 * n2 * D, cb, cudaMemcpyHostToDevice, s));
+    // B_CML slab T (0) and slabs Q,QL,QI (2-4) of 8
+    CK(cudaMemcpy2DAsync(d_cml + 4 * n2 * b0, 4 * n2 * D, h->b_cml + 8 * n2 * b0, 8 * n2 * D, n2 * D, cb, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpy2DAsync(d_cml + 4 * n2 * b0 + n2, 4 * n2 * D, h->b_cml + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, 3 * n2 * D, cb, cudaMemcpyHostToDevice, s));
+
+    Geom geo{nproma, klev, (int)std::min<long long>((long long)cb * nproma, (long long)ngptot - (long long)b0 * nproma), (int)cb};
+    TrajIn in;
+    in.paph = d_paph + n2h * b0; in.pap = d_pap + n2 * b0; in.pq = d_pq + n2 * b0; in.pt = d_pt + n2 * b0;
+    in.pl = d_cld + 2 * n2 * b0; in.pi = in.pl + n2; in.plude = d_plude + n2 * b0; in.plu = d_plu + n2 * b0;
+    in.pmfu = d_pmfu + n2 * b0; in.pmfd = d_pmfd + n2 * b0;
+    in.gt = d_cml + 4 * n2 * b0; in.gq = in.gt + n2; in.gl = in.gt + 2 * n2; in.gi = in.gt + 3 * n2;
+    in.psupsat = d_psupsat + n2 * b0; in.pqs = nullptr; in.bs_cld = 2 * n2; in.bs_cml = 4 * n2;
+    TrajOut out;
+    out.tent = d_loc + 5 * n2 * b0; out.tenq = out.tent + n2; out.tenl = out.tent + 2 * n2;
+    out.teni = out.tent + 3 * n2; out.loc_last = out.tent + 4 * n2; out.bs_loc = 5 * n2;
+    out.pclc = d_pa + n2 * b0; out.pcovptot = d_pcov + n2 * b0; out.pfplsl = d_fl + n2h * b0;
+    out.pfplsn = d_fn + n2h * b0; out.pfhpsl = d_hl + n2h * b0; out.pfhpsn = d_hn + n2h * b0;
+    if (geo.ngptot < (int)(cb * nproma)) {
+      // the last block has padding columns whose outputs must keep the caller's values
+      const size_t lb = b0 + cb - 1;
+      CK(cudaMemcpy2DAsync(d_loc + 5 * n2 * lb, n2 * D, h->b_loc + 8 * n2 * lb, n2 * D, n2 * D, 1, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_loc + 5 * n2 * lb + n2, h->b_loc + 8 * n2 * lb + 2 * n2, 3 * n2 * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_pa + n2 * lb, h->pa + n2 * lb, n2 * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_fl + n2h * lb, h->pfplsl + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_fn + n2h * lb, h->pfplsn + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_hl + n2h * lb, h->pfhpsl + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_hn + n2h * lb, h->pfhpsn + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaEventRecord(k0[ic], s));
+    CK(csc2_launch_nl(kc, geo, in, out, s));
+    CK(cudaEventRecord(k1[ic], s));
+    g.launches += 1;
+
+    auto d2h = [&](double *dst, const double *src, size_t per_blk) {
+      return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyDeviceToHost, s);
+    };
+    // B_LOC slabs T (0), Q,QL,QI (2-4) and the zeroed CLD(:,:,NCLV) (7)
+    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0, 8 * n2 * D, d_loc + 5 * n2 * b0, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + n2, 5 * n2 * D, 3 * n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 7 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + 4 * n2, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    CK(d2h(h->pa, d_pa, n2)); CK(d2h(h->pcovptot, d_pcov, n2));
+    CK(d2h(h->pfplsl, d_fl, n2h)); CK(d2h(h->pfplsn, d_fn, n2h));
+    CK(d2h(h->pfhpsl, d_hl, n2h)); CK(d2h(h->pfhpsn, d_hn, n2h));
+  }
+  for (int i = 0; i < kStreams; ++i) {
+    CK(cudaEventRecord(g.ev[2], g.pipe[i]));
+    CK(cudaStreamWaitEvent(g.stream, g.ev[2], 0));
+  }
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  CK(cudaEventSynchronize(g.ev[1]));
+  float ms = 0.f, kms = 0.f;
+  CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+  for (size_t i = 0; i < nchunks; ++i) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, k0[i], k1[i]));
+    kms += t;
+    cudaEventDestroy(k0[i]);
+    cudaEventDestroy(k1[i]);
+  }
+  if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
+  if (elapsed_kernel_s) *elapsed_kernel_s = kms * 1e-3;
+  return 0;
+}
+
+/* ---- tangent linear / adjoint on full fields ----------------------------------------- */
+
+static void inc_views(const cloudsc2_incr_in *a, const cloudsc2_incr_out *b, IncIn &din, IncOut &dout) {
+  din.paph = a->paph; din.pap = a->pap; din.pq = a->pq; din.pqs = a->pqs; din.pt = a->pt;
+  din.pl = a->pl; din.pi = a->pi; din.plude = a->plude; din.plu = a->plu; din.pmfu = a->pmfu;
+  din.pmfd = a->pmfd; din.gt = a->gtent; din.gq = a->gtenq; din.gl = a->gtenl; din.gi = a->gteni;
+  din.psupsat = a->psupsat;
+  dout.tent = b->tent; dout.tenq = b->tenq; dout.tenl = b->tenl; dout.teni = b->teni;
+  dout.pclc = b->pclc; dout.pfplsl = b->pfplsl; dout.pfplsn = b->pfplsn; dout.pfhpsl = b->pfhpsl;
+  dout.pfhpsn = b->pfhpsn; dout.pcovptot = b->pcovptot;
+}
+static int check_incr(const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
+  if (!a || !b) return fail(3, "increment struct pointer is NULL");
+  const void *pa[] = {a->paph, a->pap, a->pq, a->pqs, a->pt, a->pl, a->pi, a->plude, a->plu, a->pmfu,
+                      a->pmfd, a->gtent, a->gtenq, a->gtenl, a->gteni, a->psupsat};
+  const void *pb[] = {b->tent, b->tenq, b->tenl, b->teni, b->pclc, b->pfplsl, b->pfplsn, b->pfhpsl,
+                      b->pfhpsn, b->pcovptot};
+  for (const void *p : pa) if (!p) return fail(3, "a pointer in cloudsc2_incr_in is NULL");
+  for (const void *p : pb) if (!p) return fail(3, "a pointer in cloudsc2_incr_out is NULL");
+  return 0;
+}
+
+int cloudsc2_gpu_tl_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,
+                        const cloudsc2_incr_in *din_, const cloudsc2_incr_out *dout_, void *stream) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(dev)) return rc;
+  if (int rc = check_incr(din_, dout_)) return rc;
+  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  TrajIn in; TrajOut out; IncIn din; IncOut dout;
+  views_from_fields(*dev, nproma, klev, in, out);
+  out.loc_last = nullptr;
+  inc_views(din_, dout_, din, dout);
+  TLOpts opt{0.0, 0, nullptr, nullptr, 0};
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  CK(csc2_launch_tl(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
+  g.launches += 1;
+  return 0;
+}
+
+int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,
+                        const cloudsc2_incr_in *din_, const cloudsc2_incr_out *dout_, void *stream) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(dev)) return rc;
+  if (int rc = check_incr(din_, dout_)) return rc;
+  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  TrajIn in; TrajOut out; IncIn din; IncOut dout;
+  views_from_fields(*dev, nproma, klev, in, out);
+  out.loc_last = nullptr;
+  inc_views(din_, dout_, din, dout);
+  const long long ncp = pad_cols((long long)geo.nblocks * nproma);
+  if (int rc = g.work.reserve((size_t)2 * klev * ncp * sizeof(double))) return rc;
+  ADOpts opt{0.0, 0, nullptr, g.work.d(), ncp, 1};
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  CK(csc2_launch_ad(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
+  g.launches += 1;
+  return 0;
+}
+
+// Host-pointer wrappers: stage everything on the device in the reference layout.
+static int tlad_host(bool is_ad, int nproma, int klev, int ngptot, double ptsphy,
+                     const cloudsc2_fields *h, const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(h)) return rc;
+  if (int rc = check_incr(a, b)) return rc;
+  const int nblocks = nblocks_of(ngptot, nproma);
+  DevProblem dp;
+  if (int rc = upload_problem(h, nproma, klev, nblocks, dp)) return rc;
+  const size_t tot = 15 * dp.n2b + dp.n2hb + 6 * dp.n2b + 4 * dp.n2hb;
+  if (int rc = g.work2.reserve(tot * sizeof(double))) return rc;
+  double *p = g.work2.d();
+  cloudsc2_incr_in da; cloudsc2_incr_out db;
+  struct Item { double **dev; double *host; size_t n; };
+  std::vector<Item> items = {
+      {&da.paph, a->paph, dp.n2hb}, {&da.pap, a->pap, dp.n2b}, {&da.pq, a->pq, dp.n2b},
+      {&da.pqs, a->pqs, dp.n2b}, {&da.pt, a->pt, dp.n2b}, {&da.pl, a->pl, dp.n2b},
+      {&da.pi, a->pi, dp.n2b}, {&da.plude, a->plude, dp.n2b}, {&da.plu, a->plu, dp.n2b},
+      {&da.pmfu, a->pmfu, dp.n2b}, {&da.pmfd, a->pmfd, dp.n2b}, {&da.gtent, a->gtent, dp.n2b},
+      {&da.gtenq, a->gtenq, dp.n2b}, {&da.gtenl, a->gtenl, dp.n2b}, {&da.gteni, a->gteni, dp.n2b},
+      {&da.psupsat, a->psupsat, dp.n2b}, {&db.tent, b->tent, dp.n2b}, {&db.tenq, b->tenq, dp.n2b},
+      {&db.tenl, b->tenl, dp.n2b}, {&db.teni, b->teni, dp.n2b}, {&db.pclc, b->pclc, dp.n2b},
+      {&db.pcovptot, b->pcovptot, dp.n2b}, {&db.pfplsl, b->pfplsl, dp.n2hb},
+      {&db.pfplsn, b->pfplsn, dp.n2hb}, {&db.pfhpsl, b->pfhpsl, dp.n2hb},
+      {&db.pfhpsn, b->pfhpsn, dp.n2hb}};
+  for (auto &it : items) {
+    *it.dev = p;
+    CK(cudaMemcpyAsync(p, it.host, it.n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    p += it.n;
+  }
+  int rc = is_ad ? cloudsc2_gpu_ad_dev(nproma, klev, ngptot, ptsphy, &dp.f, &da, &db, nullptr)
+                 : cloudsc2_gpu_tl_dev(nproma, klev, ngptot, ptsphy, &dp.f, &da, &db, nullptr);
+  if (rc) return rc;
+  for (auto &it : items)
+    CK(cudaMemcpyAsync(it.host, *it.dev, it.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  return download_outputs(h, dp);
+}
+int cloudsc2_gpu_tl(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                    const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
+  return tlad_host(false, nproma, klev, ngptot, ptsphy, h, a, b);
+}
+int cloudsc2_gpu_ad(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                    const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
+  return tlad_host(true, nproma, klev, ngptot, ptsphy, h, a, b);
+}
+
+/* ---- Taylor test ----------------------------------------------------------------------- */
+
+int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
+                               const cloudsc2_fields *dev, double znormg[10], double *ratios_blk) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(dev)) return rc;
+  if (!znormg) return fail(3, "znormg is NULL");
+  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  const long long ncp = pad_cols((long long)geo.nblocks * nproma);
+  // scratch: tlsum[10][ncp] | diffsum[10][10][ncp]
+  if (int rc = g.work.reserve((size_t)110 * ncp * sizeof(double))) return rc;
+  // results: znormg[10] | degenerate flag | ratios[nblocks][10]
+  if (int rc = g.res.reserve((size_t)(16 + 10 * (size_t)geo.nblocks) * sizeof(double))) return rc;
+  double *tlsum = g.work.d(), *diffsum = tlsum + 10 * ncp;
+  double *d_z = g.res.d();
+  int *d_deg = reinterpret_cast<int *>(d_z + 10);
+  double *d_rat = d_z + 16;
+  const KConst kc = make_kconst(ptsphy);
+  TrajIn in; TrajOut out;
+  views_from_fields(*dev, nproma, klev, in, out);
+  cudaStream_t s = g.stream;
+  // baseline NL (cloudsc_driver_tl_mod.F90:135-151)
+  CK(csc2_launch_nl(kc, geo, in, out, s));
+  // TL with dx = 0.01 x (:156-194); re-emits the trajectory outputs like the reference
+  TrajOut out_tl = out;
+  out_tl.loc_last = nullptr;
+  IncIn din{}; IncOut dout{};
+  TLOpts topt{0.01, 0, tlsum, nullptr, ncp};
+  CK(csc2_launch_tl(kc, geo, in, out_tl, din, dout, topt, s));
+  // 10 perturbed NL sweeps (:197-230) + sums of F - F5
+  CK(csc2_launch_taylor_nl(kc, geo, in, out, diffsum, ncp, s));
+  // ERROR_NORM and max over blocks (:233-252)
+  CK(csc2_launch_taylor_finalize(geo, tlsum, diffsum, ncp, d_rat, d_z, d_deg, s));
+  g.launches += 4;
+  double hz[16];
+  CK(cudaMemcpyAsync(hz, d_z, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (ratios_blk)
+    CK(cudaMemcpyAsync(ratios_blk, d_rat, (size_t)10 * geo.nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int i = 0; i < 10; ++i) znormg[i] = hz[i];
+  int deg;
+  std::memcpy(&deg, &hz[10], sizeof(int));
+  if (deg) return fail(3, "TL is totally wrong: %d block(s) with ZNORM==0 or ZCOUNT==0 (cloudsc_driver_tl_mod.F90:247)", deg);
+  return 0;
+}
+
+int cloudsc2_gpu_tl_taylor(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                           double znormg[10], double *ratios_blk) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(h)) return rc;
+  DevProblem dp;
+  if (int rc = upload_problem(h, nproma, klev, nblocks_of(ngptot, nproma), dp)) return rc;
+  int rc = cloudsc2_gpu_tl_taylor_dev(nproma, klev, ngptot, ptsphy, &dp.f, znormg, ratios_blk);
+  int rc2 = download_outputs(h, dp);
+  return rc ? rc : rc2;
+}
+
+/* ---- adjoint test ------------------------------------------------------------------------ */
+
+int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
+                             const cloudsc2_fields *dev, double *znormg, double *norms_col) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(dev)) return rc;
+  if (!znormg) return fail(3, "znormg is NULL");
+  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  const size_t n2b = (size_t)nproma * klev * geo.nblocks, n2hb = (size_t)nproma * (klev + 1) * geo.nblocks;
+  const long long ncp = pad_cols((long long)geo.nblocks * nproma);
+  // scratch: y (6 n2b + 4 n2hb) | ckpt 2*klev*ncp | n1[ncp] | n2[ncp]
+  const size_t ny = 6 * n2b + 4 * n2hb;
+  if (int rc = g.work.reserve((ny + (size_t)2 * klev * ncp + 2 * ncp) * sizeof(double))) return rc;
+  if (int rc = g.res.reserve((size_t)(16 + 3 * (size_t)ncp) * sizeof(double))) return rc;
+  double *y = g.work.d();
+  IncOut dout;
+  dout.tent = y; dout.tenq = y + n2b; dout.tenl = y + 2 * n2b; dout.teni = y + 3 * n2b;
+  dout.pclc = y + 4 * n2b; dout.pcovptot = y + 5 * n2b; dout.pfplsl = y + 6 * n2b;
+  dout.pfplsn = dout.pfplsl + n2hb; dout.pfhpsl = dout.pfplsn + n2hb; dout.pfhpsn = dout.pfhpsl + n2hb;
+  double *ckpt = y + ny, *n1 = ckpt + (size_t)2 * klev * ncp, *n2 = n1 + ncp;
+  double *d_z = g.res.d(), *d_norms = d_z + 16;
+  const KConst kc = make_kconst(ptsphy);
+  TrajIn in; TrajOut out;
+  views_from_fields(*dev, nproma, klev, in, out);
+  cudaStream_t s = g.stream;
+  // the driver zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV) of every block (:112-113)
+  CK(cudaMemsetAsync(out.pcovptot, 0, n2b * sizeof(double), s));
+  {
+    const size_t n2 = (size_t)nproma * klev;
+    CK(cudaMemset2DAsync(out.loc_last, CLOUDSC2_NSTATE * n2 * sizeof(double), 0, n2 * sizeof(double), geo.nblocks, s));
+  }
+  out.loc_last = nullptr;
+  IncIn din{};
+  // TL: y = M' (0.01 x), ZSUPSAT = 0 ; N1 = <y,y> per column (:160-195)
+  TLOpts topt{0.01, 1, nullptr, n1, ncp};
+  CK(csc2_launch_tl(kc, geo, in, out, din, dout, topt, s));
+  // AD applied to y with zero-initialised input adjoints; N2 = <0.01 x, M'^T y> (:198-256)
+  ADOpts aopt{0.01, 1, n2, ckpt, ncp, 1};
+  CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
+  CK(csc2_launch_ad_finalize(geo, n1, n2, d_norms, d_z, s));
+  g.launches += 3;
+  double hz;
+  CK(cudaMemcpyAsync(&hz, d_z, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (norms_col)
+    CK(cudaMemcpyAsync(norms_col, d_norms, (size_t)3 * ngptot * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *znormg = hz;
+  return 0;
+}
+
+int cloudsc2_gpu_ad_test(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                         double *znormg, double *norms_col) {
+  if (int rc = require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(h)) return rc;
+  DevProblem dp;
+  if (int rc = upload_problem(h, nproma, klev, nblocks_of(ngptot, nproma), dp)) return rc;
+  int rc = cloudsc2_gpu_ad_test_dev(nproma, klev, ngptot, ptsphy, &dp.f, znormg, norms_col);
+  int rc2 = download_outputs(h, dp);
+  return rc ? rc : rc2;
+}
+
+/* ---- verdicts (host, pure) ---------------------------------------------------------------- */
+
+int cloudsc2_taylor_verdict(const double znormg_in[10], int *istart_out) {
+  // cloudsc_driver_tl_mod.F90:273-311
+  double z[11];
+  int istart = 0;
+  for (int ilam = 1; ilam <= 10; ++ilam) {
+    z[ilam] = std::fabs(1.0 - znormg_in[ilam - 1]);
+    if (istart == 0 && z[ilam] < 0.5) istart = ilam;
+  }
+  if (istart_out) *istart_out = istart;
+  if (istart == 0 || istart > 4) return -13;
+  int itest = -10, inegat = 1;
+  for (int ilam = istart; ilam <= 9; ++ilam) {
+    const int itempnegat = (z[ilam + 1] / z[ilam] < 1.0) ? 1 : 0;
+    if (inegat > itempnegat) itest += 10;
+    inegat = itempnegat;
+  }
+  if (itest == -10) itest = 11;
+  double zmin = z[istart];
+  for (int ilam = istart; ilam <= 10; ++ilam) zmin = std::min(zmin, z[ilam]);
+  if (zmin > 0.00001) itest += 7;
+  if (zmin > 0.000001) itest += 5;
+  return itest;
+}
+
+int cloudsc2_adjoint_verdict(double znormg) { return znormg < 10000.0 ? 1 : 0; }
+
+/* ---- expansion ------------------------------------------------------------------------------ */
+
+int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim, double *dst, int nproma,
+                            int ngptot, void *stream) {
+  if (int rc = require_init()) return rc;
+  if (!src || !dst || nlon <= 0 || nlev <= 0 || ndim <= 0 || nproma <= 0 || ngptot <= 0)
+    return fail(3, "cloudsc2_gpu_expand_dev: bad argument");
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  CK(csc2_launch_expand(src, nlon, (long long)nlev * ndim, dst, nproma, ngptot, nblocks_of(ngptot, nproma), s));
+  g.launches += 1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// cloudsc2_launch.h -- host-callable launchers of the CUDA kernels (one per .cu file).
+#pragma once
+#include "cloudsc2_common.cuh"
+
+#define CSC2_NL_THREADS 128
+#define CSC2_TL_THREADS 128
+#define CSC2_AD_THREADS 128
+
+// Fused SATUR + CLOUDSC2 over all blocks (cloudsc2_nl_kernel.cu).
+cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                           cudaStream_t s);
+// Device-side cyclic expansion (cloudsc2_nl_kernel.cu).
+cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,
+                               int ngptot, int nblocks, cudaStream_t s);
+
+// Tangent linear (cloudsc2_tl_kernel.cu).
+//  pert_scale != 0 : increments are generated on load as pert_scale * trajectory input
+//                    (the drivers' dx = 0.01 x); `din` is then ignored.
+//  dout            : TL output fields (may hold NULL pointers when only sums are wanted)
+//  colsum          : optional [10][ncol_pad] per-column sums over levels of the 10 TL outputs
+//  colsq           : optional [ncol_pad] per-column sum of squares of the 10 TL outputs (ZNORM1)
+struct TLOpts {
+  double pert_scale;
+  int zero_psupsat_pert;   // AD driver: ZSUPSAT = 0 (cloudsc_driver_ad_mod.F90:139)
+  double *colsum;
+  double *colsq;
+  long long ncol_pad;
+};
+cudaError_t csc2_launch_tl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                           const IncIn &din, const IncOut &dout, const TLOpts &opt, cudaStream_t s);
+
+// Perturbed nonlinear runs of the Taylor test (cloudsc2_tl_kernel.cu): for ilam = 1..10 (grid.y)
+// run CLOUDSC2 on x + lambda*(0.01 x) with PQS = qsat(x) + lambda*(0.01 qsat(x)) and accumulate
+// per column sum_levels(F - F5) for the 10 outputs into diffsum[ilam][field][col].
+cudaError_t csc2_launch_taylor_nl(const KConst &c, const Geom &g, const TrajIn &in,
+                                  const TrajOut &base, double *diffsum, long long ncol_pad,
+                                  cudaStream_t s);
+// ERROR_NORM + max over blocks (cloudsc_driver_tl_mod.F90:21-31, 233-252).
+cudaError_t csc2_launch_taylor_finalize(const Geom &g, const double *tlsum, const double *diffsum,
+                                        long long ncol_pad, double *ratios_blk, double *znormg,
+                                        int *degenerate, cudaStream_t s);
+
+// Adjoint (cloudsc2_ad_kernel.cu): forward sweep storing the rain/snow flux entering every
+// level in `ckpt` ([2][klev][ncol_pad]), reverse sweep recomputing each level's trajectory.
+//  dot_scale != 0 : input adjoints are not written; instead <dot_scale * x, x*> is accumulated
+//                   per column into coldot (ZNORM2, cloudsc_driver_ad_mod.F90:240-256).
+struct ADOpts {
+  double dot_scale;
+  int zero_psupsat_pert;
+  double *coldot;
+  double *ckpt;
+  long long ncol_pad;
+  int write_traj;          // write the trajectory outputs (PTENT5...) like the reference (:842-864)
+};
+cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                           const IncIn &din, const IncOut &dout, const ADOpts &opt, cudaStream_t s);
+// ZNORM3 per column and max (cloudsc_driver_ad_mod.F90:260-267).
+cudaError_t csc2_launch_ad_finalize(const Geom &g, const double *n1, const double *n2,
+                                    double *norms_col, double *znormg, cudaStream_t s);

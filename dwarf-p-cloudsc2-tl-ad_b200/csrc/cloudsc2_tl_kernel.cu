@@ -1,0 +1,310 @@
+// cloudsc2_tl_kernel.cu -- tangent-linear kernel and the kernels of the Taylor test.
+//  k_cloudsc2_tl      : SATUR + CLOUDSC2TL for every column (cloudsc2tl.F90), increments either read
+//                       from arrays or generated on load as pert_scale * x (the drivers' 1 % rule,
+//                       cloudsc_driver_tl_mod.F90:156-171), optional in-kernel column sums / norms.
+//  k_taylor_nl        : the 10 perturbed nonlinear sweeps of the Taylor test (:197-230), one grid.y
+//                       slice per lambda, perturbation applied on load, emitting only
+//                       sum_levels(F - F5) per column and field.
+//  k_taylor_finalize  : ERROR_NORM (:21-31) per block and lambda, max over blocks (:247-252).
+#include "cloudsc2_tl.cuh"
+#include "cloudsc2_launch.h"
+
+namespace {
+
+__device__ __forceinline__ double ldin(const double *p) { return __ldg(p); }
+__device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
+
+struct ColOffsets {
+  size_t o1, oh, ocld, ocml, oloc;
+};
+__device__ __forceinline__ ColOffsets col_offsets(int ibl, int jl, int nproma, int klev,
+                                                  long long bs_cld, long long bs_cml,
+                                                  long long bs_loc) {
+  const size_t n2 = (size_t)nproma * klev;
+  ColOffsets o;
+  o.o1 = (size_t)ibl * n2 + jl;
+  o.oh = (size_t)ibl * (n2 + nproma) + jl;
+  o.ocld = (size_t)ibl * bs_cld + jl;
+  o.ocml = (size_t)ibl * bs_cml + jl;
+  o.oloc = (size_t)ibl * bs_loc + jl;
+  return o;
+}
+
+__device__ __forceinline__ LevIn load_level(const TrajIn &in, const ColOffsets &o, int jk, int klev,
+                                            int nproma) {
+  LevIn x;
+  const size_t l = (size_t)jk * nproma;
+  x.paph1 = ldin(in.paph + o.oh + l + nproma);
+  x.pap = ldin(in.pap + o.o1 + l);
+  x.pt = ldin(in.pt + o.o1 + l);
+  x.pq = ldin(in.pq + o.o1 + l);
+  x.pl = ldin(in.pl + o.ocld + l);
+  x.pi = ldin(in.pi + o.ocld + l);
+  x.plude = ldin(in.plude + o.o1 + l);
+  x.plu1 = (jk < klev - 1) ? ldin(in.plu + o.o1 + l + nproma) : 0.0;
+  x.pmfu = ldin(in.pmfu + o.o1 + l);
+  x.pmfd = ldin(in.pmfd + o.o1 + l);
+  x.gt = ldin(in.gt + o.ocml + l);
+  x.gq = ldin(in.gq + o.ocml + l);
+  x.gl = ldin(in.gl + o.ocml + l);
+  x.gi = ldin(in.gi + o.ocml + l);
+  x.psupsat = ldin(in.psupsat + o.o1 + l);
+  return x;
+}
+
+// increments from arrays (all plain (NPROMA,KLEV[+1],NBLOCKS))
+__device__ __forceinline__ LevIn load_incr(const IncIn &d, const ColOffsets &o, int jk, int klev,
+                                           int nproma, double &dpqs) {
+  LevIn x;
+  const size_t l = (size_t)jk * nproma;
+  x.paph1 = ldin(d.paph + o.oh + l + nproma);
+  x.pap = ldin(d.pap + o.o1 + l);
+  x.pt = ldin(d.pt + o.o1 + l);
+  x.pq = ldin(d.pq + o.o1 + l);
+  x.pl = ldin(d.pl + o.o1 + l);
+  x.pi = ldin(d.pi + o.o1 + l);
+  x.plude = ldin(d.plude + o.o1 + l);
+  x.plu1 = (jk < klev - 1) ? ldin(d.plu + o.o1 + l + nproma) : 0.0;
+  x.pmfu = ldin(d.pmfu + o.o1 + l);
+  x.pmfd = ldin(d.pmfd + o.o1 + l);
+  x.gt = ldin(d.gt + o.o1 + l);
+  x.gq = ldin(d.gq + o.o1 + l);
+  x.gl = ldin(d.gl + o.o1 + l);
+  x.gi = ldin(d.gi + o.o1 + l);
+  x.psupsat = ldin(d.psupsat + o.o1 + l);
+  dpqs = ldin(d.pqs + o.o1 + l);
+  return x;
+}
+
+__device__ __forceinline__ LevIn scale_level(const LevIn &x, double f, bool zero_sup) {
+  LevIn d;
+  d.paph1 = x.paph1 * f; d.pap = x.pap * f; d.pt = x.pt * f; d.pq = x.pq * f; d.pl = x.pl * f;
+  d.pi = x.pi * f; d.plude = x.plude * f; d.plu1 = x.plu1 * f; d.pmfu = x.pmfu * f;
+  d.pmfd = x.pmfd * f; d.gt = x.gt * f; d.gq = x.gq * f; d.gl = x.gl * f; d.gi = x.gi * f;
+  d.psupsat = zero_sup ? 0.0 : x.psupsat * f;
+  return d;
+}
+
+template <bool ONFLY>
+__global__ void __launch_bounds__(CSC2_TL_THREADS)
+k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
+              const IncIn din, const IncOut dout, const TLOpts opt) {
+  const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ibl = gcol / g.nproma;
+  if (ibl >= g.nblocks || gcol >= g.ngptot) return;
+  const int jl = gcol - ibl * g.nproma;
+  const int klev = g.klev, nproma = g.nproma;
+  const ColOffsets o = col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
+  const bool zero_sup = opt.zero_psupsat_pert != 0;
+  const bool wr = dout.tent != nullptr;
+
+  // ZTRPAUS from the trajectory only (cloudsc2tl.F90:431-442)
+  const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
+
+  Carry st5; CarryTL st;
+  st5.paph0 = ldin(in.paph + o.oh); st5.rfl = 0.0; st5.sfl = 0.0;
+  st.paph0 = ONFLY ? st5.paph0 * opt.pert_scale : ldin(din.paph + o.oh);
+  st.rfl = 0.0; st.sfl = 0.0;
+  // top rows (cloudsc2tl.F90:419-422, :1108-1115)
+  stout(out.pfplsl + o.oh, 0.0); stout(out.pfplsn + o.oh, 0.0);
+  stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt); stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
+  if (wr) {
+    stout(dout.pfplsl + o.oh, 0.0); stout(dout.pfplsn + o.oh, 0.0);
+    stout(dout.pfhpsl + o.oh, -0.0 * c.rlvtt); stout(dout.pfhpsn + o.oh, -0.0 * c.rlstt);
+  }
+  double s_t = 0, s_q = 0, s_l = 0, s_i = 0, s_c = 0, s_fl = 0, s_fn = 0, s_hl = 0, s_hn = 0;
+  double q_t = 0, q_q = 0, q_l = 0, q_i = 0, q_c = 0, q_fl = 0, q_fn = 0, q_hl = 0, q_hn = 0;
+
+  LevIn cur = load_level(in, o, 0, klev, nproma);
+  for (int jk = 0; jk < klev; ++jk) {
+    LevIn nxt = cur;
+    if (jk + 1 < klev) nxt = load_level(in, o, jk + 1, klev, nproma);
+    const double pqs5 = in.pqs ? ldin(in.pqs + o.o1 + (size_t)jk * nproma)
+                               : satur_point(c, cur.pt, 1.0 / cur.pap);
+    LevIn dx; double dpqs;
+    if (ONFLY) {
+      dx = scale_level(cur, opt.pert_scale, zero_sup);
+      dpqs = pqs5 * opt.pert_scale;
+    } else {
+      dx = load_incr(din, o, jk, klev, nproma, dpqs);
+    }
+    LevOut y5, dy;
+    tl_level(c, crh, jk, cur, pqs5, dx, dpqs, st5, st, y5, dy);
+
+    const size_t l = (size_t)jk * nproma;
+    // trajectory outputs, re-emitted like the reference (cloudsc2tl.F90:1079-1091)
+    stout(out.tent + o.oloc + l, y5.tent); stout(out.tenq + o.oloc + l, y5.tenq);
+    stout(out.tenl + o.oloc + l, y5.tenl); stout(out.teni + o.oloc + l, y5.teni);
+    stout(out.pclc + o.o1 + l, y5.pclc);   stout(out.pcovptot + o.o1 + l, 0.0);
+    stout(out.pfplsl + o.oh + l + nproma, y5.rfln); stout(out.pfplsn + o.oh + l + nproma, y5.sfln);
+    stout(out.pfhpsl + o.oh + l + nproma, -y5.rfln * c.rlvtt);
+    stout(out.pfhpsn + o.oh + l + nproma, -y5.sfln * c.rlstt);
+    const double hl = -dy.rfln * c.rlvtt, hn = -dy.sfln * c.rlstt;
+    if (wr) {
+      stout(dout.tent + o.o1 + l, dy.tent); stout(dout.tenq + o.o1 + l, dy.tenq);
+      stout(dout.tenl + o.o1 + l, dy.tenl); stout(dout.teni + o.o1 + l, dy.teni);
+      stout(dout.pclc + o.o1 + l, dy.pclc); stout(dout.pcovptot + o.o1 + l, 0.0);
+      stout(dout.pfplsl + o.oh + l + nproma, dy.rfln); stout(dout.pfplsn + o.oh + l + nproma, dy.sfln);
+      stout(dout.pfhpsl + o.oh + l + nproma, hl); stout(dout.pfhpsn + o.oh + l + nproma, hn);
+    }
+    s_t += dy.tent; s_q += dy.tenq; s_l += dy.tenl; s_i += dy.teni; s_c += dy.pclc;
+    s_fl += dy.rfln; s_fn += dy.sfln; s_hl += hl; s_hn += hn;
+    q_t += dy.tent * dy.tent; q_q += dy.tenq * dy.tenq; q_l += dy.tenl * dy.tenl;
+    q_i += dy.teni * dy.teni; q_c += dy.pclc * dy.pclc; q_fl += dy.rfln * dy.rfln;
+    q_fn += dy.sfln * dy.sfln; q_hl += hl * hl; q_hn += hn * hn;
+    cur = nxt;
+  }
+  if (opt.colsum) {
+    double *s = opt.colsum + gcol;
+    const long long n = opt.ncol_pad;
+    s[0] = s_t; s[n] = s_q; s[2 * n] = s_l; s[3 * n] = s_i; s[4 * n] = s_c; s[5 * n] = s_fl;
+    s[6 * n] = s_fn; s[7 * n] = s_hl; s[8 * n] = s_hn; s[9 * n] = 0.0;   // PCOVPTOT' == 0
+  }
+  if (opt.colsq)   // ZNORM1, summed in the reference's field order (cloudsc_driver_ad_mod.F90:184-195)
+    opt.colsq[gcol] = q_t + q_q + q_l + q_i + q_c + q_fl + q_fn + q_hl + q_hn + 0.0;
+}
+
+struct Lambdas {
+  double v[10];
+};
+
+// x5 = x + lambda * (x * 0.01)   (cloudsc_driver_tl_mod.F90:156-171, 200-215)
+__device__ __forceinline__ double pert(double x, double lam) { return x + lam * (x * 0.01); }
+
+__global__ void __launch_bounds__(CSC2_NL_THREADS)
+k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut base,
+            const Lambdas lams, double *__restrict__ diffsum, const long long ncol_pad) {
+  const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ibl = gcol / g.nproma;
+  if (ibl >= g.nblocks || gcol >= g.ngptot) return;
+  const int jl = gcol - ibl * g.nproma;
+  const int klev = g.klev, nproma = g.nproma;
+  const int ilam = blockIdx.y;
+  const double lam = lams.v[ilam];
+  const ColOffsets o = col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, base.bs_loc);
+
+  // tropopause level of the PERTURBED state (the perturbed run is a plain CLOUDSC2 call)
+  double ztrpaus = 0.1;
+  if (c.kwin1 >= c.kwin0) {
+    auto tfg = [&](int jk) {
+      const size_t l = (size_t)jk * nproma;
+      return pert(ldin(in.pt + o.o1 + l), lam) + c.ptsphy * pert(ldin(in.gt + o.ocml + l), lam);
+    };
+    double t_hi = tfg(c.kwin0);
+    for (int jk = c.kwin0; jk <= c.kwin1; ++jk) {
+      const double t_lo = tfg(jk + 1);
+      const double e = c.ceta[jk];
+      if (e > 0.1 && e < 0.4 && t_hi > t_lo) ztrpaus = e;
+      t_hi = t_lo;
+    }
+  }
+  const CritRH crh = make_critrh(ztrpaus);
+
+  Carry st;
+  st.paph0 = pert(ldin(in.paph + o.oh), lam);
+  st.rfl = 0.0; st.sfl = 0.0;
+  double d_t = 0, d_q = 0, d_l = 0, d_i = 0, d_c = 0, d_fl = 0, d_fn = 0, d_hl = 0, d_hn = 0;
+  for (int jk = 0; jk < klev; ++jk) {
+    LevIn x = load_level(in, o, jk, klev, nproma);
+    // PQS5 = ZQSAT + lambda*(0.01*ZQSAT) with ZQSAT = SATUR of the UNPERTURBED state (:135,:204)
+    const double qs = in.pqs ? ldin(in.pqs + o.o1 + (size_t)jk * nproma)
+                             : satur_point(c, x.pt, 1.0 / x.pap);
+    const double pqs5 = pert(qs, lam);
+    x.paph1 = pert(x.paph1, lam); x.pap = pert(x.pap, lam); x.pt = pert(x.pt, lam);
+    x.pq = pert(x.pq, lam); x.pl = pert(x.pl, lam); x.pi = pert(x.pi, lam);
+    x.plude = pert(x.plude, lam); x.plu1 = pert(x.plu1, lam); x.pmfu = pert(x.pmfu, lam);
+    x.pmfd = pert(x.pmfd, lam); x.gt = pert(x.gt, lam); x.gq = pert(x.gq, lam);
+    x.gl = pert(x.gl, lam); x.gi = pert(x.gi, lam); x.psupsat = pert(x.psupsat, lam);
+    LevOut y;
+    nl_level(c, crh, jk, x, pqs5, st, y);
+    const size_t l = (size_t)jk * nproma;
+    d_t += ldin(base.tent + o.oloc + l) - y.tent;
+    d_q += ldin(base.tenq + o.oloc + l) - y.tenq;
+    d_l += ldin(base.tenl + o.oloc + l) - y.tenl;
+    d_i += ldin(base.teni + o.oloc + l) - y.teni;
+    d_c += ldin(base.pclc + o.o1 + l) - y.pclc;
+    d_fl += ldin(base.pfplsl + o.oh + l + nproma) - y.rfln;
+    d_fn += ldin(base.pfplsn + o.oh + l + nproma) - y.sfln;
+    d_hl += ldin(base.pfhpsl + o.oh + l + nproma) - (-y.rfln * c.rlvtt);
+    d_hn += ldin(base.pfhpsn + o.oh + l + nproma) - (-y.sfln * c.rlstt);
+  }
+  double *d = diffsum + (size_t)ilam * 10 * ncol_pad + gcol;
+  const long long n = ncol_pad;
+  d[0] = d_t; d[n] = d_q; d[2 * n] = d_l; d[3 * n] = d_i; d[4 * n] = d_c; d[5 * n] = d_fl;
+  d[6 * n] = d_fn; d[7 * n] = d_hl; d[8 * n] = d_hn; d[9 * n] = 0.0;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+  // valid for non-negative doubles: the IEEE bit pattern is monotone in the value
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void k_taylor_finalize(const Geom g, const Lambdas lams, const double *__restrict__ tlsum,
+                                  const double *__restrict__ diffsum, const long long ncol_pad,
+                                  double *__restrict__ ratios_blk, double *__restrict__ znormg,
+                                  int *__restrict__ degenerate) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nblocks * 10) return;
+  const int ibl = t / 10, ilam = t - ibl * 10;
+  const double lam = lams.v[ilam];
+  const int c0 = ibl * g.nproma;
+  int icend = g.ngptot - c0;
+  if (icend > g.nproma) icend = g.nproma;
+  double znorm = 0.0, zcount = 0.0;
+  for (int f = 0; f < 10; ++f) {   // T,Q,L,I,PA,PFPLSL,PFPLSN,PFHPSL,PFHPSN,PCOVPTOT (:235-244)
+    double s_tl = 0.0, s_d = 0.0;
+    const double *a = tlsum + (size_t)f * ncol_pad + c0;
+    const double *b = diffsum + ((size_t)ilam * 10 + f) * ncol_pad + c0;
+    for (int jl = 0; jl < icend; ++jl) { s_tl += a[jl]; s_d += b[jl]; }
+    const double den = s_tl * lam;
+    if (fabs(den) > 2.220446049250313e-16) {   // EPSILON(ZLAMBDA)
+      zcount += 1.0;
+      znorm += fabs(s_d / den);
+    }
+  }
+  if (znorm == 0.0 || zcount == 0.0) {
+    atomicAdd(degenerate, 1);
+    ratios_blk[(size_t)ibl * 10 + ilam] = nan("");
+  } else {
+    const double r = znorm / zcount;
+    ratios_blk[(size_t)ibl * 10 + ilam] = r;
+    atomic_max_nonneg(&znormg[ilam], r);
+  }
+}
+
+}  // namespace
+
+cudaError_t csc2_launch_tl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                           const IncIn &din, const IncOut &dout, const TLOpts &opt, cudaStream_t s) {
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  const int grid = (int)((ncol + CSC2_TL_THREADS - 1) / CSC2_TL_THREADS);
+  if (opt.pert_scale != 0.0) k_cloudsc2_tl<true><<<grid, CSC2_TL_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
+  else k_cloudsc2_tl<false><<<grid, CSC2_TL_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
+  return cudaGetLastError();
+}
+
+static Lambdas make_lambdas() {
+  Lambdas l;
+  for (int i = 1; i <= 10; ++i) l.v[i - 1] = pow(10.0, -(double)i);   // ZLAMBDA=10**(-ILAM) (:198)
+  return l;
+}
+
+cudaError_t csc2_launch_taylor_nl(const KConst &c, const Geom &g, const TrajIn &in,
+                                  const TrajOut &base, double *diffsum, long long ncol_pad,
+                                  cudaStream_t s) {
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  dim3 grid((unsigned)((ncol + CSC2_NL_THREADS - 1) / CSC2_NL_THREADS), 10, 1);
+  k_taylor_nl<<<grid, CSC2_NL_THREADS, 0, s>>>(c, g, in, base, make_lambdas(), diffsum, ncol_pad);
+  return cudaGetLastError();
+}
+
+cudaError_t csc2_launch_taylor_finalize(const Geom &g, const double *tlsum, const double *diffsum,
+                                        long long ncol_pad, double *ratios_blk, double *znormg,
+                                        int *degenerate, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(znormg, 0, 16 * sizeof(double), s);   // znormg[10] + flag
+  if (e != cudaSuccess) return e;
+  const int n = g.nblocks * 10;
+  k_taylor_finalize<<<(n + 127) / 128, 128, 0, s>>>(g, make_lambdas(), tlsum, diffsum, ncol_pad,
+                                                    ratios_blk, znormg, degenerate);
+  return cudaGetLastError();
+}

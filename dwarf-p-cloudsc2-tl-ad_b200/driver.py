@@ -1,0 +1,240 @@
+"""Host-side mirror of the reference's three drivers on top of the C ABI.
+
+    reference                                              here
+    CLOUDSC_DRIVER     (cloudsc2_nl/cloudsc_driver_mod.F90:22)     Cloudsc2.nl / nl_dev
+    CLOUDSC_DRIVER_TL  (cloudsc2_tl/cloudsc_driver_tl_mod.F90:33)  Cloudsc2.tl_taylor[_dev]
+    CLOUDSC_DRIVER_AD  (cloudsc2_ad/cloudsc_driver_ad_mod.F90:22)  Cloudsc2.ad_test[_dev]
+    CLOUDSC2TL / CLOUDSC2AD on full fields                         Cloudsc2.tl / ad [_dev]
+
+Everything computes inside libcloudsc2_b200.so (CUDA, sm_100a).  Errors follow the reference's
+convention of aborting (ABOR1): any non-zero return code raises Cloudsc2Error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .state import ArrayState, nblocks
+
+
+class Cloudsc2Error(RuntimeError):
+    pass
+
+
+def gpu_available() -> bool:
+    return bool(_abi.load_library().cloudsc2_gpu_available())
+
+
+def taylor_verdict(znormg) -> tuple[int, int]:
+    """cloudsc_driver_tl_mod.F90:273-311 -> (penalty, istart); passed iff 0 <= penalty <= 5."""
+    lib = _abi.load_library()
+    z = np.ascontiguousarray(znormg, dtype=np.float64)
+    istart = C.c_int(0)
+    pen = lib.cloudsc2_taylor_verdict(z.ctypes.data_as(_abi.c_double_p), C.byref(istart))
+    return int(pen), int(istart.value)
+
+
+def adjoint_verdict(znormg: float) -> bool:
+    """cloudsc_driver_ad_mod.F90:286-294."""
+    return bool(_abi.load_library().cloudsc2_adjoint_verdict(float(znormg)))
+
+
+INCR_IN_HALF = ("paph",)
+INCR_OUT_HALF = ("pfplsl", "pfplsn", "pfhpsl", "pfhpsn")
+
+
+def alloc_increments(nb: int, klev: int, nproma: int, fill: float = 0.0):
+    """The 16 + 10 increment arrays of CLOUDSC2TL / CLOUDSC2AD as NumPy (NB, KLEV[+1], NPROMA)."""
+    din = {n: np.full((nb, klev + (1 if n in INCR_IN_HALF else 0), nproma), fill)
+           for n in _abi.INCR_IN}
+    dout = {n: np.full((nb, klev + (1 if n in INCR_OUT_HALF else 0), nproma), fill)
+            for n in _abi.INCR_OUT}
+    return din, dout
+
+
+def _incr_structs(din: dict, dout: dict):
+    a, b = _abi.IncrIn(), _abi.IncrOut()
+    for n in _abi.INCR_IN:
+        setattr(a, n, din[n].ctypes.data if isinstance(din[n], np.ndarray) else int(din[n]))
+    for n in _abi.INCR_OUT:
+        setattr(b, n, dout[n].ctypes.data if isinstance(dout[n], np.ndarray) else int(dout[n]))
+    return a, b
+
+
+class DeviceState:
+    """Device-resident copy of an ArrayState in the reference's blocked layout (library-owned
+    cudaMalloc memory; no torch involved)."""
+
+    def __init__(self, gpu: "Cloudsc2", st: ArrayState | None = None, *, nproma=None, klev=None,
+                 ngptot=None):
+        self.gpu = gpu
+        if st is not None:
+            nproma, klev, ngptot = st.nproma, st.klev, st.ngptot
+        self.nproma, self.klev, self.ngptot = nproma, klev, ngptot
+        self.nblocks = nblocks(ngptot, nproma)
+        n2 = nproma * klev * self.nblocks
+        n2h = nproma * (klev + 1) * self.nblocks
+        self.sizes = {"pt": n2, "pq": n2, "pap": n2, "paph": n2h, "plu": n2, "plude": n2,
+                      "pmfu": n2, "pmfd": n2, "psupsat": n2, "pclv": _abi.NCLV * n2,
+                      "b_cml": _abi.NSTATE * n2, "b_loc": _abi.NSTATE * n2, "pa": n2,
+                      "pcovptot": n2, "pfplsl": n2h, "pfplsn": n2h, "pfhpsl": n2h, "pfhpsn": n2h}
+        self.ptr = {}
+        for n, cnt in self.sizes.items():
+            self.ptr[n] = gpu.malloc(cnt * 8)
+        if st is not None:
+            self.upload(st)
+
+    def upload(self, st: ArrayState, names=None):
+        for n in names or self.sizes:
+            self.gpu.h2d(self.ptr[n], st.a[n])
+
+    def download(self, st: ArrayState, names=_abi.FIELD_OUT):
+        for n in names:
+            self.gpu.d2h(st.a[n], self.ptr[n])
+
+    def zero(self, names=_abi.FIELD_OUT):
+        for n in names:
+            self.gpu.memset(self.ptr[n], 0, self.sizes[n] * 8)
+
+    def fields(self) -> _abi.Fields:
+        f = _abi.Fields()
+        for n in _abi.FIELD_IN + _abi.FIELD_OUT:
+            setattr(f, n, self.ptr[n])
+        return f
+
+    def nbytes(self) -> int:
+        return 8 * sum(self.sizes.values())
+
+    def free(self):
+        for p in self.ptr.values():
+            self.gpu.free(p)
+        self.ptr = {}
+
+
+class Cloudsc2:
+    """One initialised GPU context (cloudsc2_gpu_init ... cloudsc2_gpu_finalize)."""
+
+    def __init__(self, params: _abi.Params, klev: int, ceta, device: int = 0):
+        self.lib = _abi.load_library()
+        self.params = params
+        self.klev = int(klev)
+        ceta = np.ascontiguousarray(ceta, dtype=np.float64)
+        self._check(self.lib.cloudsc2_gpu_init(C.byref(params), self.klev,
+                                               ceta.ctypes.data_as(_abi.c_double_p), device))
+        self._open = True
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.cloudsc2_gpu_last_error().decode(errors="replace")
+            raise Cloudsc2Error(f"libcloudsc2_b200 rc={rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "_open", False):
+            self.lib.cloudsc2_gpu_finalize()
+            self._open = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def launch_count(self) -> int:
+        return int(self.lib.cloudsc2_gpu_launch_count())
+
+    def sync(self):
+        self._check(self.lib.cloudsc2_gpu_sync())
+
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.cloudsc2_gpu_malloc(C.byref(p), max(int(nbytes), 8)))
+        return int(p.value)
+
+    def free(self, ptr: int):
+        self._check(self.lib.cloudsc2_gpu_free(ptr))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.lib.cloudsc2_gpu_memcpy_h2d(dptr, arr.ctypes.data, arr.nbytes))
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        assert arr.flags.c_contiguous
+        self._check(self.lib.cloudsc2_gpu_memcpy_d2h(arr.ctypes.data, dptr, arr.nbytes))
+
+    def memset(self, dptr: int, value: int, nbytes: int):
+        self._check(self.lib.cloudsc2_gpu_memset(dptr, value, nbytes))
+
+    # -- nonlinear ----------------------------------------------------------------------------
+    def nl(self, st: ArrayState) -> tuple[float, float]:
+        """Host arrays in, host arrays out (the drop-in for CLOUDSC_DRIVER's block loop).
+        Returns (kernel seconds, total seconds incl. H2D/D2H) from CUDA events."""
+        tk, tt = C.c_double(0), C.c_double(0)
+        f = st.fields()
+        self._check(self.lib.cloudsc2_gpu_nl(st.nproma, st.klev, st.ngptot, st.ptsphy, C.byref(f),
+                                             C.byref(tk), C.byref(tt)))
+        return tk.value, tt.value
+
+    def nl_dev(self, ds: DeviceState, ptsphy: float, pqs: int | None = None, stream: int | None = None):
+        f = ds.fields()
+        self._check(self.lib.cloudsc2_gpu_nl_dev(ds.nproma, ds.klev, ds.ngptot, ptsphy, C.byref(f),
+                                                 pqs, stream))
+
+    # -- TL / AD on full fields ---------------------------------------------------------------
+    def tl(self, st: ArrayState, din: dict, dout: dict):
+        a, b = _incr_structs(din, dout)
+        f = st.fields()
+        self._check(self.lib.cloudsc2_gpu_tl(st.nproma, st.klev, st.ngptot, st.ptsphy, C.byref(f),
+                                             C.byref(a), C.byref(b)))
+
+    def ad(self, st: ArrayState, din: dict, dout: dict):
+        a, b = _incr_structs(din, dout)
+        f = st.fields()
+        self._check(self.lib.cloudsc2_gpu_ad(st.nproma, st.klev, st.ngptot, st.ptsphy, C.byref(f),
+                                             C.byref(a), C.byref(b)))
+
+    def tl_dev(self, ds: DeviceState, ptsphy: float, din: dict, dout: dict, stream: int | None = None):
+        a, b = _incr_structs(din, dout)
+        f = ds.fields()
+        self._check(self.lib.cloudsc2_gpu_tl_dev(ds.nproma, ds.klev, ds.ngptot, ptsphy, C.byref(f),
+                                                 C.byref(a), C.byref(b), stream))
+
+    def ad_dev(self, ds: DeviceState, ptsphy: float, din: dict, dout: dict, stream: int | None = None):
+        a, b = _incr_structs(din, dout)
+        f = ds.fields()
+        self._check(self.lib.cloudsc2_gpu_ad_dev(ds.nproma, ds.klev, ds.ngptot, ptsphy, C.byref(f),
+                                                 C.byref(a), C.byref(b), stream))
+
+    # -- self tests -----------------------------------------------------------------------------
+    def tl_taylor(self, st: ArrayState | DeviceState, ptsphy: float | None = None,
+                  allow_degenerate: bool = False):
+        """Taylor test -> (znormg[10] raw ratios, ratios per block [nblocks, 10])."""
+        z = np.zeros(10)
+        rb = np.zeros((st.nblocks, 10))
+        f = st.fields()
+        dev = isinstance(st, DeviceState)
+        fn = self.lib.cloudsc2_gpu_tl_taylor_dev if dev else self.lib.cloudsc2_gpu_tl_taylor
+        rc = fn(st.nproma, st.klev, st.ngptot, ptsphy if dev else st.ptsphy, C.byref(f),
+                z.ctypes.data_as(_abi.c_double_p), rb.ctypes.data_as(_abi.c_double_p))
+        if not (allow_degenerate and rc == 3):
+            self._check(rc)
+        return z, rb
+
+    def ad_test(self, st: ArrayState | DeviceState, ptsphy: float | None = None):
+        """Adjoint dot-product test -> (ZNORMG, per-column [ngptot, 3] = N1, N2, N3)."""
+        zn = C.c_double(0)
+        nc = np.zeros((st.ngptot, 3))
+        f = st.fields()
+        dev = isinstance(st, DeviceState)
+        fn = self.lib.cloudsc2_gpu_ad_test_dev if dev else self.lib.cloudsc2_gpu_ad_test
+        self._check(fn(st.nproma, st.klev, st.ngptot, ptsphy if dev else st.ptsphy, C.byref(f),
+                       C.byref(zn), nc.ctypes.data_as(_abi.c_double_p)))
+        return zn.value, nc
+
+    # -- expansion --------------------------------------------------------------------------------
+    def expand_dev(self, src_ptr: int, nlon: int, nlev: int, ndim: int, dst_ptr: int, nproma: int,
+                   ngptot: int, stream: int | None = None):
+        self._check(self.lib.cloudsc2_gpu_expand_dev(src_ptr, nlon, nlev, ndim, dst_ptr, nproma,
+                                                     ngptot, stream))

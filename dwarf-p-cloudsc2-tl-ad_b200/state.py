@@ -117,3 +117,45 @@ class ArrayState:
                 "tend_loc_l": a["b_loc"][:, 3], "tend_loc_i": a["b_loc"][:, 4],
                 "pa": a["pa"], "pfplsl": a["pfplsl"], "pfplsn": a["pfplsn"],
                 "pfhpsl": a["pfhpsl"], "pfhpsn": a["pfhpsn"], "pcovptot": a["pcovptot"]}
+
+
+def read_h5_f8(path: str, dataset: str) -> np.ndarray:
+    """Read a contiguous little-endian f8 dataset with the library's own mini HDF5 reader
+    (replaces LOAD_ARRAY, hdf5_file_mod.F90:135-164, for the files the reference ships)."""
+    lib = _abi.load_library()
+    dims = (C.c_int * 4)()
+    nd = C.c_int(0)
+    n = lib.cloudsc2_h5_read_f8(str(path).encode(), dataset.encode(), None, 0, C.byref(dims),
+                                C.byref(nd))
+    if n < 0:
+        raise KeyError(f"{dataset!r} in {path}: mini-HDF5 reader error {n}")
+    out = np.empty(int(n), dtype=np.float64)
+    lib.cloudsc2_h5_read_f8(str(path).encode(), dataset.encode(),
+                            out.ctypes.data_as(_abi.c_double_p), n, C.byref(dims), C.byref(nd))
+    return out.reshape(tuple(dims[i] for i in range(nd.value))) if nd.value else out
+
+
+def read_h5_i4(path: str, dataset: str) -> np.ndarray:
+    lib = _abi.load_library()
+    n = lib.cloudsc2_h5_read_i4(str(path).encode(), dataset.encode(), None, 0)
+    if n < 0:
+        raise KeyError(f"{dataset!r} in {path}: mini-HDF5 reader error {n}")
+    out = np.empty(int(n), dtype=np.int32)
+    lib.cloudsc2_h5_read_i4(str(path).encode(), dataset.encode(),
+                            out.ctypes.data_as(C.POINTER(C.c_int)), n)
+    return out
+
+
+def validate(ref: np.ndarray, fld: np.ndarray, ngptot: int) -> dict:
+    """validate_mod.F90:165-211 + ERROR_PRINT :263-296 for one blocked field (NB, NLEV, NPROMA)."""
+    lib = _abi.load_library()
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    fld = np.ascontiguousarray(fld, dtype=np.float64)
+    nb, nlev, nproma = fld.shape
+    out = (C.c_double * 5)()
+    lib.cloudsc2_validate_host(ref.ctypes.data_as(_abi.c_double_p),
+                               fld.ctypes.data_as(_abi.c_double_p), nproma, nlev, ngptot, out)
+    flag = C.c_int(0)
+    rel = lib.cloudsc2_error_rel(out, C.byref(flag))
+    return {"min": out[0], "max": out[1], "max_abs_err": out[2], "sum_abs_err": out[3],
+            "sum_abs_ref": out[4], "rel_err_pct": rel, "flag": bool(flag.value)}
