@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- CLOUDSC2 NL / TL / AD throughput on B200 (columns/s, KLEV = 137) against the HBM roofline.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                      (reference CPU path on the host cores)
+
+One "step" = one pass of the nonlinear hot path (fused SATUR + CLOUDSC2, the block loop of
+CLOUDSC_DRIVER, reference src/cloudsc2_nl/cloudsc_driver_mod.F90:82-111) over this rank's columns.
+Workload (BASELINE.json configs[3]/[4]): 100 synthetic source columns (seed 0) expanded ON THE
+DEVICE to NGPTOT = 163 840 columns per GPU (1280 blocks of NPROMA = 128; x 8 GPUs = 1 310 720
+columns, the smallest scaling size of configs[4]); blocks are sharded contiguously over the ranks,
+there is no data-path collective (weak scaling).  The same timed loop is repeated for the
+tangent-linear and adjoint kernels and reported under "modes".
+
+Printed keys (one JSON line, rank 0):
+  value / ms_per_step : NL columns/s over all ranks, inputs resident in HBM, CUDA events, max over ranks
+  e2e                 : same metric through the host-pointer C ABI call cloudsc2_gpu_nl (pinned HOST
+                        arrays in the reference layout, H2D and D2H inside the timed region)
+  roofline            : NL kernel, algorithmic bytes 27 440 B/column / launch duration
+  cpu_baseline        : the CPU oracle's CLOUDSC_DRIVER loop (C restatement of the reference; the
+                        Fortran reference cannot be built in this image) on the host cores
+  modes               : tl / ad columns/s and roofline fractions (57 072 / 84 512 B/column as written)
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+KLEV = 137
+NL_BYTES_PER_COL = (14 * KLEV + (KLEV + 1) + 6 * KLEV + 4 * (KLEV + 1)) * 8           # 27 440
+TL_BYTES_PER_COL = 2 * (2193 + 1374) * 8                                              # 57 072 (as written)
+AD_BYTES_PER_COL = 10564 * 8                                                          # 84 512 (as written)
+# what our kernels actually have to move:
+#  TL: 2056 traj in (SATUR fused) + 2193 incr in + 1374 traj out + 1374 incr out
+TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
+METRIC = "NL columns/s (KLEV=137)"
+UNIT = "columns/s"
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(pkg, ob, src, prm, nproma: int, ngptot: int, threads: int, repeats: int):
+    """The reference CPU path (oracle restatement of CLOUDSC_DRIVER) on `ngptot` columns.
+    Returns best columns/s over `repeats` (the reference times the block loop only)."""
+    st = pkg.ArrayState(src, nproma, ngptot)
+    best = float("inf")
+    os.environ.setdefault("OMP_SCHEDULE", "static")
+    for _ in range(repeats):
+        best = min(best, ob.driver_nl(prm, src.ceta, st, numomp=threads))
+    return ngptot / best, best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ngptot-per-gpu", type=int, default=163840)
+    ap.add_argument("--nproma", type=int, default=128)
+    ap.add_argument("--modes", default="nl,tl,ad")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    pkg = importlib.import_module("dwarf-p-cloudsc2-tl-ad_b200")
+    prm = pkg.default_params(lregcl=False)
+    src = pkg.synth_source(seed=0, klon=100, klev=KLEV)
+    nproma, ngp = args.nproma, args.ngptot_per_gpu
+    config = {"workload": f"CLOUDSC2 NL (SATUR+CLOUDSC2), KLEV={KLEV}, NPROMA={nproma}, "
+                          f"NGPTOT={ngp} per GPU x {args.gpus} GPU(s) = {ngp * args.gpus}, "
+                          "100 synthetic source columns (seed 0) expanded on device",
+              "klev": KLEV, "nproma": nproma, "ngptot_per_gpu": ngp, "ngptot_total": ngp * args.gpus,
+              "parallelism": f"block-sharded x{args.gpus}, no data-path collective",
+              "l2": "inputs (2.7 GB per GPU) larger than L2; no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from tests import oracle_binding as ob
+        threads = ob.max_threads()
+        sample = min(ngp, 32768)
+        t_steps = []
+        st = pkg.ArrayState(src, nproma, sample)
+        os.environ.setdefault("OMP_SCHEDULE", "static")
+        for i in range(args.warmup + args.steps):
+            t = ob.driver_nl(prm, src.ceta, st, numomp=threads)
+            if i >= args.warmup:
+                t_steps.append(t)
+        ms = 1e3 * float(np.mean(t_steps))
+        val = sample / (ms * 1e-3)
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"{sample} of the {ngp} columns per step (NPROMA={nproma}), "
+                                           "block loop only, C restatement of the reference "
+                                           "(Fortran reference not buildable here)"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available() or not pkg.gpu_available():
+        raise SystemExit("bench.py: no CUDA device -- the CLOUDSC2 B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    gpu = pkg.Cloudsc2(prm, KLEV, src.ceta, device=local_rank)
+    sh = pkg.shard_blocks(ngp * world, nproma, rank, world)
+    assert sh.ngptot == ngp
+    # a non-default torch stream: the kernels are launched on it through the ABI's `stream`
+    # argument, and torch.cuda.Event records on it (events only see torch's current stream)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    # device-resident problem: upload the 100 source columns once, expand on the device
+    ds = pkg.DeviceState(gpu, nproma=nproma, klev=KLEV, ngptot=ngp)
+    srcmap = {"pt": "pt", "pq": "pq", "pap": "pap", "paph": "paph", "plu": "plu", "plude": "plude",
+              "pmfu": "pmfu", "pmfd": "pmfd", "psupsat": "psupsat", "pa": "pa", "pclv": "pclv",
+              "b_cml": "tend_cml"}
+    for dst, s in srcmap.items():
+        a = np.ascontiguousarray(src.f[s])
+        nlev = a.shape[-2]
+        ndim = a.size // (nlev * 100)
+        p = gpu.malloc(a.nbytes)
+        gpu.h2d(p, a)
+        gpu.expand_dev(p, 100, nlev, ndim, ds.ptr[dst], nproma, ngp, stream=stream, gcol0=sh.gcol0)
+        torch.cuda.synchronize()
+        gpu.free(p)
+    ds.zero(("b_loc", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn"))
+    torch.cuda.synchronize()
+
+    peak, peak_src = load_peaks()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / steps)       # ms per step, max over ranks
+
+    modes = [m for m in args.modes.split(",") if m]
+    results = {}
+
+    # ---- NL (the headline) ---------------------------------------------------------------
+    l0 = gpu.launch_count()
+    if sampler:
+        sampler.start()
+    ms_nl = timed(lambda: gpu.nl_dev(ds, src.ptsphy, stream=stream), args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    launches = gpu.launch_count() - l0 - args.warmup
+    value = ngp * world / (ms_nl * 1e-3)
+    nl_gbs = NL_BYTES_PER_COL * ngp / (ms_nl * 1e-3) / 1e9
+    results["nl"] = {"columns_per_s": value, "ms_per_step": ms_nl, "gbs_per_gpu": nl_gbs,
+                     "frac_of_hbm": nl_gbs / peak, "bytes_per_column": NL_BYTES_PER_COL}
+
+    # ---- TL / AD ------------------------------------------------------------------------------
+    if "tl" in modes or "ad" in modes:
+        n2 = nproma * KLEV * ds.nblocks
+        n2h = nproma * (KLEV + 1) * ds.nblocks
+        din = {n: gpu.malloc(8 * (n2h if n == "paph" else n2)) for n in pkg._abi.INCR_IN}
+        dout = {n: gpu.malloc(8 * (n2h if n.startswith("pf") else n2)) for n in pkg._abi.INCR_OUT}
+        # increments dx = 0.01 x built on the device by scaling copies of the inputs
+        scale_pairs = {"paph": ("paph", 0), "pap": ("pap", 0), "pq": ("pq", 0), "pt": ("pt", 0),
+                       "plude": ("plude", 0), "plu": ("plu", 0), "pmfu": ("pmfu", 0), "pmfd": ("pmfd", 0),
+                       "psupsat": ("psupsat", 0)}
+        # torch views on library memory via __cuda_array_interface__
+        class _Wrap:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                                 "version": 2}
+        for n, (srcname, _) in scale_pairs.items():
+            cnt = n2h if n == "paph" else n2
+            torch.as_tensor(_Wrap(din[n], cnt), device=dev).copy_(
+                torch.as_tensor(_Wrap(ds.ptr[srcname], cnt), device=dev) * 0.01)
+        for n in ("pqs", "pl", "pi", "gtent", "gtenq", "gtenl", "gteni"):
+            torch.as_tensor(_Wrap(din[n], n2), device=dev).fill_(1e-7)
+        torch.cuda.synchronize()
+        if "tl" in modes:
+            ms_tl = timed(lambda: gpu.tl_dev(ds, src.ptsphy, din, dout, stream=stream),
+                          max(3, args.steps // 2), 3)
+            gbs = TL_BYTES_PER_COL * ngp / (ms_tl * 1e-3) / 1e9
+            results["tl"] = {"columns_per_s": ngp * world / (ms_tl * 1e-3), "ms_per_step": ms_tl,
+                             "gbs_per_gpu": gbs, "frac_of_hbm": gbs / peak,
+                             "bytes_per_column": TL_BYTES_PER_COL,
+                             "note": "CLOUDSC2TL as written: 16+16 arrays in, 10+10 out"}
+        if "ad" in modes:
+            try:
+                for n in pkg._abi.INCR_OUT:
+                    cnt = n2h if n.startswith("pf") else n2
+                    torch.as_tensor(_Wrap(dout[n], cnt), device=dev).fill_(1e-6)
+                torch.cuda.synchronize()
+                ms_ad = timed(lambda: gpu.ad_dev(ds, src.ptsphy, din, dout, stream=stream),
+                              max(3, args.steps // 2), 3)
+                gbs = AD_BYTES_PER_COL * ngp / (ms_ad * 1e-3) / 1e9
+                results["ad"] = {"columns_per_s": ngp * world / (ms_ad * 1e-3), "ms_per_step": ms_ad,
+                                 "gbs_per_gpu": gbs, "frac_of_hbm": gbs / peak,
+                                 "bytes_per_column": AD_BYTES_PER_COL,
+                                 "note": "CLOUDSC2AD as written: traj in/out, adjoints RMW"}
+            except pkg.Cloudsc2Error as e:
+                results["ad"] = {"error": str(e)}
+        for p in list(din.values()) + list(dout.values()):
+            gpu.free(p)
+
+    # ---- e2e through the host-pointer C ABI call ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        st = pkg.ArrayState(src, nproma, ngp, gcol0=sh.gcol0)
+        pinned = []
+        for n, a in st.a.items():
+            gpu.pin(a)
+            pinned.append(a)
+        n2 = nproma * KLEV * st.nblocks
+        n2h = nproma * (KLEV + 1) * st.nblocks
+        h2d = 8 * (8 * n2 + n2h + 2 * n2 + 4 * n2)          # 8 plain + PAPH + PCLV(QL,QI) + B_CML(T,Q,QL,QI)
+        d2h = 8 * (5 * n2 + 2 * n2 + 4 * n2h)               # B_LOC(T,Q,QL,QI,last) + PA + PCOVPTOT + 4 fluxes
+        gpu.nl(st)                                           # warm-up (allocates staging buffers)
+        gpu.nl(st)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            gpu.nl(st)                                       # synchronous: returns with results on the host
+        t_e2e = (time.perf_counter() - t0) / args.e2e_steps
+        barrier()
+        t_e2e = max_over_ranks(t_e2e)
+        e2e = {"value": ngp * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e,
+               "api": "cloudsc2_gpu_nl (host arrays, reference layout, page-locked by "
+                      "cloudsc2_gpu_host_register)",
+               "checksum_tend_t": float(np.abs(st.a["b_loc"][:, 0]).sum())}
+        for a in pinned:
+            gpu.unpin(a)
+        del st
+
+    total_launches = int(sum_over_ranks(float(launches)))
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from tests import oracle_binding as ob
+        threads = ob.max_threads()
+        sample = min(ngp, 65536)
+        cps, _ = cpu_reference_run(pkg, ob, src, prm, nproma, sample, threads, repeats=3)
+        cps4, _ = cpu_reference_run(pkg, ob, src, prm, 32, min(sample, 32768), min(4, threads), repeats=2)
+        cpu = {"value": cps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample} columns, NPROMA={nproma}, best of 3, block loop only "
+                         "(C restatement of the reference; Fortran not buildable in this image)",
+               "readme_config_4threads_nproma32": cps4}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_nl, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "impl": "b200",
+                "roofline": {"bound": "hbm", "achieved": nl_gbs, "peak": peak, "unit": "GB/s",
+                             "frac": nl_gbs / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "k_cloudsc2_nl<false>",
+                             "algorithmic_bytes_per_column": NL_BYTES_PER_COL},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
+                "modes": results}
+        print(json.dumps(line))
+    ds.free()
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -9,6 +9,8 @@ the library or a CUDA device is missing.
 from ._abi import load_library, Params, Fields, IncrIn, IncrOut, NCLV, NSTATE, LIB_PATH
 from .state import (ArrayState, SourceColumns, default_params, expand, nblocks, synth_source,
                     read_h5_f8, read_h5_i4, validate)
+from . import driver, sharding
+from .sharding import Shard, allreduce_norms, shard_blocks, sharded_adjoint, sharded_taylor
 from .driver import (Cloudsc2, Cloudsc2Error, DeviceState, adjoint_verdict, gpu_available,
                      taylor_verdict)
 
@@ -17,5 +19,6 @@ __all__ = [
     "ArrayState", "SourceColumns", "default_params", "expand", "nblocks", "synth_source",
     "read_h5_f8", "read_h5_i4", "validate",
     "Cloudsc2", "Cloudsc2Error", "DeviceState", "adjoint_verdict", "gpu_available",
-    "taylor_verdict",
+    "taylor_verdict", "driver", "sharding", "Shard", "allreduce_norms", "shard_blocks",
+    "sharded_adjoint", "sharded_taylor",
 ]

@@ -91,6 +91,9 @@ def _declare(lib):
         "cloudsc2_taylor_verdict": (i, [c_double_p, C.POINTER(i)]),
         "cloudsc2_adjoint_verdict": (i, [d]),
         "cloudsc2_gpu_expand_dev": (i, [vp, i, i, i, vp, i, i, vp]),
+        "cloudsc2_gpu_expand_shard_dev": (i, [vp, i, i, i, vp, i, i, C.c_longlong, vp]),
+        "cloudsc2_gpu_host_register": (i, [vp, C.c_ulonglong]),
+        "cloudsc2_gpu_host_unregister": (i, [vp]),
         "cloudsc2_gpu_malloc": (i, [C.POINTER(vp), C.c_ulonglong]),
         "cloudsc2_gpu_free": (i, [vp]),
         "cloudsc2_gpu_memcpy_h2d": (i, [vp, vp, C.c_ulonglong]),

@@ -283,6 +283,15 @@ int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes) {
   CK(cudaMemset(dst, value, bytes));
   return 0;
 }
+int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes) {
+  if (int rc = require_init()) return rc;
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int cloudsc2_gpu_host_unregister(void *ptr) {
+  CK(cudaHostUnregister(ptr));
+  return 0;
+}
 int cloudsc2_gpu_sync(void) {
   if (int rc = require_init()) return rc;
   CK(cudaStreamSynchronize(g.stream));
@@ -678,15 +687,19 @@ int cloudsc2_adjoint_verdict(double znormg) { return znormg < 10000.0 ? 1 : 0; }
 
 /* ---- expansion ------------------------------------------------------------------------------ */
 
-int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim, double *dst, int nproma,
-                            int ngptot, void *stream) {
+int cloudsc2_gpu_expand_shard_dev(const double *src, int nlon, int nlev, int ndim, double *dst,
+                                  int nproma, int ngptot, long long gcol0, void *stream) {
   if (int rc = require_init()) return rc;
-  if (!src || !dst || nlon <= 0 || nlev <= 0 || ndim <= 0 || nproma <= 0 || ngptot <= 0)
+  if (!src || !dst || nlon <= 0 || nlev <= 0 || ndim <= 0 || nproma <= 0 || ngptot <= 0 || gcol0 < 0)
     return fail(3, "cloudsc2_gpu_expand_dev: bad argument");
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
-  CK(csc2_launch_expand(src, nlon, (long long)nlev * ndim, dst, nproma, ngptot, nblocks_of(ngptot, nproma), s));
+  CK(csc2_launch_expand(src, nlon, (long long)nlev * ndim, dst, nproma, ngptot, nblocks_of(ngptot, nproma), gcol0, s));
   g.launches += 1;
   return 0;
+}
+int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim, double *dst, int nproma,
+                            int ngptot, void *stream) {
+  return cloudsc2_gpu_expand_shard_dev(src, nlon, nlev, ndim, dst, nproma, ngptot, 0, stream);
 }
 
 }  // extern "C"

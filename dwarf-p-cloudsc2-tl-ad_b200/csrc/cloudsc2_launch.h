@@ -11,7 +11,7 @@ cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, con
                            cudaStream_t s);
 // Device-side cyclic expansion (cloudsc2_nl_kernel.cu).
 cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,
-                               int ngptot, int nblocks, cudaStream_t s);
+                               int ngptot, int nblocks, long long gcol0, cudaStream_t s);
 
 // Tangent linear (cloudsc2_tl_kernel.cu).
 //  pert_scale != 0 : increments are generated on load as pert_scale * trajectory input

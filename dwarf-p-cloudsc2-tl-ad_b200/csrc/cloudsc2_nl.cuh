@@ -44,7 +44,8 @@ __device__ __forceinline__ void cuadjtqs_point(const KConst &c, double zqp /*1/p
     const double cor = 1.0 / (1.0 - c.retv * qsat);
     qsat *= cor;
     const double z2s = z5alcp * (r * r);
-    const double cond = (q - qsat) / (1.0 + qsat * cor * z2s);
+    const double den = 1.0 / (1.0 + qsat * cor * z2s);
+    const double cond = (q - qsat) * den;
     t += zaldcp * cond;
     q -= cond;
   }

@@ -108,10 +108,11 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   }
 }
 
-// expand_mod.F90:270-302 on the device: dst(nproma, rows, nblocks) <- src(nlon, rows), column
-// g <- g mod nlon, zero beyond ngptot.
+// expand_mod.F90:270-302 on the device: dst(nproma, rows, nblocks) <- src(nlon, rows), local
+// column j <- source column (gcol0 + j) mod nlon, zero beyond ngptot.
 __global__ void k_expand(const double *__restrict__ src, int nlon, long long rows,
-                         double *__restrict__ dst, int nproma, int ngptot, long long total) {
+                         double *__restrict__ dst, int nproma, int ngptot, long long gcol0,
+                         long long total) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; idx < total; idx += stride) {
@@ -120,7 +121,7 @@ __global__ void k_expand(const double *__restrict__ src, int nlon, long long row
     const long long r = t % rows;
     const long long b = t / rows;
     const long long gcol = b * nproma + jl;
-    dst[idx] = (gcol < ngptot) ? __ldg(src + r * nlon + (gcol % nlon)) : 0.0;
+    dst[idx] = (gcol < ngptot) ? __ldg(src + r * nlon + ((gcol0 + gcol) % nlon)) : 0.0;
   }
 }
 
@@ -136,10 +137,10 @@ cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, con
 }
 
 cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,
-                               int ngptot, int nblocks, cudaStream_t s) {
+                               int ngptot, int nblocks, long long gcol0, cudaStream_t s) {
   const long long total = (long long)nproma * rows * nblocks;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  k_expand<<<(int)blocks, 256, 0, s>>>(src, nlon, rows, dst, nproma, ngptot, total);
+  k_expand<<<(int)blocks, 256, 0, s>>>(src, nlon, rows, dst, nproma, ngptot, gcol0, total);
   return cudaGetLastError();
 }

@@ -114,15 +114,23 @@ class DeviceState:
 
 
 class Cloudsc2:
-    """One initialised GPU context (cloudsc2_gpu_init ... cloudsc2_gpu_finalize)."""
+    """One set of constants/switches bound to the library's (single, global) GPU context
+    (cloudsc2_gpu_init ... cloudsc2_gpu_finalize).  The library is not re-entrant, so
+    when several Cloudsc2 objects exist the one being used re-initialises the context with its own
+    constants first -- like the reference, where the switches are module variables set before the
+    driver call (dwarf_cloudsc.F90:105-107)."""
+
+    _owner = None     # the object whose constants are currently loaded in the library
 
     def __init__(self, params: _abi.Params, klev: int, ceta, device: int = 0):
         self.lib = _abi.load_library()
         self.params = params
         self.klev = int(klev)
-        ceta = np.ascontiguousarray(ceta, dtype=np.float64)
-        self._check(self.lib.cloudsc2_gpu_init(C.byref(params), self.klev,
-                                               ceta.ctypes.data_as(_abi.c_double_p), device))
+        self.device = int(device)
+        self.ceta = np.ascontiguousarray(ceta, dtype=np.float64)
+        self._launches = 0
+        self._open = False
+        self._bind()
         self._open = True
 
     # -- plumbing ---------------------------------------------------------------------------
@@ -131,9 +139,24 @@ class Cloudsc2:
             msg = self.lib.cloudsc2_gpu_last_error().decode(errors="replace")
             raise Cloudsc2Error(f"libcloudsc2_b200 rc={rc}: {msg}")
 
+    def _bind(self):
+        if Cloudsc2._owner is self:
+            return
+        prev = Cloudsc2._owner
+        if prev is not None:
+            prev._launches += int(self.lib.cloudsc2_gpu_launch_count())
+        Cloudsc2._owner = None
+        self._check(self.lib.cloudsc2_gpu_init(C.byref(self.params), self.klev,
+                                               self.ceta.ctypes.data_as(_abi.c_double_p),
+                                               self.device))
+        Cloudsc2._owner = self
+
     def close(self):
         if getattr(self, "_open", False):
-            self.lib.cloudsc2_gpu_finalize()
+            if Cloudsc2._owner is self:
+                self._launches += int(self.lib.cloudsc2_gpu_launch_count())
+                self.lib.cloudsc2_gpu_finalize()
+                Cloudsc2._owner = None
             self._open = False
 
     def __enter__(self):
@@ -143,12 +166,16 @@ class Cloudsc2:
         self.close()
 
     def launch_count(self) -> int:
-        return int(self.lib.cloudsc2_gpu_launch_count())
+        """Kernels launched by the library on behalf of this object."""
+        live = int(self.lib.cloudsc2_gpu_launch_count()) if Cloudsc2._owner is self else 0
+        return self._launches + live
 
     def sync(self):
+        self._bind()
         self._check(self.lib.cloudsc2_gpu_sync())
 
     def malloc(self, nbytes: int) -> int:
+        self._bind()
         p = C.c_void_p()
         self._check(self.lib.cloudsc2_gpu_malloc(C.byref(p), max(int(nbytes), 8)))
         return int(p.value)
@@ -171,6 +198,7 @@ class Cloudsc2:
     def nl(self, st: ArrayState) -> tuple[float, float]:
         """Host arrays in, host arrays out (the drop-in for CLOUDSC_DRIVER's block loop).
         Returns (kernel seconds, total seconds incl. H2D/D2H) from CUDA events."""
+        self._bind()
         tk, tt = C.c_double(0), C.c_double(0)
         f = st.fields()
         self._check(self.lib.cloudsc2_gpu_nl(st.nproma, st.klev, st.ngptot, st.ptsphy, C.byref(f),
@@ -178,30 +206,35 @@ class Cloudsc2:
         return tk.value, tt.value
 
     def nl_dev(self, ds: DeviceState, ptsphy: float, pqs: int | None = None, stream: int | None = None):
+        self._bind()
         f = ds.fields()
         self._check(self.lib.cloudsc2_gpu_nl_dev(ds.nproma, ds.klev, ds.ngptot, ptsphy, C.byref(f),
                                                  pqs, stream))
 
     # -- TL / AD on full fields ---------------------------------------------------------------
     def tl(self, st: ArrayState, din: dict, dout: dict):
+        self._bind()
         a, b = _incr_structs(din, dout)
         f = st.fields()
         self._check(self.lib.cloudsc2_gpu_tl(st.nproma, st.klev, st.ngptot, st.ptsphy, C.byref(f),
                                              C.byref(a), C.byref(b)))
 
     def ad(self, st: ArrayState, din: dict, dout: dict):
+        self._bind()
         a, b = _incr_structs(din, dout)
         f = st.fields()
         self._check(self.lib.cloudsc2_gpu_ad(st.nproma, st.klev, st.ngptot, st.ptsphy, C.byref(f),
                                              C.byref(a), C.byref(b)))
 
     def tl_dev(self, ds: DeviceState, ptsphy: float, din: dict, dout: dict, stream: int | None = None):
+        self._bind()
         a, b = _incr_structs(din, dout)
         f = ds.fields()
         self._check(self.lib.cloudsc2_gpu_tl_dev(ds.nproma, ds.klev, ds.ngptot, ptsphy, C.byref(f),
                                                  C.byref(a), C.byref(b), stream))
 
     def ad_dev(self, ds: DeviceState, ptsphy: float, din: dict, dout: dict, stream: int | None = None):
+        self._bind()
         a, b = _incr_structs(din, dout)
         f = ds.fields()
         self._check(self.lib.cloudsc2_gpu_ad_dev(ds.nproma, ds.klev, ds.ngptot, ptsphy, C.byref(f),
@@ -211,6 +244,7 @@ class Cloudsc2:
     def tl_taylor(self, st: ArrayState | DeviceState, ptsphy: float | None = None,
                   allow_degenerate: bool = False):
         """Taylor test -> (znormg[10] raw ratios, ratios per block [nblocks, 10])."""
+        self._bind()
         z = np.zeros(10)
         rb = np.zeros((st.nblocks, 10))
         f = st.fields()
@@ -224,6 +258,7 @@ class Cloudsc2:
 
     def ad_test(self, st: ArrayState | DeviceState, ptsphy: float | None = None):
         """Adjoint dot-product test -> (ZNORMG, per-column [ngptot, 3] = N1, N2, N3)."""
+        self._bind()
         zn = C.c_double(0)
         nc = np.zeros((st.ngptot, 3))
         f = st.fields()
@@ -235,6 +270,15 @@ class Cloudsc2:
 
     # -- expansion --------------------------------------------------------------------------------
     def expand_dev(self, src_ptr: int, nlon: int, nlev: int, ndim: int, dst_ptr: int, nproma: int,
-                   ngptot: int, stream: int | None = None):
-        self._check(self.lib.cloudsc2_gpu_expand_dev(src_ptr, nlon, nlev, ndim, dst_ptr, nproma,
-                                                     ngptot, stream))
+                   ngptot: int, stream: int | None = None, gcol0: int = 0):
+        """expand_mod.F90:270-302 on the device; gcol0 = first global column of this shard."""
+        self._bind()
+        self._check(self.lib.cloudsc2_gpu_expand_shard_dev(src_ptr, nlon, nlev, ndim, dst_ptr,
+                                                           nproma, ngptot, gcol0, stream))
+
+    def pin(self, arr: np.ndarray):
+        self._bind()
+        self._check(self.lib.cloudsc2_gpu_host_register(arr.ctypes.data, arr.nbytes))
+
+    def unpin(self, arr: np.ndarray):
+        self._check(self.lib.cloudsc2_gpu_host_unregister(arr.ctypes.data))

@@ -66,10 +66,15 @@ def nblocks(ngptot: int, nproma: int) -> int:
     return ngptot // nproma + min(ngptot % nproma, 1)
 
 
-def expand(src: np.ndarray, nproma: int, ngptot: int) -> np.ndarray:
-    """expand_mod.F90:270-335 through cloudsc2_expand_host.  src (..., NLEV, NLON)."""
+def expand(src: np.ndarray, nproma: int, ngptot: int, gcol0: int = 0) -> np.ndarray:
+    """expand_mod.F90:270-335 through cloudsc2_expand_host.  src (..., NLEV, NLON).
+    gcol0: first global column of a shard (the source is rotated so that local column j is
+    source column (gcol0 + j) mod NLON)."""
     lib = _abi.load_library()
-    src = np.ascontiguousarray(src, dtype=np.float64)
+    src = np.asarray(src, dtype=np.float64)
+    if gcol0:
+        src = np.roll(src, -(gcol0 % src.shape[-1]), axis=-1)
+    src = np.ascontiguousarray(src)
     nlon, nlev = src.shape[-1], src.shape[-2]
     ndim = int(np.prod(src.shape[:-2])) if src.ndim > 2 else 1
     nb = nblocks(ngptot, nproma)
@@ -83,16 +88,17 @@ def expand(src: np.ndarray, nproma: int, ngptot: int) -> np.ndarray:
 class ArrayState:
     """Blocked arrays of one problem (mirror of CLOUDSC2_ARRAY_STATE%LOAD)."""
 
-    def __init__(self, src: SourceColumns, nproma: int, ngptot: int):
+    def __init__(self, src: SourceColumns, nproma: int, ngptot: int, gcol0: int = 0):
         self.nproma, self.klev, self.ngptot = nproma, src.klev, ngptot
+        self.gcol0 = gcol0
         self.nblocks = nblocks(ngptot, nproma)
         self.ptsphy = src.ptsphy
         self.ceta = np.ascontiguousarray(src.ceta)
         a = {}
         for n in ("pt", "pq", "pap", "paph", "plu", "plude", "pmfu", "pmfd", "psupsat", "pa",
                   "pclv"):
-            a[n] = expand(src.f[n], nproma, ngptot)
-        a["b_cml"] = expand(src.f["tend_cml"], nproma, ngptot)
+            a[n] = expand(src.f[n], nproma, ngptot, gcol0)
+        a["b_cml"] = expand(src.f["tend_cml"], nproma, ngptot, gcol0)
         nb, kl = self.nblocks, self.klev
         a["b_loc"] = np.zeros((nb, _abi.NSTATE, kl, nproma))
         a["pcovptot"] = np.zeros((nb, kl, nproma))

@@ -159,6 +159,11 @@ int cloudsc2_adjoint_verdict(double znormg);
  * (nproma, nlev, ndim, nblocks).  Both device pointers. */
 int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim,
                             double *dst, int nproma, int ngptot, void *stream);
+/* Same for one shard of a block-sharded problem (cloudsc2_nl/dwarf_cloudsc.F90:65-69: each rank
+ * owns a contiguous range of the NGPTOTG global columns): local column j <- source column
+ * (gcol0 + j) mod nlon, for the ngptot local columns of this shard. */
+int cloudsc2_gpu_expand_shard_dev(const double *src, int nlon, int nlev, int ndim, double *dst,
+                                  int nproma, int ngptot, long long gcol0, void *stream);
 
 /* ---- device memory helpers for non-torch hosts ------------------------------------------ */
 int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes);
@@ -167,6 +172,11 @@ int cloudsc2_gpu_memcpy_h2d(void *dst, const void *src, unsigned long long bytes
 int cloudsc2_gpu_memcpy_d2h(void *dst, const void *src, unsigned long long bytes);
 int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes);
 int cloudsc2_gpu_sync(void);
+/* Page-lock / unlock caller-owned host arrays so that the copies inside the host-pointer entry
+ * points run at full PCIe rate and overlap with the kernel (the Fortran host keeps ownership:
+ * ALLOCATE in expand_mod.F90:110,127,148).  Optional; pageable memory works, slower. */
+int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes);
+int cloudsc2_gpu_host_unregister(void *ptr);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,9 @@ int cloudsc2_nblocks(int ngptot, int nproma);
 /* Minimal HDF5 reader: superblock v0, contiguous little-endian f8/i4 datasets in the root group
  * -- what config-files/reference.h5 (and the missing input.h5) use.  Replaces the calls the
  * host makes into libhdf5 (common/module/hdf5_file_mod.F90:135-164) for these files only.
- * Returns number of elements read into out (up to max_elems), <0 on error / not found. */
+ * Returns the number of elements of the dataset (at most max_elems of them are copied into out,
+ * which may be NULL to query the size), or <0: -1 cannot open, -2 bad format, -3 not found,
+ * -4 unsupported feature, -5 wrong element type. */
 long long cloudsc2_h5_read_f8(const char *path, const char *dataset, double *out,
                               long long max_elems, int dims_out[4], int *ndims_out);
 long long cloudsc2_h5_read_i4(const char *path, const char *dataset, int *out,

@@ -1,0 +1,225 @@
+"""CPU suite: the C-ABI library loads without a GPU, exports every symbol include/*.h declares,
+refuses to compute without a device, and the host helpers (expansion, synthetic source, mini HDF5
+reader, validation statistics, verdicts) behave like the reference's host code."""
+import ctypes as C
+import re
+import struct
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_functions():
+    names = []
+    for h in sorted((ROOT / "include").glob("*.h")):
+        txt = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        names += re.findall(r"\b(cloudsc2_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_header_symbols_are_exported(pkg):
+    lib = pkg.load_library()
+    declared = _declared_functions()
+    assert len(declared) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", str(pkg.LIB_PATH)], capture_output=True,
+                         text=True, check=True).stdout
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    missing = [n for n in declared if n not in exported]
+    assert not missing, missing
+    for n in declared:
+        assert getattr(lib, n) is not None
+    # and the ctypes table covers exactly the header
+    assert sorted(pkg._abi.EXPORTED_SYMBOLS) == declared
+
+
+def test_no_cpu_fallback(pkg, src100):
+    """Without a CUDA device every compute entry point must fail loudly (errors)."""
+    if pkg.gpu_available():
+        pytest.skip("a GPU is present; the no-device behaviour is checked on the CPU container")
+    with pytest.raises(pkg.Cloudsc2Error, match="no CUDA device"):
+        pkg.Cloudsc2(pkg.default_params(), src100.klev, src100.ceta)
+    lib = pkg.load_library()
+    f = pkg.Fields()
+    rc = lib.cloudsc2_gpu_nl(32, 137, 64, 3600.0, C.byref(f), None, None)
+    assert rc != 0 and b"init" in lib.cloudsc2_gpu_last_error()
+
+
+def test_product_package_does_not_import_the_oracle(pkg):
+    for py in (ROOT / "dwarf-p-cloudsc2-tl-ad_b200").rglob("*.py"):
+        assert "oracle" not in py.read_text().replace("no CPU fallback", ""), py
+    out = subprocess.run(["ldd", str(pkg.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "liboracle" not in out
+
+
+def test_nblocks_matches_reference_formula(pkg):
+    lib = pkg.load_library()
+    for ngptot, nproma in [(100, 1), (100, 100), (160000, 32), (100, 32), (5, 8), (64, 64), (65, 64)]:
+        want = ngptot // nproma + min(ngptot % nproma, 1)     # cloudsc_driver_mod.F90:62
+        assert lib.cloudsc2_nblocks(ngptot, nproma) == want == pkg.nblocks(ngptot, nproma)
+
+
+@pytest.mark.parametrize("nproma,ngptot", [(1, 100), (32, 100), (100, 100), (32, 250), (64, 1000), (7, 23)])
+def test_expand_is_cyclic_with_zero_tail(pkg, src100, nproma, ngptot):
+    """expand_mod.F90:270-302: column g <- source column g mod nlon, tail of last block zero."""
+    for name in ("pt", "paph", "pclv"):
+        src = src100.f[name]
+        out = pkg.expand(src, nproma, ngptot)
+        nb = pkg.nblocks(ngptot, nproma)
+        assert out.shape[0] == nb and out.shape[-1] == nproma
+        flat = np.moveaxis(out, 0, -2).reshape(src.shape[:-1] + (nb * nproma,))
+        g = np.arange(ngptot)
+        assert np.array_equal(flat[..., :ngptot], src[..., g % src.shape[-1]])
+        assert not flat[..., ngptot:].any()
+
+
+def test_synth_source_is_deterministic_and_plausible(pkg):
+    a = pkg.synth_source(seed=3, klon=12, klev=137)
+    b = pkg.synth_source(seed=3, klon=12, klev=137)
+    c = pkg.synth_source(seed=4, klon=12, klev=137)
+    for k in a.f:
+        assert np.array_equal(a.f[k], b.f[k]), k
+    assert not np.array_equal(a.f["pt"], c.f["pt"])
+    f = a.f
+    assert (np.diff(f["paph"], axis=0) > 0).all()                     # monotone half levels
+    assert ((f["pap"] > f["paph"][:-1]) & (f["pap"] < f["paph"][1:])).all()
+    assert f["pt"].min() > 150 and f["pt"].max() < 330
+    assert (f["pq"] > 0).all() and (f["pmfu"] >= 0).all() and (f["pmfd"] <= 0).all()
+    assert ((a.ceta > 0.1) & (a.ceta < 0.4)).sum() > 10                # tropopause window populated
+    assert a.ceta[-1] < 1.0 and (np.diff(a.ceta) > 0).all()
+
+
+def test_array_state_layout(pkg, src100):
+    st = pkg.ArrayState(src100, nproma=32, ngptot=100)
+    assert st.nblocks == 4
+    assert st.a["pt"].shape == (4, 137, 32) and st.a["paph"].shape == (4, 138, 32)
+    assert st.a["pclv"].shape == (4, 5, 137, 32) and st.a["b_cml"].shape == (4, 8, 137, 32)
+    # Fortran (NPROMA,KLEV,NBLOCKS) element (jl,jk,ibl) at ((ibl*KLEV+jk)*NPROMA+jl)
+    flat = st.a["pt"].ravel()
+    assert flat[(2 * 137 + 5) * 32 + 7] == src100.f["pt"][5, (2 * 32 + 7) % 100]
+
+
+def test_validate_statistics(pkg):
+    rng = np.random.default_rng(0)
+    ref = rng.standard_normal((3, 5, 8))
+    fld = ref.copy()
+    fld[1, 2, 3] += 0.5
+    s = pkg.validate(ref, fld, ngptot=20)          # last block has 4 valid columns
+    assert s["max_abs_err"] == pytest.approx(0.5)
+    valid = np.ones_like(ref, dtype=bool)
+    valid[2, :, 4:] = False
+    assert s["sum_abs_ref"] == pytest.approx(np.abs(ref[valid]).sum())
+    assert s["rel_err_pct"] == pytest.approx(100 * 0.5 / np.abs(ref[valid]).sum())
+    assert s["flag"]
+    assert not pkg.validate(ref, ref, ngptot=24)["flag"]
+
+
+def test_verdicts(pkg):
+    good = np.array([1.3, 1.02, 1.002, 1.0002, 1.00001, 1.0000002, 1.000003, 1.00004, 1.0005, 1.006])
+    pen, istart = pkg.taylor_verdict(good)
+    assert (pen, istart) == (0, 1)
+    assert pkg.taylor_verdict(np.full(10, 3.0)) == (-13, 0)            # never below 0.5 -> err 13
+    late = np.array([3.0, 3.0, 3.0, 3.0, 1.1, 1.01, 1.001, 1.0001, 1.00001, 1.000001])
+    assert pkg.taylor_verdict(late)[0] == -13                          # ISTART > 4
+    assert pkg.adjoint_verdict(9999.0) and not pkg.adjoint_verdict(10000.0)
+
+
+# ---- mini HDF5 reader -------------------------------------------------------------------------
+
+def _tiny_h5(path, datasets):
+    """Write a superblock-v0 HDF5 file with contiguous datasets in the root group, byte by byte
+    (same on-disk structures as config-files/reference.h5: TREE/HEAP/SNOD, v1 object headers)."""
+    names = sorted(datasets)
+    heap_data = b"\0" * 8
+    name_off = {}
+    for n in names:
+        name_off[n] = len(heap_data)
+        s = n.encode() + b"\0"
+        heap_data += s + b"\0" * (-len(s) % 8)
+    heap_data += b"\0" * 32
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+    pos = 96                      # after superblock (56 bytes + 40-byte root entry)
+    root_ohdr = pos; pos += 16 + 24
+    btree = pos; pos += 24 + 8 * (2 * 16 + 1) + 8 * 2 * 16
+    heap = pos; pos += 32
+    heap_data_addr = pos; pos += len(heap_data)
+    snod = pos; pos += 8 + 40 * 32
+    ohdrs, raws = {}, {}
+    for n in names:
+        ohdrs[n] = pos; pos += 16 + 256
+    for n in names:
+        raws[n] = pos; pos += datasets[n].nbytes + (-datasets[n].nbytes % 8)
+    eof = pos
+    b = bytearray(eof)
+    b[0:8] = b"\x89HDF\r\n\x1a\n"
+    b[8:16] = bytes([0, 0, 0, 0, 0, 8, 8, 0])
+    b[16:24] = struct.pack("<HHI", 16, 16, 0)
+    b[24:56] = struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+    b[56:96] = struct.pack("<QQII", 0, root_ohdr, 1, 0) + struct.pack("<QQ", btree, heap)
+    # root object header: one symbol-table message
+    b[root_ohdr:root_ohdr + 16] = struct.pack("<BBHII", 1, 0, 1, 1, 24) + b"\0" * 4
+    b[root_ohdr + 16:root_ohdr + 40] = struct.pack("<HHBBBB", 0x11, 16, 0, 0, 0, 0) + struct.pack("<QQ", btree, heap)
+    b[btree:btree + 24] = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF)
+    b[btree + 24:btree + 48] = struct.pack("<QQQ", 0, snod, name_off[names[-1]])
+    b[heap:heap + 32] = b"HEAP" + struct.pack("<BBBBQQQ", 0, 0, 0, 0, len(heap_data), len(heap_data) - 32, heap_data_addr)
+    b[heap_data_addr:heap_data_addr + len(heap_data)] = heap_data
+    b[snod:snod + 8] = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+    for k, n in enumerate(names):
+        e = snod + 8 + 40 * k
+        b[e:e + 40] = struct.pack("<QQII", name_off[n], ohdrs[n], 0, 0) + b"\0" * 16
+    for n in names:
+        a = datasets[n]
+        msgs = b""
+        dims = b"".join(struct.pack("<Q", d) for d in a.shape)
+        body = struct.pack("<BBBB", 1, a.ndim, 0, 0) + b"\0" * 4 + dims
+        msgs += struct.pack("<HHBBBB", 1, len(body), 0, 0, 0, 0) + body
+        if a.dtype == np.float64:
+            body = struct.pack("<BBBBI", 0x11, 0x20, 0x3f, 0, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+        else:
+            body = struct.pack("<BBBBI", 0x10, 0x08, 0, 0, 4) + struct.pack("<HH", 0, 32)
+        body += b"\0" * (-len(body) % 8)
+        msgs += struct.pack("<HHBBBB", 3, len(body), 1, 0, 0, 0) + body
+        body = struct.pack("<BB", 3, 1) + struct.pack("<QQ", raws[n], a.nbytes)
+        body += b"\0" * (-len(body) % 8)
+        msgs += struct.pack("<HHBBBB", 8, len(body), 0, 0, 0, 0) + body
+        o = ohdrs[n]
+        b[o:o + 16] = struct.pack("<BBHII", 1, 0, 3, 1, len(msgs)) + b"\0" * 4
+        b[o + 16:o + 16 + len(msgs)] = msgs
+        b[raws[n]:raws[n] + a.nbytes] = a.tobytes()
+    Path(path).write_bytes(bytes(b))
+
+
+def test_mini_hdf5_reader_roundtrip(pkg, tmp_path):
+    rng = np.random.default_rng(5)
+    d = {"PT": rng.standard_normal((7, 5)), "PAPH": rng.standard_normal((8, 5)),
+         "TENDENCY_LOC_CLD": rng.standard_normal((5, 7, 5)), "KLON": np.array([5], dtype=np.int32),
+         "KLEV": np.array([7], dtype=np.int32)}
+    p = tmp_path / "tiny.h5"
+    _tiny_h5(p, d)
+    for n in ("PT", "PAPH", "TENDENCY_LOC_CLD"):
+        got = pkg.read_h5_f8(p, n)
+        assert got.shape == d[n].shape and np.array_equal(got, d[n]), n
+    assert pkg.read_h5_i4(p, "KLON")[0] == 5 and pkg.read_h5_i4(p, "KLEV")[0] == 7
+    with pytest.raises(KeyError):
+        pkg.read_h5_f8(p, "NOPE")
+    with pytest.raises(KeyError):
+        pkg.read_h5_f8(p, "KLON")          # wrong type
+    with pytest.raises(KeyError):
+        pkg.read_h5_f8(tmp_path / "absent.h5", "PT")
+
+
+def test_mini_hdf5_reader_on_reference_file(pkg):
+    """Only where the reference checkout is mounted (build container); skipped on the GPU box."""
+    ref = Path("/root/reference/config-files/reference.h5")
+    if not ref.exists():
+        pytest.skip("reference checkout not mounted")
+    assert pkg.read_h5_i4(ref, "KLON")[0] == 100 and pkg.read_h5_i4(ref, "KLEV")[0] == 137
+    fn = pkg.read_h5_f8(ref, "PFPLSN")
+    assert fn.shape == (138, 100) and fn.min() >= 0 and 0 < fn.max() < 1e-4
+    hn = pkg.read_h5_f8(ref, "PFHPSN")
+    nz = fn > 0
+    assert np.allclose(-hn[nz] / fn[nz], 2.8345e6, rtol=1e-12)      # RLSTT
+    assert pkg.read_h5_f8(ref, "TENDENCY_LOC_CLD").shape == (5, 137, 100)

@@ -1,0 +1,126 @@
+"""GPU suite, adjoint path and the adjoint (dot-product) test.
+
+Tolerances: AD fields |gpu - oracle| <= AD_RTOL * max|field| per field (AD_RTOL = 1e-8: the adjoint
+chains many divisions by trajectory quantities; measured ~1e-12); adjoint symmetry to the
+reference's own tolerance: |N1 - N2| / eps / N2 < 10000 (cloudsc_driver_ad_mod.F90:286-294).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+AD_RTOL = 1e-8
+
+G2O_IN = {"paph": "paphp1", "pap": "papp1", "pq": "pqm1", "pqs": "pqs", "pt": "ptm1", "pl": "pl",
+          "pi": "pi", "plude": "plude", "plu": "plu", "pmfu": "pmfu", "pmfd": "pmfd",
+          "gtent": "pgtent", "gtenq": "pgtenq", "gtenl": "pgtenl", "gteni": "pgteni",
+          "psupsat": "psupsat"}
+G2O_OUT = {"tent": "ptent", "tenq": "ptenq", "tenl": "ptenl", "teni": "pteni", "pclc": "pclc",
+           "pfplsl": "pfplsl", "pfplsn": "pfplsn", "pfhpsl": "pfhpsl", "pfhpsn": "pfhpsn",
+           "pcovptot": "pcovptot"}
+
+
+@pytest.mark.parametrize("nproma,ngptot,lregcl", [(100, 100, True), (32, 100, True), (1, 40, False),
+                                                  (64, 200, False)])
+def test_ad_fields_match_oracle(pkg, ob, src100, nproma, ngptot, lregcl):
+    prm = pkg.default_params(lregcl=lregcl)
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    nb = st.nblocks
+    rng = np.random.default_rng(7)
+    din, dout = pkg.driver.alloc_increments(nb, 137, nproma)
+    # non-zero input adjoints on entry (they must be ACCUMULATED), random output adjoints
+    for n, v in din.items():
+        v[:] = 1e-3 * rng.standard_normal(v.shape)
+    scale_out = {"tent": 1e3, "tenq": 1e6, "tenl": 1e7, "teni": 1e7, "pclc": 1.0, "pfplsl": 1e4,
+                 "pfplsn": 1e4, "pfhpsl": 1e-2, "pfhpsn": 1e-2, "pcovptot": 1.0}
+    for n, v in dout.items():
+        v[:] = scale_out[n] * rng.standard_normal(v.shape)
+    din0 = {k: v.copy() for k, v in din.items()}
+    dout0 = {k: v.copy() for k, v in dout.items()}
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        gpu.ad(st, din, dout)
+    traj = {"ptent": st.a["b_loc"][:, 0], "ptenq": st.a["b_loc"][:, 2], "pclc": st.a["pa"],
+            "pfplsn": st.a["pfplsn"], "pfhpsl": st.a["pfhpsl"]}
+    for b in range(nb):
+        icend = min(nproma, ngptot - b * nproma)
+        x5 = {k: np.ascontiguousarray(v[:, :icend]) for k, v in ob.block_inputs(st, b, prm).items()}
+        xa = {o: din0[gname][b][:, :icend].copy() for gname, o in G2O_IN.items()}
+        ya = {o: dout0[gname][b][:, :icend].copy() for gname, o in G2O_OUT.items()}
+        y5 = ob.cloudsc2ad_block(prm, src100.ceta, st.ptsphy, x5, xa, ya)
+        for gname, o in G2O_IN.items():
+            ref, got = xa[o], din[gname][b][:, :icend]
+            # compare the increments the adjoint added, scaled by their own magnitude
+            inc_ref = ref - (0.0 if gname == "psupsat" else din0[gname][b][:, :icend])
+            inc_got = got - (0.0 if gname == "psupsat" else din0[gname][b][:, :icend])
+            scale = max(np.abs(inc_ref).max(), 1e-300)
+            err = np.abs(inc_got - inc_ref).max() / scale
+            assert err <= AD_RTOL, (gname, b, err)
+        for gname, o in G2O_OUT.items():
+            assert not dout[gname][b][:, :icend].any(), gname            # consumed and zeroed
+            assert not ya[o].any()
+            if icend < nproma:                                           # padding untouched
+                assert np.array_equal(dout[gname][b][:, icend:], dout0[gname][b][:, icend:])
+        for o, arr in traj.items():                                      # trajectory outputs (:842-864)
+            scale = max(np.abs(y5[o]).max(), 1e-300)
+            assert np.abs(arr[b][:, :icend] - y5[o]).max() <= 1e-11 * scale, o
+
+
+@pytest.mark.parametrize("lregcl", [False, True])
+def test_dot_product_identity_random(pkg, src100, lregcl):
+    """<M' dx, y> == <dx, M'^T y> for random dx, y through the full-field TL and AD kernels."""
+    prm = pkg.default_params(lregcl=lregcl)
+    nproma, ngptot = 64, 256
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    nb = st.nblocks
+    rng = np.random.default_rng(11)
+    a = st.a
+    base = {"paph": a["paph"], "pap": a["pap"], "pq": a["pq"], "pqs": 1e-3 * np.ones_like(a["pq"]),
+            "pt": a["pt"], "pl": a["pclv"][:, 0], "pi": a["pclv"][:, 1], "plude": a["plude"],
+            "plu": a["plu"], "pmfu": a["pmfu"], "pmfd": a["pmfd"], "gtent": a["b_cml"][:, 0],
+            "gtenq": a["b_cml"][:, 2], "gtenl": a["b_cml"][:, 3], "gteni": a["b_cml"][:, 4],
+            "psupsat": a["psupsat"]}
+    dx = {k: np.ascontiguousarray(0.01 * v * rng.standard_normal(v.shape)) for k, v in base.items()}
+    # The reference's adjoint ASSIGNS PSUPSAT = PTSPHY*ZQP1 (cloudsc2ad.F90:1733, an extra PTSPHY
+    # and no accumulation), which is not the transpose of the TL statement (:346); its own test
+    # sets ZSUPSAT = 0 ("obsolete, better not use", cloudsc_driver_ad_mod.F90:139). Same here.
+    dx["psupsat"][:] = 0.0
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        _, tl_out = pkg.driver.alloc_increments(nb, 137, nproma)
+        gpu.tl(st, dx, tl_out)
+        y = {k: np.ascontiguousarray(v * rng.uniform(0.5, 1.5, v.shape)) for k, v in tl_out.items()}
+        lhs = sum(float((tl_out[k] * y[k]).sum()) for k in y)
+        adj, _ = pkg.driver.alloc_increments(nb, 137, nproma)
+        ycopy = {k: v.copy() for k, v in y.items()}
+        gpu.ad(st, adj, ycopy)
+    rhs = sum(float((dx[k] * adj[k]).sum()) for k in dx)
+    assert lhs != 0.0
+    assert abs(lhs - rhs) <= 1e-10 * abs(lhs), (lhs, rhs)
+
+
+def test_adjoint_test_config3(pkg, ob, src100):
+    """BASELINE config 3: dwarf-cloudsc2-ad 1 100 100 (LREGCL=.TRUE.)."""
+    prm = pkg.default_params(lregcl=True)
+    st = pkg.ArrayState(src100, nproma=100, ngptot=100)
+    ref = pkg.ArrayState(src100, nproma=100, ngptot=100)
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        zn, nc = gpu.ad_test(st)
+    zo, nco, _ = ob.driver_ad(prm, src100.ceta, ref)
+    assert pkg.adjoint_verdict(zn) and zn < 10000.0, zn
+    assert nc.shape == (100, 3)
+    assert np.allclose(nc[:, 0], nco[:, 0], rtol=1e-9)      # N1 = <y, y> per column
+    assert np.allclose(nc[:, 1], nco[:, 1], rtol=1e-9)      # N2 = <dx, AD y>
+    assert zn == pytest.approx(nc[:, 2].max())
+    assert (nc[:, 2] < 10000.0).all()
+    assert ob.lib().orc_adjoint_verdict(zo) == 1
+
+
+@pytest.mark.parametrize("nproma,ngptot,lregcl", [(32, 100, True), (128, 1000, False), (1, 100, True)])
+def test_adjoint_test_other_blockings(pkg, src100, nproma, ngptot, lregcl):
+    prm = pkg.default_params(lregcl=lregcl)
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        zn, nc = gpu.ad_test(st)
+    assert zn < 10000.0, zn
+    assert (nc[:, 0] > 0).all()
+    # cyclic expansion: column g behaves exactly like column g mod 100
+    if ngptot > 100:
+        assert np.array_equal(nc[100:200], nc[:100])

@@ -1,0 +1,131 @@
+"""GPU suite, tangent-linear path and Taylor test.
+
+Tolerances: TL fields |gpu - oracle| <= TL_RTOL * max|field| (TL_RTOL = 1e-9: the TL divides by
+trajectory quantities that can be tiny, amplifying the 1-2 ulp exp differences); Taylor ratios:
+identical verdict, and per-column ratios equal to a lambda-dependent tolerance because
+sum(F - F5) is cancellation-dominated for small lambda (SURVEY 7 "hard parts").
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TL_RTOL = 1e-9
+
+
+def _tl_reference(ob, prm, src, st, scale=0.01):
+    """Oracle CLOUDSC2TL block by block with dx = scale * x -> dict of stacked (NB, KLEV[+1], NPROMA)."""
+    y5s, dys = [], []
+    for b in range(st.nblocks):
+        icend = min(st.nproma, st.ngptot - b * st.nproma)
+        x5 = ob.block_inputs(st, b, prm)
+        x5 = {k: np.ascontiguousarray(v[:, :icend]) for k, v in x5.items()}
+        dx = {k: scale * v for k, v in x5.items()}
+        y5, dy = ob.cloudsc2tl_block(prm, src.ceta, st.ptsphy, x5, dx)
+        y5s.append(y5)
+        dys.append(dy)
+    return y5s, dys
+
+
+@pytest.mark.parametrize("nproma,ngptot,lregcl", [(100, 100, False), (32, 100, False), (1, 100, False),
+                                                  (64, 640, True), (128, 300, True)])
+def test_tl_fields_match_oracle(pkg, ob, src100, nproma, ngptot, lregcl):
+    prm = pkg.default_params(lregcl=lregcl)
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    nb = st.nblocks
+    din, dout = pkg.driver.alloc_increments(nb, 137, nproma)
+    # increments = 1 % of the inputs (cloudsc_driver_tl_mod.F90:156-171), PQS' = 1 % of SATUR
+    a = st.a
+    din["paph"][:] = 0.01 * a["paph"]; din["pap"][:] = 0.01 * a["pap"]; din["pq"][:] = 0.01 * a["pq"]
+    din["pt"][:] = 0.01 * a["pt"]; din["pl"][:] = 0.01 * a["pclv"][:, 0]; din["pi"][:] = 0.01 * a["pclv"][:, 1]
+    din["plude"][:] = 0.01 * a["plude"]; din["plu"][:] = 0.01 * a["plu"]; din["pmfu"][:] = 0.01 * a["pmfu"]
+    din["pmfd"][:] = 0.01 * a["pmfd"]; din["gtent"][:] = 0.01 * a["b_cml"][:, 0]
+    din["gtenq"][:] = 0.01 * a["b_cml"][:, 2]; din["gtenl"][:] = 0.01 * a["b_cml"][:, 3]
+    din["gteni"][:] = 0.01 * a["b_cml"][:, 4]; din["psupsat"][:] = 0.01 * a["psupsat"]
+    for b in range(nb):
+        din["pqs"][b] = 0.01 * ob.satur(prm, a["pap"][b], np.where(a["pt"][b] > 0, a["pt"][b], 250.0))
+    for v in dout.values():
+        v.fill(-3.5)
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        gpu.tl(st, din, dout)
+    y5s, dys = _tl_reference(ob, prm, src100, st)
+    names = {"tent": "ptent", "tenq": "ptenq", "tenl": "ptenl", "teni": "pteni", "pclc": "pclc",
+             "pfplsl": "pfplsl", "pfplsn": "pfplsn", "pfhpsl": "pfhpsl", "pfhpsn": "pfhpsn",
+             "pcovptot": "pcovptot"}
+    traj = {"ptent": st.a["b_loc"][:, 0], "ptenq": st.a["b_loc"][:, 2], "ptenl": st.a["b_loc"][:, 3],
+            "pteni": st.a["b_loc"][:, 4], "pclc": st.a["pa"], "pfplsl": st.a["pfplsl"],
+            "pfplsn": st.a["pfplsn"], "pfhpsl": st.a["pfhpsl"], "pfhpsn": st.a["pfhpsn"]}
+    for gname, oname in names.items():
+        ref = np.concatenate([d[oname] for d in dys], axis=1)             # (KLEV, ngptot)
+        got = np.concatenate([dout[gname][b][:, :min(nproma, ngptot - b * nproma)] for b in range(nb)], axis=1)
+        scale = max(np.abs(ref).max(), 1e-300)
+        # columns whose trajectory sits on a branch knife-edge may flip; count them, allow none here
+        err = np.abs(got - ref).max(axis=0) / scale
+        assert (err <= TL_RTOL).all(), (gname, err.max(), int((err > TL_RTOL).sum()))
+    for oname, arr in traj.items():
+        ref = np.concatenate([d[oname] for d in y5s], axis=1)
+        got = np.concatenate([arr[b][:, :min(nproma, ngptot - b * nproma)] for b in range(nb)], axis=1)
+        scale = max(np.abs(ref).max(), 1e-300)
+        assert np.abs(got - ref).max() <= 1e-11 * scale, oname
+    tail = ngptot - (nb - 1) * nproma
+    if tail < nproma:
+        assert (dout["tent"][-1, :, tail:] == -3.5).all()                  # padding untouched
+
+
+def test_tl_is_linear_on_gpu(pkg, src100):
+    prm = pkg.default_params()
+    st = pkg.ArrayState(src100, 50, 100)
+    rng = np.random.default_rng(2)
+    base = {"paph": st.a["paph"], "pap": st.a["pap"], "pq": st.a["pq"], "pqs": 1e-3 * np.ones_like(st.a["pq"]),
+            "pt": st.a["pt"], "pl": st.a["pclv"][:, 0], "pi": st.a["pclv"][:, 1], "plude": st.a["plude"],
+            "plu": st.a["plu"], "pmfu": st.a["pmfu"], "pmfd": st.a["pmfd"], "gtent": st.a["b_cml"][:, 0],
+            "gtenq": st.a["b_cml"][:, 2], "gtenl": st.a["b_cml"][:, 3], "gteni": st.a["b_cml"][:, 4],
+            "psupsat": st.a["psupsat"]}
+    d1 = {k: np.ascontiguousarray(0.01 * v * rng.standard_normal(v.shape)) for k, v in base.items()}
+    d2 = {k: np.ascontiguousarray(0.01 * v * rng.standard_normal(v.shape)) for k, v in base.items()}
+    d3 = {k: 2.0 * d1[k] - 3.0 * d2[k] for k in base}
+    outs = []
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        for d in (d1, d2, d3):
+            _, dout = pkg.driver.alloc_increments(st.nblocks, 137, 50)
+            gpu.tl(st, d, dout)
+            outs.append(dout)
+    for n in outs[0]:
+        want = 2.0 * outs[0][n] - 3.0 * outs[1][n]
+        scale = max(np.abs(want).max(), 1e-300)
+        assert np.abs(outs[2][n] - want).max() <= 1e-10 * scale, n
+
+
+def test_taylor_test_config2(pkg, ob, src100, gpu_nl):
+    """BASELINE config 2: dwarf-cloudsc2-tl 1 100 1 -- verdict identical to the oracle's, per-column
+    ratios equal within a lambda-dependent tolerance."""
+    st = pkg.ArrayState(src100, nproma=1, ngptot=100)
+    ref = pkg.ArrayState(src100, nproma=1, ngptot=100)
+    z, rb = gpu_nl.tl_taylor(st)
+    zo, rbo, _ = ob.driver_tl(gpu_nl.params, src100.ceta, ref, numomp=2)
+    pen, istart = pkg.taylor_verdict(z)
+    assert (pen, istart) == ob.taylor_verdict(zo)
+    assert 0 <= pen <= 5
+    assert rb.shape == (100, 10) and np.isfinite(rb).all()
+    lam = 10.0 ** -np.arange(1, 11)
+    # |r_gpu - r_oracle| <= 1e-9 (physics) + 2e-13/lambda (cancellation in sum(F-F5), F ~ 1e-16 rel)
+    tol = 1e-9 * np.maximum(1.0, np.abs(rbo)) + 2e-13 / lam * np.maximum(1.0, np.abs(rbo))
+    assert (np.abs(rb - rbo) <= tol).all(), np.abs(rb - rbo).max(axis=0)
+    assert np.allclose(z, rb.max(axis=0))
+    # the call also leaves the trajectory outputs in the caller's arrays, like the reference
+    for n, a in st.outputs().items():
+        scale = max(np.abs(ref.outputs()[n]).max(), 1e-300)
+        assert np.abs(a - ref.outputs()[n]).max() <= 1e-11 * scale, n
+
+
+@pytest.mark.parametrize("nproma,ngptot", [(32, 100), (100, 100), (64, 1000)])
+def test_taylor_test_blocked(pkg, ob, src100, gpu_nl, nproma, ngptot):
+    """Per-block sums (NPROMA > 1): summation order differs (tree vs JL-fastest), verdict must agree."""
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    ref = pkg.ArrayState(src100, nproma, ngptot)
+    z, rb = gpu_nl.tl_taylor(st)
+    zo, rbo, _ = ob.driver_tl(gpu_nl.params, src100.ceta, ref, numomp=2)
+    assert pkg.taylor_verdict(z)[0] <= 5 and pkg.taylor_verdict(z)[0] >= 0
+    assert pkg.taylor_verdict(z)[1] == ob.taylor_verdict(zo)[1]
+    lam = 10.0 ** -np.arange(1, 11)
+    tol = 1e-8 * np.maximum(1.0, np.abs(rbo)) + 1e-12 / lam * np.maximum(1.0, np.abs(rbo))
+    assert (np.abs(rb - rbo) <= tol).all()
