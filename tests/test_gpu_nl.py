@@ -161,3 +161,23 @@ def test_errors_are_reported_not_swallowed(pkg, src100, gpu_nl):
     # the session context was finalised by the failed init? no: init validates before touching it
     gpu_nl.nl(st)
     assert gpu_nl.launch_count() > 0
+
+
+def test_device_shard_expansion_and_sharded_tests(pkg, src100, gpu_nl):
+    """cloudsc2_gpu_expand_shard_dev with a global column offset == host expansion of that shard,
+    and the sharded Taylor helper on one rank == the unsharded call."""
+    sh = pkg.shard_blocks(1000, 64, 1, 3)
+    src = np.ascontiguousarray(src100.f["tend_cml"])
+    want = pkg.expand(src, 64, sh.ngptot, gcol0=sh.gcol0)
+    dsrc, ddst = gpu_nl.malloc(src.nbytes), gpu_nl.malloc(want.nbytes)
+    gpu_nl.h2d(dsrc, src)
+    gpu_nl.expand_dev(dsrc, 100, 137, 8, ddst, 64, sh.ngptot, gcol0=sh.gcol0)
+    gpu_nl.sync()
+    got = np.empty_like(want)
+    gpu_nl.d2h(got, ddst)
+    gpu_nl.free(dsrc)
+    gpu_nl.free(ddst)
+    assert np.array_equal(got, want)
+    z, sh1 = pkg.sharded_taylor(gpu_nl, src100, 32, 100, 0, 1)
+    z2, _ = gpu_nl.tl_taylor(pkg.ArrayState(src100, 32, 100))
+    assert np.array_equal(z, z2) and sh1.ngptot == 100
