@@ -45,16 +45,16 @@ struct AdjTraj {
 };
 __device__ __forceinline__ void adj_iter_fwd(const KConst &c, const AdjTraj &tr, double zqp5,
                                              double &t5, double &q5, AdjIter &it) {
-  it.r = 1.0 / (t5 - tr.z4es);
-  it.foeew = c.r2es * exp(tr.z3es * (t5 - c.rtt) * it.r);
+  it.r = csc2_rcp(t5 - tr.z4es);
+  it.foeew = c.r2es * csc2_exp(tr.z3es * (t5 - c.rtt) * it.r);
   it.qs_raw = zqp5 * it.foeew;
   it.cap = it.qs_raw > CSC2_ZQMAX;
   if (it.cap) it.qs_raw = CSC2_ZQMAX;
-  it.cor = 1.0 / (1.0 - c.retv * it.qs_raw);
+  it.cor = csc2_rcp(1.0 - c.retv * it.qs_raw);
   it.qs = it.qs_raw * it.cor;
   it.z2s = tr.z5alcp * (it.r * it.r);
   it.q = q5;
-  it.den = 1.0 / (1.0 + it.qs * it.cor * it.z2s);
+  it.den = csc2_rcp(1.0 + it.qs * it.cor * it.z2s);
   const double cond = (q5 - it.qs) * it.den;
   t5 += tr.zaldcp * cond;
   q5 -= cond;
@@ -118,26 +118,22 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double zi5 = x5.pi + dt * x5.gi;
   const double zdp5 = x5.paph1 - paph0_5;
   double zzz5 = c.rcpd_inv;
-  if (RV) zzz5 = 1.0 / (c.rcpd + c.rcpd * c.rvtmp2 * zqp25);
+  if (RV) zzz5 = csc2_rcp(c.rcpd + c.rcpd * c.rvtmp2 * zqp25);
   const double zlfdcp5 = c.rlmlt * zzz5, zlsdcp5 = c.rlstt * zzz5, zlvdcp5 = c.rlvtt * zzz5;
-  const double pap5_inv = 1.0 / x5.pap;
+  const double pap5_inv = csc2_rcp(x5.pap);
 
-  const double rw = 1.0 / (ztp25 - c.r4les), ri = 1.0 / (ztp25 - c.r4ies);
+  const double rw = csc2_rcp(ztp25 - c.r4les), ri = csc2_rcp(ztp25 - c.r4ies);
   const bool cold = ztp25 < c.rtt;
   const double targ = 0.17 * (ztp25 - c.rlptrc);
-  double zfwat5, zfoeew5;
-  if (cold) {
-    zfwat5 = 0.545 * (tanh(targ) + 1.0);
-    zfoeew5 = c.r2es * exp(c.r3ies * (ztp25 - c.rtt) * ri);
-  } else {
-    zfwat5 = 1.0;
-    zfoeew5 = c.r2es * exp(c.r3les * (ztp25 - c.rtt) * rw);
-  }
+  double tanh_p1, sech2;
+  csc2_tanh_p1_sech2(targ, tanh_p1, sech2);
+  const double zfwat5 = cold ? 0.545 * tanh_p1 : 1.0;
+  const double zfoeew5 = c.r2es * csc2_exp((cold ? c.r3ies * ri : c.r3les * rw) * (ztp25 - c.rtt));
   const double zesdp15 = zfoeew5 * pap5_inv;
   const double zesdp5 = dmin_(zesdp15, CSC2_ZQMAX);
   const double zfacw5 = c.r5les * (rw * rw), zfaci5 = c.r5ies * (ri * ri);
   const double zfac5 = zfwat5 * zfacw5 + (1.0 - zfwat5) * zfaci5;
-  const double zcor5 = 1.0 / (1.0 - c.retv * zesdp5);
+  const double zcor5 = csc2_rcp(1.0 - c.retv * zesdp5);
   const double zdqsdtemp5 = zfac5 * zcor5 * pqs5;
 
   const double zcrh2 = crit_rh(crh, c.ceta[jk]);
@@ -157,30 +153,30 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   } else {
     cbranch = 2;
     zqpd5 = zqsat5 - zqt5; zqcd5 = zqsat5 - zqcrit5;
-    den5_inv = 1.0 / (zqcd5 - zscalm * (zqt5 - zqcrit5));
-    zsqrt5 = sqrt(zqpd5 * den5_inv);
+    den5_inv = csc2_rcp(zqcd5 - zscalm * (zqt5 - zqcrit5));
+    zsqrt5 = csc2_sqrt(zqpd5 * den5_inv);
     zclc5 = 1.0 - zsqrt5;
     zqc15 = (zscalm * zqpd5 + (1.0 - zscalm) * zqcd5) * (zclc5 * zclc5);
   }
 
-  const double zdp5_inv = 1.0 / zdp5;
+  const double zdp5_inv = csc2_rcp(zdp5);
   const double zgdp5 = c.rg * zdp5_inv;
   const double zlude5 = x5.plude * dt * zgdp5;
   const bool llo1 = (jk < c.klev - 1) && zlude5 >= c.rlmin && x5.plu1 >= CSC2_ZEPS2;
   double pclc5 = zclc5, zqc25 = zqc15, econv = 0.0, plu_inv = 0.0;
   if (llo1) {
-    plu_inv = 1.0 / x5.plu1;
-    econv = exp(-zlude5 * plu_inv);
+    plu_inv = csc2_rcp(x5.plu1);
+    econv = csc2_expn(-zlude5 * plu_inv);
     pclc5 = zclc5 + (1.0 - zclc5) * (1.0 - econv);
     zqc25 = zqc15 + zlude5;
   }
 
-  const double zfac1 = 1.0 / (c.rd * ztp25);
+  const double zfac1 = csc2_rcp(c.rd * ztp25);
   const double zrho5 = x5.pap * zfac1;
-  const double zfac2 = 1.0 / (x5.pap - c.retv * zfoeew5);
+  const double zfac2 = csc2_rcp(x5.pap - c.retv * zfoeew5);
   const double zrodqsdp5 = -zrho5 * pqs5 * zfac2;
   const double zldcp5 = zfwat5 * zlvdcp5 + (1.0 - zfwat5) * zlsdcp5;
-  const double zfac3 = 1.0 / (1.0 + zldcp5 * zdqsdtemp5);
+  const double zfac3 = csc2_rcp(1.0 + zldcp5 * zdqsdtemp5);
   const double dtdzmo5 = c.rg * (c.rcpd_inv - zldcp5 * zrodqsdp5) * zfac3;
   const double zdqsdz5 = zdqsdtemp5 * dtdzmo5 - c.rg * zrodqsdp5;
   const double zfac4 = c.rd * ztp25 * pap5_inv;            // 1/ZRHO5
@@ -200,8 +196,8 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   double ztp15 = ztp25, zcons5 = 0.0, zcons5_inv = 0.0, zz2s5 = 0.0, zsnmlt5 = 0.0;
   const bool warm2 = (ztp25 - c.zmeltp2) > 0.0;
   if (melt) {
-    zcons5 = c.zcons2 * zdp5 / zlfdcp5;
-    zcons5_inv = 1.0 / zcons5;
+    zcons5 = c.zcons2 * zdp5 * csc2_rcp(zlfdcp5);
+    zcons5_inv = csc2_rcp(zcons5);
     zz2s5 = warm2 ? zcons5 * (ztp25 - c.zmeltp2) : 0.0;
     zsnmlt5 = (sfl5 <= zz2s5) ? sfl5 : zz2s5;
     ztp15 = ztp25 - zsnmlt5 * zcons5_inv;
@@ -212,15 +208,15 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   double pclc5_inv = 0.0, zcldl5 = 0.0, zexp35 = 0.0, zexpdl5 = 0.0, zprr5 = 0.0;
   double zcldi5 = 0.0, zexp15 = 0.0, zexp25 = 0.0, zexpdi5 = 0.0, zprs5 = 0.0;
   if (cloudy) {
-    pclc5_inv = 1.0 / pclc5;
+    pclc5_inv = csc2_rcp(pclc5);
     zcldl5 = zqlwc15 * pclc5_inv;
-    zexp35 = exp(-SQA_(zcldl5 * c.rlcrit_inv));
-    zexpdl5 = exp(-(c.zckcodtl * (1.0 - zexp35)));
+    zexp35 = csc2_expn(-SQA_(zcldl5 * c.rlcrit_inv));
+    zexpdl5 = csc2_exp(-(c.zckcodtl * (1.0 - zexp35)));
     zprr5 = zqlwc15 - pclc5 * zcldl5 * zexpdl5;
     zcldi5 = zqiwc15 * pclc5_inv;
-    zexp15 = exp(0.025 * (ztp15 - c.rtt));
-    zexp25 = exp(-SQA_(zcldi5 * c.rlcrit_inv));
-    zexpdi5 = exp(-(c.zckcodti * zexp15 * (1.0 - zexp25)));
+    zexp15 = csc2_exp(0.025 * (ztp15 - c.rtt));
+    zexp25 = csc2_expn(-SQA_(zcldi5 * c.rlcrit_inv));
+    zexpdi5 = csc2_exp(-(c.zckcodti * zexp15 * (1.0 - zexp25)));
     zprs5 = zqiwc15 - pclc5 * zcldi5 * zexpdi5;
   }
   const double zc2dp5 = c.zcons2 * zdp5;
@@ -386,8 +382,9 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
       ztp1_ += zcons5 * zz2s;
       zcons += (ztp25 - c.zmeltp2) * zz2s;
     }
-    zdp_ += c.zcons2 * zcons / zlfdcp5;
-    if (RV) zlfdcp_ -= zc2dp5 * zcons / (zlfdcp5 * zlfdcp5);
+    const double lf5_inv = csc2_rcp(zlfdcp5);
+    zdp_ += c.zcons2 * zcons * lf5_inv;
+    if (RV) zlfdcp_ -= zc2dp5 * zcons * (lf5_inv * lf5_inv);
   } else {
     zsfl_ = zsfln;
     zrfl_ = zrfln;
@@ -463,12 +460,12 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     double zqcd = (1.0 - zscalm) * zqc_ * (zclc5 * zclc5);
     pclc_ += (zscalm * zqpd5 + (1.0 - zscalm) * zqcd5) * 2.0 * zclc5 * zqc_;
     if (lreg) {                                            // :1554-1559
-      const double zrat = zqpd5 / zqcd5;
+      const double zrat = zqpd5 * csc2_rcp(zqcd5);
       const double b = 1.0 - zscalm * (1.0 - zrat);
-      const double zyyy = dmin_(0.3, 3.5 * sqrt(zrat * (b * b * b)) / (1.0 - zscalm));
+      const double zyyy = dmin_(0.3, 3.5 * csc2_sqrt(zrat * (b * b * b)) * csc2_rcp(1.0 - zscalm));
       pclc_ = zyyy * pclc_;
     }
-    const double h = (0.5 / zsqrt5) * pclc_ * den5_inv;
+    const double h = (0.5 * csc2_rcp(zsqrt5)) * pclc_ * den5_inv;
     zqpd -= h;
     const double h2 = h * zqpd5 * den5_inv;
     zqcd += h2;
@@ -502,8 +499,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     pap_ -= zesdp * zfoeew5 * (pap5_inv * pap5_inv);
     if (cold) {
       ztp1_ += c.r3ies * (c.rtt - c.r4ies) * zfoeew_ * zfoeew5 * (ri * ri);
-      const double ch = cosh(targ);
-      ztp1_ += 0.545 * 0.17 * zfwat_ / (ch * ch);
+      ztp1_ += (0.545 * 0.17) * zfwat_ * sech2;
     } else {
       ztp1_ += c.r3les * (c.rtt - c.r4les) * zfoeew_ * zfoeew5 * (rw * rw);
     }
@@ -514,7 +510,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     const double zzz = c.rlvtt * zlvdcp_ + c.rlstt * zlsdcp_ + c.rlmlt * zlfdcp_;
     // the reference evaluates the denominator with ZQP15 as left by the forward sweep, i.e. the
     // post-adjustment humidity (:1712)
-    zqp1_ -= zzz * c.rcpd * c.rvtmp2 / SQA_(c.rcpd + c.rcpd * c.rvtmp2 * q5adj);
+    zqp1_ -= zzz * c.rcpd * c.rvtmp2 * SQA_(csc2_rcp(c.rcpd + c.rcpd * c.rvtmp2 * q5adj));
   }
   g.paph_hi = zdp_ - paph_g;
   g.paph_lo = paph_g - zdp_;

@@ -299,6 +299,19 @@ int cloudsc2_gpu_sync(void) {
   return 0;
 }
 
+int cloudsc2_gpu_math_probe(int fn, const double *x, double *y, int n) {
+  if (int rc = require_init()) return rc;
+  if (!x || !y || n <= 0 || fn < 0 || fn > 5) return fail(3, "bad arguments to cloudsc2_gpu_math_probe");
+  if (int rc = g.work.reserve(2 * (size_t)n * sizeof(double))) return rc;
+  double *dx = g.work.d(), *dy = dx + n;
+  CK(cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(csc2_launch_math_probe(fn, dx, dy, n, g.stream));
+  g.launches += 1;
+  CK(cudaMemcpyAsync(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 /* ---- nonlinear ----------------------------------------------------------------------- */
 
 int cloudsc2_gpu_nl_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,

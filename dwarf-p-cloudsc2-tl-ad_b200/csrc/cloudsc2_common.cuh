@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "../../include/cloudsc2_b200.h"
+#include "cloudsc2_math.cuh"
 
 #define CSC2_KLEV_MAX 192   // KLEV of the dwarf is 137; bound so that KConst fits the param space
 
@@ -65,24 +66,24 @@ struct IncOut {
 __device__ __forceinline__ double dmin_(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ double dmax_(double a, double b) { return a > b ? a : b; }
 
-// SATUR, LDPHYLIN branch (satur.F90:106-123) incl. FOEALFA (fcttre.func.h:73-75).
-// The liquid / ice exponentials are skipped when their weight is exactly 0.
+// SATUR, LDPHYLIN branch (satur.F90:106-123) incl. FOEALFA (fcttre.func.h:73-75).  Straight-line:
+// both Tetens exponentials are always evaluated (their weights may be 0) so that the compiler
+// can interleave the two polynomial chains.
 __device__ __forceinline__ double satur_point(const KConst &c, double t, double pap_inv) {
-  double x = (dmax_(c.rtice, dmin_(c.rtwat, t)) - c.rtice) * c.rtwat_rtice_r;
-  double alfa = dmin_(1.0, x * x);
-  double tm = t - c.rtt;
-  double el = 0.0, ei = 0.0;
-  if (alfa > 0.0) el = c.r2es * exp(c.r3les * tm / (t - c.r4les));
-  if (alfa < 1.0) ei = c.r2es * exp(c.r3ies * tm / (t - c.r4ies));
-  double foeew = alfa * el + (1.0 - alfa) * ei;
-  double qs = dmin_(foeew * pap_inv, CSC2_ZQMAX);
-  return qs / (1.0 - c.retv * qs);
+  const double x = (dmax_(c.rtice, dmin_(c.rtwat, t)) - c.rtice) * c.rtwat_rtice_r;
+  const double alfa = dmin_(1.0, x * x);
+  const double tm = t - c.rtt;
+  const double el = csc2_exp(c.r3les * tm * csc2_rcp(t - c.r4les));
+  const double ei = csc2_exp(c.r3ies * tm * csc2_rcp(t - c.r4ies));
+  const double foeew = c.r2es * (alfa * el + (1.0 - alfa) * ei);
+  const double qs = dmin_(foeew * pap_inv, CSC2_ZQMAX);
+  return qs * csc2_rcp(1.0 - c.retv * qs);
 }
 
 // Critical relative humidity profile (cloudsc2.F90:384-399).  zrh2 / zdeta1 depend only on the
 // column's ZTRPAUS and are hoisted out of the level loop by the callers.
 struct CritRH {
-  double zeta3, zrh2, zdeta1;
+  double zeta3, zrh2, zdeta1, zdeta1_inv;
 };
 __device__ __forceinline__ CritRH make_critrh(double ztrpaus) {
   CritRH r;
@@ -90,14 +91,19 @@ __device__ __forceinline__ CritRH make_critrh(double ztrpaus) {
   double q = (ztrpaus - 0.25) / 0.15;
   r.zrh2 = 0.35 + 0.14 * (q * q) + 0.04 * dmin_(ztrpaus - 0.25, 0.0) / 0.15;
   r.zdeta1 = 0.09 + 0.16 * (0.4 - ztrpaus) / 0.3;
+  r.zdeta1_inv = 1.0 / r.zdeta1;
   return r;
 }
 __device__ __forceinline__ double crit_rh(const CritRH &r, double ceta) {
   const double zdeta2 = 0.3;
-  if (ceta < r.zeta3) return 1.0;
-  if (ceta < r.zeta3 + zdeta2) return 1.0 + (r.zrh2 - 1.0) * ((ceta - r.zeta3) / zdeta2);
-  if (ceta < 1.0 - r.zdeta1) return r.zrh2;
-  return 1.0 + (r.zrh2 - 1.0) * sqrt((1.0 - ceta) / r.zdeta1);
+  // the four segments of cloudsc2.F90:388-399, selected without branches (ceta is warp-uniform)
+  const double lin = 1.0 + (r.zrh2 - 1.0) * ((ceta - r.zeta3) * (1.0 / zdeta2));
+  const double low = 1.0 + (r.zrh2 - 1.0) * csc2_sqrt(dmax_(1.0 - ceta, 0.0) * r.zdeta1_inv);
+  double v = low;
+  if (ceta < 1.0 - r.zdeta1) v = r.zrh2;
+  if (ceta < r.zeta3 + zdeta2) v = lin;
+  if (ceta < r.zeta3) v = 1.0;
+  return v;
 }
 
 // Tropopause pre-pass (cloudsc2.F90:315-326): ZTRPAUS = CETA of the lowest level JK < KLEV in the

@@ -57,3 +57,7 @@ cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, con
 // ZNORM3 per column and max (cloudsc_driver_ad_mod.F90:260-267).
 cudaError_t csc2_launch_ad_finalize(const Geom &g, const double *n1, const double *n2,
                                     double *norms_col, double *znormg, cudaStream_t s);
+
+// Accuracy probe of cloudsc2_math.cuh: y[i] = fn(x[i]); fn 0 rcp, 1 exp, 2 expn, 3 sqrt,
+// 4 tanh+1, 5 sech^2 (device pointers).
+cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cudaStream_t s);

@@ -38,13 +38,13 @@ __device__ __forceinline__ void cuadjtqs_point(const KConst &c, double zqp /*1/p
   const double zaldcp = liq ? c.ralvdcp : c.ralsdcp;
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
-    const double r = 1.0 / (t - z4es);
-    const double foeew = c.r2es * exp(z3es * (t - c.rtt) * r);
+    const double r = csc2_rcp(t - z4es);
+    const double foeew = c.r2es * csc2_exp(z3es * (t - c.rtt) * r);
     double qsat = dmin_(zqp * foeew, CSC2_ZQMAX);
-    const double cor = 1.0 / (1.0 - c.retv * qsat);
+    const double cor = csc2_rcp(1.0 - c.retv * qsat);
     qsat *= cor;
     const double z2s = z5alcp * (r * r);
-    const double den = 1.0 / (1.0 + qsat * cor * z2s);
+    const double den = csc2_rcp(1.0 + qsat * cor * z2s);
     const double cond = (q - qsat) * den;
     t += zaldcp * cond;
     q -= cond;
@@ -52,6 +52,9 @@ __device__ __forceinline__ void cuadjtqs_point(const KConst &c, double zqp /*1/p
 }
 
 // One level.  `pqs` is the saturation humidity of the level (SATUR output or caller-supplied).
+// Straight-line code: every data-dependent IF of the reference is a select on values that are
+// computed unconditionally with guarded operands, so that the compiler can overlap the
+// independent exp / reciprocal chains of a level (the kernel is FP64-issue bound, not HBM bound).
 __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int jk,
                                          const LevIn &x, double pqs, Carry &st, LevOut &y) {
   const double dt = c.ptsphy;
@@ -63,24 +66,20 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   // :268-278
   const double zdp = x.paph1 - st.paph0;
   double zzz = c.rcpd_inv;
-  if (c.rvtmp2 != 0.0) zzz = 1.0 / (c.rcpd + c.rcpd * c.rvtmp2 * zqp1);
+  if (c.rvtmp2 != 0.0) zzz = csc2_rcp(c.rcpd + c.rcpd * c.rvtmp2 * zqp1);
   const double zlfdcp = c.rlmlt * zzz, zlsdcp = c.rlstt * zzz, zlvdcp = c.rlvtt * zzz;
-  const double pap_inv = 1.0 / x.pap;
+  const double pap_inv = csc2_rcp(x.pap);
+  const double zdp_inv = csc2_rcp(zdp);
 
   // dqs/dT correction factor (:349-375)
-  const double rw = 1.0 / (ztp1 - c.r4les), ri = 1.0 / (ztp1 - c.r4ies);
-  double zfwat, zfoeew;
-  if (ztp1 < c.rtt) {
-    zfwat = 0.545 * (tanh(0.17 * (ztp1 - c.rlptrc)) + 1.0);
-    zfoeew = c.r2es * exp(c.r3ies * (ztp1 - c.rtt) * ri);
-  } else {
-    zfwat = 1.0;
-    zfoeew = c.r2es * exp(c.r3les * (ztp1 - c.rtt) * rw);
-  }
+  const bool cold = ztp1 < c.rtt;
+  const double rw = csc2_rcp(ztp1 - c.r4les), ri = csc2_rcp(ztp1 - c.r4ies);
+  const double zfwat = cold ? 0.545 * csc2_tanh_p1(0.17 * (ztp1 - c.rlptrc)) : 1.0;
+  const double zfoeew = c.r2es * csc2_exp((cold ? c.r3ies * ri : c.r3les * rw) * (ztp1 - c.rtt));
   const double zesdp = dmin_(zfoeew * pap_inv, CSC2_ZQMAX);
   const double zfacw = c.r5les * (rw * rw), zfaci = c.r5ies * (ri * ri);
   const double zfac = zfwat * zfacw + (1.0 - zfwat) * zfaci;
-  const double zcor = 1.0 / (1.0 - c.retv * zesdp);
+  const double zcor = csc2_rcp(1.0 - c.retv * zesdp);
   const double zdqsdtemp = zfac * zcor * pqs;
 
   // critical humidity, ice supersaturation (:384-408)
@@ -93,32 +92,37 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   const double zscalm = c.zscalm[jk];
   const double zqt = zqp1 + zl + zi;
   double pclc, zqc;
-  if (zqt <= zqcrit) {
-    pclc = 0.0; zqc = 0.0;
-  } else if (zqt >= zqsat) {
-    pclc = 1.0; zqc = (1.0 - zscalm) * (zqsat - zqcrit);
-  } else {
+  {
+    const bool clear = zqt <= zqcrit, overcast = zqt >= zqsat;
+    const bool partial = !clear && !overcast;
     const double zqpd = zqsat - zqt, zqcd = zqsat - zqcrit;
-    pclc = 1.0 - sqrt(zqpd / (zqcd - zscalm * (zqt - zqcrit)));
-    zqc = (zscalm * zqpd + (1.0 - zscalm) * zqcd) * (pclc * pclc);
+    // in the partial branch zqpd > 0 and the denominator is > (1-zscalm)*zqcd > 0
+    const double den = partial ? (zqcd - zscalm * (zqt - zqcrit)) : 1.0;
+    const double root = csc2_sqrt((partial ? zqpd : 0.0) * csc2_rcp(den));
+    const double pc = 1.0 - root;
+    pclc = partial ? pc : (overcast ? 1.0 : 0.0);
+    zqc = partial ? (zscalm * zqpd + (1.0 - zscalm) * zqcd) * (pc * pc)
+                  : (overcast ? (1.0 - zscalm) * zqcd : 0.0);
   }
 
   // convective detrainment (:431-444)
-  const double zgdp = c.rg / zdp;
+  const double zgdp = c.rg * zdp_inv;
   const double zlude = x.plude * dt * zgdp;
-  if (jk < c.klev - 1 && zlude >= c.rlmin && x.plu1 >= CSC2_ZEPS2) {
-    pclc = pclc + (1.0 - pclc) * (1.0 - exp(-zlude / x.plu1));
-    zqc = zqc + zlude;
+  {
+    const bool llo1 = jk < c.klev - 1 && zlude >= c.rlmin && x.plu1 >= CSC2_ZEPS2;
+    const double e = csc2_expn(-zlude * csc2_rcp(llo1 ? x.plu1 : 1.0));
+    pclc = llo1 ? pclc + (1.0 - pclc) * (1.0 - e) : pclc;
+    zqc = llo1 ? zqc + zlude : zqc;
   }
 
   // compensating subsidence (:448-460)
   {
-    const double zfac1 = 1.0 / (c.rd * ztp1);
+    const double zfac1 = csc2_rcp(c.rd * ztp1);
     const double zrho = x.pap * zfac1;
-    const double zfac2 = 1.0 / (x.pap - c.retv * zfoeew);
+    const double zfac2 = csc2_rcp(x.pap - c.retv * zfoeew);
     const double zrodqsdp = -zrho * pqs * zfac2;
     const double zldcp = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;
-    const double zfac3 = 1.0 / (1.0 + zldcp * zdqsdtemp);
+    const double zfac3 = csc2_rcp(1.0 + zldcp * zdqsdtemp);
     const double dtdzmo = c.rg * (c.rcpd_inv - zldcp * zrodqsdp) * zfac3;
     const double zdqsdz = zdqsdtemp * dtdzmo - c.rg * zrodqsdp;
     const double zfac4 = c.rd * ztp1 * pap_inv;                  // 1/ZRHO
@@ -132,48 +136,42 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   double zcondl = (zqlwc - zl) * c.zqtmst;
   double zcondi = (zqiwc - zi) * c.zqtmst;
 
-  // melting of incoming snow (:487-498)
-  double zrfln = st.rfl, zsfln = st.sfl;
-  if (st.sfl != 0.0) {
-    const double zcons = c.zcons2 * zdp / zlfdcp;
+  // melting of incoming snow (:487-498); with ZSFL == 0 the statements reduce to the identity
+  double zrfln, zsfln;
+  {
+    const double zcons = c.zcons2 * zdp * csc2_rcp(zlfdcp);
     const double zsnmlt = dmin_(st.sfl, zcons * dmax_(0.0, ztp1 - c.zmeltp2));
     zrfln = st.rfl + zsnmlt;
     zsfln = st.sfl - zsnmlt;
-    ztp1 = ztp1 - zsnmlt / zcons;
+    ztp1 = ztp1 - zsnmlt * csc2_rcp(zcons);
   }
 
   // autoconversion liquid / ice (:504-534)
-  double zprr = 0.0, zprs = 0.0;
-  if (pclc > CSC2_ZEPS2) {
-    const double pclc_inv = 1.0 / pclc;
-    {
-      const double zcldl = zqlwc * pclc_inv;
-      const double rr = zcldl * c.rlcrit_inv;
-      const double zd = c.zckcodtl * (1.0 - exp(-(rr * rr)));
-      const double zlnew = pclc * zcldl * exp(-zd);
-      zprr = zqlwc - zlnew;
-      zqlwc = zqlwc - zprr;
-    }
-    {
-      const double zcldi = zqiwc * pclc_inv;
-      const double rr = zcldi * c.rlcrit_inv;
-      const double zd = c.zckcodti * exp(0.025 * (ztp1 - c.rtt)) * (1.0 - exp(-(rr * rr)));
-      const double zinew = pclc * zcldi * exp(-zd);
-      zprs = zqiwc - zinew;
-      zqiwc = zqiwc - zprs;
-    }
+  double zprr, zprs;
+  {
+    const bool cloudy = pclc > CSC2_ZEPS2;
+    const double pclc_inv = csc2_rcp(cloudy ? pclc : 1.0);
+    const double zcldl = zqlwc * pclc_inv;
+    const double rl = zcldl * c.rlcrit_inv;
+    const double zdl = c.zckcodtl * (1.0 - csc2_expn(-(rl * rl)));
+    const double zlnew = pclc * zcldl * csc2_exp(-zdl);
+    const double zcldi = zqiwc * pclc_inv;
+    const double rr = zcldi * c.rlcrit_inv;
+    const double zdi = c.zckcodti * csc2_exp(0.025 * (ztp1 - c.rtt)) * (1.0 - csc2_expn(-(rr * rr)));
+    const double zinew = pclc * zcldi * csc2_exp(-zdi);
+    zprr = cloudy ? zqlwc - zlnew : 0.0;
+    zprs = cloudy ? zqiwc - zinew : 0.0;
+    zqlwc = zqlwc - zprr;
+    zqiwc = zqiwc - zprs;
   }
 
   // new precipitation, rain/snow split on the post-melt T (:538-552)
   const double zc2dp = c.zcons2 * zdp;
   const double zdr = zc2dp * (zprr + zprs);
-  double zrfreeze = 0.0;
-  if (ztp1 < c.rtt) {
-    zrfreeze = zc2dp * zprr;
-    zsfln += zdr;
-  } else {
-    zrfln += zdr;
-  }
+  const bool frz1 = ztp1 < c.rtt;
+  double zrfreeze = frz1 ? zc2dp * zprr : 0.0;
+  zsfln += frz1 ? zdr : 0.0;
+  zrfln += frz1 ? 0.0 : zdr;
 
   // first-guess T and q after the tendencies (:601-618)
   const double zldcpw = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;   // as written at :609-610
@@ -193,14 +191,12 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   {
     const double zdq = dmax_(0.0, zqold - zqp1);
     const double zdr2 = zc2dp * zdq;
-    if (ztp1 < c.rtt) {
-      zrfreeze += zfwat * zdr2;
-      zcondi += zdq * c.zqtmst;
-      zsfln += zdr2;
-    } else {
-      zcondl += zdq * c.zqtmst;
-      zrfln += zdr2;
-    }
+    const bool frz2 = ztp1 < c.rtt;
+    zrfreeze += frz2 ? zfwat * zdr2 : 0.0;
+    zcondi += frz2 ? zdq * c.zqtmst : 0.0;
+    zcondl += frz2 ? 0.0 : zdq * c.zqtmst;
+    zsfln += frz2 ? zdr2 : 0.0;
+    zrfln += frz2 ? 0.0 : zdr2;
   }
 
   // final tendencies and fluxes (:694-716)

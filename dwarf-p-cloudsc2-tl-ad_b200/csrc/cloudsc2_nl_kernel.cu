@@ -125,7 +125,29 @@ __global__ void k_expand(const double *__restrict__ src, int nlon, long long row
   }
 }
 
+// accuracy probe of the branch-free elementary functions (tests/test_gpu_math.py)
+__global__ void k_math_probe(int fn, const double *__restrict__ x, double *__restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r, t;
+  switch (fn) {
+    case 0: r = csc2_rcp(v); break;
+    case 1: r = csc2_exp(v); break;
+    case 2: r = csc2_expn(v); break;
+    case 3: r = csc2_sqrt(v); break;
+    case 4: r = csc2_tanh_p1(v); break;
+    default: csc2_tanh_p1_sech2(v, t, r); break;
+  }
+  y[i] = r;
+}
+
 }  // namespace
+
+cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cudaStream_t s) {
+  k_math_probe<<<(n + 127) / 128, 128, 0, s>>>(fn, x, y, n);
+  return cudaGetLastError();
+}
 
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {

@@ -276,6 +276,15 @@ class Cloudsc2:
         self._check(self.lib.cloudsc2_gpu_expand_shard_dev(src_ptr, nlon, nlev, ndim, dst_ptr,
                                                            nproma, ngptot, gcol0, stream))
 
+    def math_probe(self, fn: int, x: np.ndarray) -> np.ndarray:
+        """Evaluate one of the kernels' elementary functions (csrc/cloudsc2_math.cuh) on the GPU."""
+        self._bind()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        self._check(self.lib.cloudsc2_gpu_math_probe(fn, x.ctypes.data_as(_abi.c_double_p),
+                                                     y.ctypes.data_as(_abi.c_double_p), x.size))
+        return y
+
     def pin(self, arr: np.ndarray):
         self._bind()
         self._check(self.lib.cloudsc2_gpu_host_register(arr.ctypes.data, arr.nbytes))

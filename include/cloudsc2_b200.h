@@ -178,6 +178,13 @@ int cloudsc2_gpu_sync(void);
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes);
 int cloudsc2_gpu_host_unregister(void *ptr);
 
+/* ---- diagnostics -------------------------------------------------------------------------- */
+/* Evaluate one of the kernels' branch-free FP64 elementary functions (csrc/cloudsc2_math.cuh,
+ * the replacements of the Fortran intrinsics EXP/TANH/COSH/SQRT and of "/" used by
+ * cloudsc2.F90) on n host values: fn 0 = 1/x, 1 = exp, 2 = exp clamped below, 3 = sqrt,
+ * 4 = tanh+1, 5 = 1/cosh^2.  Used by the accuracy tests only. */
+int cloudsc2_gpu_math_probe(int fn, const double *x, double *y, int n);
+
 #ifdef __cplusplus
 }
 #endif
