@@ -136,7 +136,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double zcor5 = csc2_rcp(1.0 - c.retv * zesdp5);
   const double zdqsdtemp5 = zfac5 * zcor5 * pqs5;
 
-  const double zcrh2 = crit_rh(crh, c.ceta[jk]);
+  const double zcrh2 = crit_rh(crh, c.ceta[jk], c.sq1mceta[jk]);
   const bool vcold = ztp25 < c.rtice;
   const double zsupsat5 = vcold ? (1.8 - 3.e-03 * ztp25) : 1.0;
   const double zqsat5 = pqs5 * zsupsat5;

@@ -58,6 +58,7 @@ template <bool RV, bool DOT>
 __global__ void __launch_bounds__(CSC2_AD_THREADS)
 k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const ADOpts opt) {
+  csc2_math_init();
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks || gcol >= g.ngptot) return;

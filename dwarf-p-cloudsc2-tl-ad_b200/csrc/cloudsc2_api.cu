@@ -95,12 +95,16 @@ KConst make_kconst(double ptsphy) {
   c.zqtmst = 1.0 / ptsphy;
   c.rlcrit_inv = 1.0 / (p.rclcrit * 2.0);
   c.rcpd_inv = 1.0 / p.rcpd;
+  c.rlmlt_inv = 1.0 / p.rlmlt;
+  c.zcons2_inv = ptsphy * p.rg;
+  c.zcor_cap = 1.0 / (1.0 - p.retv * CSC2_ZQMAX);
   c.lregcl = p.lregcl;
   c.klev = g.klev;
   c.kwin0 = g.kwin0;
   c.kwin1 = g.kwin1;
   std::memcpy(c.ceta, g.ceta, sizeof(double) * g.klev);
   std::memcpy(c.zscalm, g.zscalm, sizeof(double) * g.klev);
+  for (int k = 0; k < g.klev; ++k) c.sq1mceta[k] = std::sqrt(std::max(1.0 - g.ceta[k], 0.0));
   return c;
 }
 

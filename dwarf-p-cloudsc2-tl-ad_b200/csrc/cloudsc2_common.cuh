@@ -24,11 +24,15 @@ struct KConst {
   double ptsphy, zckcodtl, zckcodti, zckcodtla, zckcodtia, zcons2, zcons3, zmeltp2, zqtmst;
   double rlcrit_inv;       // 1 / (2*RCLCRIT)   (ZLCRIT, cloudsc2.F90:508,525)
   double rcpd_inv;         // 1 / RCPD
+  double rlmlt_inv;        // 1 / RLMLT
+  double zcons2_inv;       // PTSPHY * RG = 1 / ZCONS2
+  double zcor_cap;         // 1 / (1 - RETV*ZQMAX): ZCOR when ZESDP is capped (cloudsc2.F90:356,372)
   int lregcl;              // YRNCL%LREGCL
   int klev;
   int kwin0, kwin1;        // bounding range of levels with 0.1 < CETA < 0.4 (tropopause window)
   double ceta[CSC2_KLEV_MAX];    // YRECLD%CETA
   double zscalm[CSC2_KLEV_MAX];  // ZSCAL*MAX(CETA-0.2,ZEPS1)**0.2  (cloudsc2.F90:266)
+  double sq1mceta[CSC2_KLEV_MAX];  // SQRT(MAX(1-CETA,0)), factor of the lowest ZCRH2 segment (:398)
 };
 
 // Addressing of the blocked arrays: element (jl, jk, ibl) of a field with block stride bs is
@@ -83,7 +87,7 @@ __device__ __forceinline__ double satur_point(const KConst &c, double t, double 
 // Critical relative humidity profile (cloudsc2.F90:384-399).  zrh2 / zdeta1 depend only on the
 // column's ZTRPAUS and are hoisted out of the level loop by the callers.
 struct CritRH {
-  double zeta3, zrh2, zdeta1, zdeta1_inv;
+  double zeta3, zrh2, zdeta1, zrsq_deta1;
 };
 __device__ __forceinline__ CritRH make_critrh(double ztrpaus) {
   CritRH r;
@@ -91,14 +95,15 @@ __device__ __forceinline__ CritRH make_critrh(double ztrpaus) {
   double q = (ztrpaus - 0.25) / 0.15;
   r.zrh2 = 0.35 + 0.14 * (q * q) + 0.04 * dmin_(ztrpaus - 0.25, 0.0) / 0.15;
   r.zdeta1 = 0.09 + 0.16 * (0.4 - ztrpaus) / 0.3;
-  r.zdeta1_inv = 1.0 / r.zdeta1;
+  r.zrsq_deta1 = 1.0 / sqrt(r.zdeta1);
   return r;
 }
-__device__ __forceinline__ double crit_rh(const CritRH &r, double ceta) {
+// sq1mceta = SQRT(1-CETA) of the level: SQRT((1-CETA)/ZDETA1) = SQRT(1-CETA) / SQRT(ZDETA1)
+__device__ __forceinline__ double crit_rh(const CritRH &r, double ceta, double sq1mceta) {
   const double zdeta2 = 0.3;
-  // the four segments of cloudsc2.F90:388-399, selected without branches (ceta is warp-uniform)
+  // the four segments of cloudsc2.F90:388-399, selected without branches
   const double lin = 1.0 + (r.zrh2 - 1.0) * ((ceta - r.zeta3) * (1.0 / zdeta2));
-  const double low = 1.0 + (r.zrh2 - 1.0) * csc2_sqrt(dmax_(1.0 - ceta, 0.0) * r.zdeta1_inv);
+  const double low = 1.0 + (r.zrh2 - 1.0) * (sq1mceta * r.zrsq_deta1);
   double v = low;
   if (ceta < 1.0 - r.zdeta1) v = r.zrh2;
   if (ceta < r.zeta3 + zdeta2) v = lin;

@@ -7,8 +7,9 @@
 // 14 %) -- which also fence the scheduler's view and leave the dependent DFMA chains exposed
 // ("wait" stalls).  The functions below assume what the physics guarantees (finite arguments,
 // denominators well inside the normal range) and are straight-line code:
-//   csc2_rcp(x)   : MUFU.RCP64H seed + Newton refinement, no denormal / inf fix-up branch
-//   csc2_exp(x)   : Cody-Waite reduction + degree-11 minimax polynomial in two interleaved chains
+//   csc2_rcp(x)   : MUFU.RCP64H seed + one third-order step, no denormal / inf fix-up branch
+//   csc2_exp(x)   : Cody-Waite reduction to |r| <= ln2/32 with a 16-entry shared-memory table of
+//                   2^(j/16) + degree-6 minimax polynomial
 //   csc2_expn(x)  : same with the argument clamped below at -700 (exp(-700) = 1e-304 stands in
 //                   for underflow; used where the argument is -(something unbounded))
 //   csc2_sqrt(x)  : MUFU.RSQ64H seed + coupled Newton (Goldschmidt) iteration, x = 0 -> 0
@@ -20,55 +21,66 @@
 #pragma once
 #include <cuda_runtime.h>
 
-// polynomial coefficients live in the constant bank so that DFMA takes them as c[bank][off]
-// operands (no UMOV pairs).  exp(r) = 1 + r + r^2 P(r) on |r| <= ln2/2, P of degree 9 from a
-// Remez exchange on the relative error of exp (tools/gen_exp_coeffs.py 11): 1.1e-17 with the
-// coefficients rounded to double.
-static __constant__ double csc2_expc[10] = {
-    5.00000000000001110e-01, 1.66666666666664132e-01, 4.16666666665301555e-02,
-    8.33333333349446127e-03, 1.38888889436301140e-03, 1.98412695065786879e-04,
-    2.48014930989065504e-05, 2.75575863738401650e-06, 2.76302483792114415e-07,
-    2.50000616028356664e-08};
+// exp(x) = 2^k * 2^(j/16) * exp(r), n = 16 k + j = nearest integer to 16 x / ln2, |r| <= ln2/32.
+//  * 2^(j/16) comes from a 16-entry table in SHARED memory: 16 doubles cover the 32 banks exactly
+//    once, so any pattern of per-lane indices is conflict-free (equal indices broadcast);
+//  * exp(r) = 1 + r + r^2 P(r), P of degree 4 from a Remez exchange on the relative error of exp
+//    (tools/gen_exp_coeffs.py 6 16): 1.2e-17;
+//  * 11 FP64-pipe instructions instead of 16 for the table-free degree-11 form -- the kernels are
+//    FP64-issue bound and spend a third of their FP64 work in exp.
+// Polynomial coefficients live in the constant bank so that DFMA takes them as c[bank][off]
+// operands (no 64-bit immediates / UMOV pairs).
+static __constant__ double csc2_expc[5] = {
+    4.99999999999996059e-01, 1.66666666644170708e-01, 4.16666666932605373e-02,
+    8.33347194847556573e-03, 1.38885940074739067e-03};
+static __constant__ double csc2_exptab_c[16] = {
+    1.00000000000000000e+00, 1.04427378242741375e+00, 1.09050773266525769e+00,
+    1.13878863475669156e+00, 1.18920711500272103e+00, 1.24185781207348400e+00,
+    1.29683955465100964e+00, 1.35425554693689265e+00, 1.41421356237309515e+00,
+    1.47682614593949935e+00, 1.54221082540794074e+00, 1.61049033194925428e+00,
+    1.68179283050742900e+00, 1.75625216037329945e+00, 1.83400808640934243e+00,
+    1.91520656139714740e+00};
+__shared__ double csc2_exptab[16];
 
-// 1/x: the MUFU.RCP64H seed works on the high word of x (relative error ~2^-20 .. 2^-23); two
-// quadratic Newton steps take it below 2^-70, the last FMA rounds to <= 1 ulp.
+// Every kernel that evaluates csc2_exp calls this once, with ALL threads of the CTA, before any
+// thread may exit.
+__device__ __forceinline__ void csc2_math_init() {
+  if (threadIdx.x < 16) csc2_exptab[threadIdx.x] = csc2_exptab_c[threadIdx.x];
+  __syncthreads();
+}
+
+// 1/x: the MUFU.RCP64H seed works on the high word of x (relative error e ~ 2^-20 .. 2^-23); one
+// third-order step y (1 + e + e^2) leaves e^3 < 2^-60, the final FMA rounds to <= 1 ulp.
 __device__ __forceinline__ double csc2_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RCP64H
   double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
   return fma(y, e, y);
 }
 __device__ __forceinline__ double csc2_div(double a, double b) { return a * csc2_rcp(b); }
 
 // exp for arguments known to lie in [-700, 700]
 __device__ __forceinline__ double csc2_exp(double x) {
-  // k = nearest integer to x*log2(e) via the 1.5*2^52 shift; its low word is k as int32
+  // n = nearest integer to x*16/ln2 via the 1.5*2^52 shift; its low word is n as int32
   const double shift = 6755399441055744.0;
-  const double t = fma(x, 1.4426950408889634, shift);
-  const int k = __double2loint(t);
+  const double t = fma(x, 2.30831206542234142e+01, shift);
+  const int n = __double2loint(t);
   const double kd = t - shift;
-  // r = x - k*ln2 in two pieces (ln2_hi has 21 trailing zero bits: k*ln2_hi is exact)
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
+  const double tab = csc2_exptab[n & 15];
+  // r = x - n*ln2/16 in two pieces (the high piece has 21 trailing zero bits: n*hi is exact)
+  double r = fma(kd, -4.33216987730702385306e-02, x);
+  r = fma(kd, -1.19263433079411731251e-11, r);
   const double r2 = r * r;
-  // P(r) = E(r2) + r O(r2) in two interleaved Horner chains
-  double pe = csc2_expc[8];
-  double po = csc2_expc[9];
-  pe = fma(pe, r2, csc2_expc[6]);
-  po = fma(po, r2, csc2_expc[7]);
-  pe = fma(pe, r2, csc2_expc[4]);
-  po = fma(po, r2, csc2_expc[5]);
-  pe = fma(pe, r2, csc2_expc[2]);
-  po = fma(po, r2, csc2_expc[3]);
-  pe = fma(pe, r2, csc2_expc[0]);
-  po = fma(po, r2, csc2_expc[1]);
-  const double q = fma(po, r, pe);
-  const double p = fma(q, r2, r) + 1.0;
-  // scale by 2^k: add k to the exponent field (|k| <= 1010 keeps the result normal)
-  const int hi = __double2hiint(p) + (k << 20);
-  return __hiloint2double(hi, __double2loint(p));
+  const double pa = fma(csc2_expc[1], r, csc2_expc[0]);
+  double pb = fma(csc2_expc[3], r, csc2_expc[2]);
+  pb = fma(csc2_expc[4], r2, pb);
+  const double q = fma(pb, r2, pa);
+  const double p = fma(q, r2, r);               // exp(r) - 1
+  const double v = fma(tab, p, tab);            // in [0.97, 1.96]
+  // scale by 2^k: add k to the exponent field (|k| <= 1011 keeps the result normal)
+  const int hi = __double2hiint(v) + ((n >> 4) << 20);
+  return __hiloint2double(hi, __double2loint(v));
 }
 // exp for arguments <= 0 of unbounded magnitude
 __device__ __forceinline__ double csc2_expn(double x) { return csc2_exp(fmax(x, -700.0)); }

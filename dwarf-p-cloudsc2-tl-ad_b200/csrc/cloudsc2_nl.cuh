@@ -76,14 +76,16 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   const double rw = csc2_rcp(ztp1 - c.r4les), ri = csc2_rcp(ztp1 - c.r4ies);
   const double zfwat = cold ? 0.545 * csc2_tanh_p1(0.17 * (ztp1 - c.rlptrc)) : 1.0;
   const double zfoeew = c.r2es * csc2_exp((cold ? c.r3ies * ri : c.r3les * rw) * (ztp1 - c.rtt));
-  const double zesdp = dmin_(zfoeew * pap_inv, CSC2_ZQMAX);
   const double zfacw = c.r5les * (rw * rw), zfaci = c.r5ies * (ri * ri);
   const double zfac = zfwat * zfacw + (1.0 - zfwat) * zfaci;
-  const double zcor = csc2_rcp(1.0 - c.retv * zesdp);
+  // ZCOR = 1/(1-RETV*ZESDP) with ZESDP = MIN(ZFOEEW/PAPP1, ZQMAX) shares the reciprocal of the
+  // subsidence section: 1/(1-RETV*ZFOEEW/PAPP1) = PAPP1 * ZFAC2, ZFAC2 = 1/(PAPP1-RETV*ZFOEEW) (:451)
+  const double zfac2 = csc2_rcp(x.pap - c.retv * zfoeew);
+  const double zcor = (zfoeew * pap_inv > CSC2_ZQMAX) ? c.zcor_cap : x.pap * zfac2;
   const double zdqsdtemp = zfac * zcor * pqs;
 
   // critical humidity, ice supersaturation (:384-408)
-  const double zcrh2 = crit_rh(crh, c.ceta[jk]);
+  const double zcrh2 = crit_rh(crh, c.ceta[jk], c.sq1mceta[jk]);
   const double zsupsat = (ztp1 < c.rtice) ? (1.8 - 3.e-03 * ztp1) : 1.0;
   const double zqsat = pqs * zsupsat;
   const double zqcrit = zcrh2 * zqsat;
@@ -119,7 +121,6 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   {
     const double zfac1 = csc2_rcp(c.rd * ztp1);
     const double zrho = x.pap * zfac1;
-    const double zfac2 = csc2_rcp(x.pap - c.retv * zfoeew);
     const double zrodqsdp = -zrho * pqs * zfac2;
     const double zldcp = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;
     const double zfac3 = csc2_rcp(1.0 + zldcp * zdqsdtemp);
@@ -139,11 +140,15 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   // melting of incoming snow (:487-498); with ZSFL == 0 the statements reduce to the identity
   double zrfln, zsfln;
   {
-    const double zcons = c.zcons2 * zdp * csc2_rcp(zlfdcp);
+    // ZCONS = ZCONS2*ZDP/ZLFDCP and its inverse without a division: 1/ZLFDCP = (1/RLMLT)/ZZZ
+    const double zzz_inv = (c.rvtmp2 != 0.0) ? c.rcpd + c.rcpd * c.rvtmp2 * zqp1 : c.rcpd;
+    const double lf_inv = c.rlmlt_inv * zzz_inv;
+    const double zcons = c.zcons2 * zdp * lf_inv;
+    const double zcons_inv = c.zcons2_inv * zdp_inv * zlfdcp;
     const double zsnmlt = dmin_(st.sfl, zcons * dmax_(0.0, ztp1 - c.zmeltp2));
     zrfln = st.rfl + zsnmlt;
     zsfln = st.sfl - zsnmlt;
-    ztp1 = ztp1 - zsnmlt * csc2_rcp(zcons);
+    ztp1 = ztp1 - zsnmlt * zcons_inv;
   }
 
   // autoconversion liquid / ice (:504-534)

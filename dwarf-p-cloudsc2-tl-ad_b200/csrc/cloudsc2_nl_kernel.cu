@@ -6,7 +6,10 @@
 // the next level's 15 inputs prefetched while the current level is computed.  Loads/stores are
 // coalesced along NPROMA (JL); every input is read exactly once (plus the ~40-level tropopause
 // pre-pass over PT/PGTENT, which the main sweep re-reads out of L2), PQSAT never touches memory.
+#include <cstdlib>
+
 #include "cloudsc2_nl.cuh"
+#include "cloudsc2_stage.cuh"
 #include "cloudsc2_launch.h"
 
 namespace {
@@ -14,47 +17,56 @@ namespace {
 __device__ __forceinline__ double ldin(const double *p) { return __ldg(p); }
 __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 
-struct ColOffsets {
-  size_t o1, oh, ocld, ocml, oloc;
-};
+constexpr int NL_NF = 16;      // staged fields per level: 15 inputs + optional PQS
 
-__device__ __forceinline__ LevIn load_level(const TrajIn &in, const ColOffsets &o, int jk, int klev,
-                                            int nproma) {
-  LevIn x;
+// issue the asynchronous copies of level jk of this thread's column into ring slot `slot`
+template <bool HAS_PQS, int NT>
+__device__ __forceinline__ void stage_level(double *ring, int slot, const TrajIn &in,
+                                            const ColOffsets &o, int jk, int klev, int nproma) {
+  double *d = ring + (size_t)slot * (NL_NF * NT);
   const size_t l = (size_t)jk * nproma;
-  x.paph1 = ldin(in.paph + o.oh + l + nproma);
-  x.pap = ldin(in.pap + o.o1 + l);
-  x.pt = ldin(in.pt + o.o1 + l);
-  x.pq = ldin(in.pq + o.o1 + l);
-  x.pl = ldin(in.pl + o.ocld + l);
-  x.pi = ldin(in.pi + o.ocld + l);
-  x.plude = ldin(in.plude + o.o1 + l);
-  x.plu1 = (jk < klev - 1) ? ldin(in.plu + o.o1 + l + nproma) : 0.0;
-  x.pmfu = ldin(in.pmfu + o.o1 + l);
-  x.pmfd = ldin(in.pmfd + o.o1 + l);
-  x.gt = ldin(in.gt + o.ocml + l);
-  x.gq = ldin(in.gq + o.ocml + l);
-  x.gl = ldin(in.gl + o.ocml + l);
-  x.gi = ldin(in.gi + o.ocml + l);
-  x.psupsat = ldin(in.psupsat + o.o1 + l);
+  csc2_cp_async8(d + 0 * NT, in.paph + o.oh + l + nproma);
+  csc2_cp_async8(d + 1 * NT, in.pap + o.o1 + l);
+  csc2_cp_async8(d + 2 * NT, in.pt + o.o1 + l);
+  csc2_cp_async8(d + 3 * NT, in.pq + o.o1 + l);
+  csc2_cp_async8(d + 4 * NT, in.pl + o.ocld + l);
+  csc2_cp_async8(d + 5 * NT, in.pi + o.ocld + l);
+  csc2_cp_async8(d + 6 * NT, in.plude + o.o1 + l);
+  if (jk < klev - 1) csc2_cp_async8(d + 7 * NT, in.plu + o.o1 + l + nproma);
+  csc2_cp_async8(d + 8 * NT, in.pmfu + o.o1 + l);
+  csc2_cp_async8(d + 9 * NT, in.pmfd + o.o1 + l);
+  csc2_cp_async8(d + 10 * NT, in.gt + o.ocml + l);
+  csc2_cp_async8(d + 11 * NT, in.gq + o.ocml + l);
+  csc2_cp_async8(d + 12 * NT, in.gl + o.ocml + l);
+  csc2_cp_async8(d + 13 * NT, in.gi + o.ocml + l);
+  csc2_cp_async8(d + 14 * NT, in.psupsat + o.o1 + l);
+  if (HAS_PQS) csc2_cp_async8(d + 15 * NT, in.pqs + o.o1 + l);
+}
+template <int NT>
+__device__ __forceinline__ LevIn read_level(const double *ring, int slot, int jk, int klev) {
+  const double *d = ring + (size_t)slot * (NL_NF * NT);
+  LevIn x;
+  x.paph1 = d[0 * NT]; x.pap = d[1 * NT]; x.pt = d[2 * NT]; x.pq = d[3 * NT]; x.pl = d[4 * NT];
+  x.pi = d[5 * NT]; x.plude = d[6 * NT];
+  x.plu1 = (jk < klev - 1) ? d[7 * NT] : 0.0;
+  x.pmfu = d[8 * NT]; x.pmfd = d[9 * NT]; x.gt = d[10 * NT]; x.gq = d[11 * NT]; x.gl = d[12 * NT];
+  x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
   return x;
 }
 
-template <bool HAS_PQS>
-__global__ void __launch_bounds__(CSC2_NL_THREADS)
+// STAGES = depth of the shared-memory ring (levels in flight + the one being computed)
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out) {
+  extern __shared__ double ring_all[];
+  double *ring = ring_all + threadIdx.x;
+  csc2_math_init();
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks) return;
   const int jl = gcol - ibl * g.nproma;
   const int klev = g.klev, nproma = g.nproma;
-  const size_t n2 = (size_t)nproma * klev;
-  ColOffsets o;
-  o.o1 = (size_t)ibl * n2 + jl;
-  o.oh = (size_t)ibl * (n2 + nproma) + jl;
-  o.ocld = (size_t)ibl * in.bs_cld + jl;
-  o.ocml = (size_t)ibl * in.bs_cml + jl;
-  o.oloc = (size_t)ibl * out.bs_loc + jl;
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
 
   if (gcol >= g.ngptot) {
     // padding column of the last block: the driver zeroes whole blocks (driver_mod.F90:87-88),
@@ -64,6 +76,13 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
       if (out.loc_last) stout(out.loc_last + o.oloc + (size_t)jk * nproma, 0.0);
     }
     return;
+  }
+
+  // start the pipeline before the tropopause pre-pass so that its latency is covered
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < klev) stage_level<HAS_PQS, NT>(ring, s, in, o, s, klev, nproma);
+    csc2_cp_async_commit();
   }
 
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
@@ -78,16 +97,15 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
   stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
 
-  LevIn cur = load_level(in, o, 0, klev, nproma);
-  double pqs_cur = HAS_PQS ? ldin(in.pqs + o.o1) : 0.0;
+  int slot = 0, pslot = STAGES - 1;
   for (int jk = 0; jk < klev; ++jk) {
-    LevIn nxt = cur;
-    double pqs_nxt = 0.0;
-    if (jk + 1 < klev) {
-      nxt = load_level(in, o, jk + 1, klev, nproma);
-      if (HAS_PQS) pqs_nxt = ldin(in.pqs + o.o1 + (size_t)(jk + 1) * nproma);
-    }
-    const double pqs = HAS_PQS ? pqs_cur : satur_point(c, cur.pt, 1.0 / cur.pap);
+    const int pf = jk + STAGES - 1;
+    if (pf < klev) stage_level<HAS_PQS, NT>(ring, pslot, in, o, pf, klev, nproma);
+    csc2_cp_async_commit();
+    csc2_cp_async_wait<STAGES - 1>();
+    const LevIn cur = read_level<NT>(ring, slot, jk, klev);
+    const double pqs = HAS_PQS ? ring[(size_t)slot * (NL_NF * NT) + 15 * NT]
+                               : satur_point(c, cur.pt, csc2_rcp(cur.pap));
     LevOut y;
     nl_level(c, crh, jk, cur, pqs, st, y);
 
@@ -103,8 +121,8 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     stout(out.pfplsn + o.oh + l + nproma, y.sfln);
     stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);   // cloudsc2.F90:730-735
     stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
-    cur = nxt;
-    pqs_cur = pqs_nxt;
+    slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+    pslot = (pslot + 1 == STAGES) ? 0 : pslot + 1;
   }
 }
 
@@ -127,6 +145,7 @@ __global__ void k_expand(const double *__restrict__ src, int nlon, long long row
 
 // accuracy probe of the branch-free elementary functions (tests/test_gpu_math.py)
 __global__ void k_math_probe(int fn, const double *__restrict__ x, double *__restrict__ y, int n) {
+  csc2_math_init();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
@@ -149,13 +168,46 @@ cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cu
   return cudaGetLastError();
 }
 
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
+static cudaError_t launch_nl_variant(const KConst &c, const Geom &g, const TrajIn &in,
+                                     const TrajOut &out, cudaStream_t s) {
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  const int grid = (int)((ncol + NT - 1) / NT);
+  const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double);
+  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, NT, smem, s>>>(c, g, in, out);
+  return cudaGetLastError();
+}
+
+// CSC2_NL_VARIANT (tuning knob, read once): CTA size / CTAs per SM / ring depth
+static int nl_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CSC2_NL_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {
-  const long long ncol = (long long)g.nblocks * g.nproma;
-  const int grid = (int)((ncol + CSC2_NL_THREADS - 1) / CSC2_NL_THREADS);
-  if (in.pqs) k_cloudsc2_nl<true><<<grid, CSC2_NL_THREADS, 0, s>>>(c, g, in, out);
-  else k_cloudsc2_nl<false><<<grid, CSC2_NL_THREADS, 0, s>>>(c, g, in, out);
-  return cudaGetLastError();
+  if (in.pqs) return launch_nl_variant<true, 2, 128, 168>(c, g, in, out, s);
+  switch (nl_variant()) {   //                     stages, threads/CTA, registers -> warps per SM
+    case 1: return launch_nl_variant<false, 3, 128, 168>(c, g, in, out, s);   // 12
+    case 2: return launch_nl_variant<false, 2, 128, 128>(c, g, in, out, s);   // 16
+    case 3: return launch_nl_variant<false, 2, 64, 144>(c, g, in, out, s);    // 14
+    case 4: return launch_nl_variant<false, 2, 128, 96>(c, g, in, out, s);    // 20
+    case 5: return launch_nl_variant<false, 2, 96, 112>(c, g, in, out, s);    // 18
+    case 6: return launch_nl_variant<false, 2, 64, 112>(c, g, in, out, s);    // 18
+    case 7: return launch_nl_variant<false, 2, 64, 104>(c, g, in, out, s);    // 18 (19 by regs)
+    default: return launch_nl_variant<false, 2, 128, 168>(c, g, in, out, s);  // 12
+  }
 }
 
 cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,

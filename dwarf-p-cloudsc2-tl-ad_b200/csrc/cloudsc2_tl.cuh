@@ -105,7 +105,7 @@ __device__ __forceinline__ void tl_level(const KConst &c, const CritRH &crh, int
   const double zdqsdtemp5 = zfac5 * zcor5 * pqs5;
 
   // critical humidity, ice supersaturation (:505-539)
-  const double zcrh2 = crit_rh(crh, c.ceta[jk]);
+  const double zcrh2 = crit_rh(crh, c.ceta[jk], c.sq1mceta[jk]);
   const bool vcold = ztp15 < c.rtice;
   const double zsupsat5 = vcold ? 1.8 - 3.e-03 * ztp15 : 1.0;
   const double zsupsat = vcold ? -3.e-03 * ztp1 : 0.0;

@@ -89,6 +89,7 @@ template <bool ONFLY>
 __global__ void __launch_bounds__(CSC2_TL_THREADS)
 k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const TLOpts opt) {
+  csc2_math_init();
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks || gcol >= g.ngptot) return;
@@ -174,6 +175,7 @@ __device__ __forceinline__ double pert(double x, double lam) { return x + lam * 
 __global__ void __launch_bounds__(CSC2_NL_THREADS)
 k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut base,
             const Lambdas lams, double *__restrict__ diffsum, const long long ncol_pad) {
+  csc2_math_init();
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks || gcol >= g.ngptot) return;

@@ -4,15 +4,17 @@
 exp(r) = 1 + r + r^2 * P(r) on |r| <= ln2/2 with P of degree DEG-2 obtained by a Remez exchange
 (minimax in RELATIVE error of exp) carried out in 60-digit arithmetic with mpmath; coefficients
 are then rounded to double and the achieved error re-measured with the rounded values.
-Run:  python tools/gen_exp_coeffs.py [DEG]      (prints a C initialiser)
+With a table of NTAB entries 2^(j/NTAB) the reduced argument satisfies |r| <= ln2/(2 NTAB).
+Run:  python tools/gen_exp_coeffs.py [DEG [NTAB]]      (prints C initialisers)
 """
 import sys
 import mpmath as mp
 
 mp.mp.dps = 60
 DEG = int(sys.argv[1]) if len(sys.argv) > 1 else 11
+NTAB = int(sys.argv[2]) if len(sys.argv) > 2 else 1     # table size: |r| <= ln2 / (2 NTAB)
 N = DEG - 2 + 1            # number of coefficients of P
-B = mp.log(2) / 2 * mp.mpf("1.0001")
+B = mp.log(2) / (2 * NTAB) * mp.mpf("1.0001")
 
 
 def f(r):                  # target for P: (exp(r) - 1 - r) / r^2
@@ -78,3 +80,15 @@ cd = [float(x) for x in c]
 worst = max(abs(err([mp.mpf(v) for v in cd], -B + 2 * B * k / 2000)) for k in range(2001))
 print(f"// degree {DEG}: minimax relative error {float(abs(E)):.3e}, with double coefficients {float(worst):.3e}")
 print("{" + ", ".join(f"{v:.17e}" for v in cd) + "}")
+
+if NTAB > 1:
+    print(f"// 2^(j/{NTAB}), j = 0..{NTAB - 1}, correctly rounded")
+    print("{" + ", ".join(f"{float(mp.mpf(2) ** (mp.mpf(j) / NTAB)):.17e}" for j in range(NTAB)) + "}")
+    l2 = mp.log(2) / NTAB
+    hi = float(l2)
+    # ln2/NTAB split: hi with 21 trailing zero bits so that k*hi is exact for |k| < 2^21
+    import struct
+    bits = struct.unpack("<Q", struct.pack("<d", hi))[0] & ~((1 << 21) - 1)
+    hi = struct.unpack("<d", struct.pack("<Q", bits))[0]
+    lo = float(l2 - mp.mpf(hi))
+    print(f"// ln2/{NTAB} = hi + lo : {hi:.20e} {lo:.20e} ; {NTAB}/ln2 = {float(NTAB / mp.log(2)):.17e}")
