@@ -13,6 +13,7 @@
 //            or contracted on the fly with dx = dot_scale * x for the adjoint test (ZNORM2).
 // Output adjoints are consumed AND zeroed as the reference does (:917-919, :955-966, :1678-1690).
 #include "cloudsc2_ad.cuh"
+#include "cloudsc2_stage.cuh"
 #include "cloudsc2_launch.h"
 
 namespace {
@@ -20,64 +21,76 @@ namespace {
 __device__ __forceinline__ double ldin(const double *p) { return __ldg(p); }
 __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 
-struct ColOffsets {
-  size_t o1, oh, ocld, ocml, oloc;
-};
+constexpr int NT = CSC2_AD_THREADS;
+// fields staged per level: 15 trajectory inputs, PQS (optional), 2 check-points, 9 output adjoints
+constexpr int AD_NF = 27;
+constexpr int AD_STAGES = 2;
 
-__device__ __forceinline__ LevIn load_level(const TrajIn &in, const ColOffsets &o, int jk, int klev,
-                                            int nproma) {
-  LevIn x;
+// Asynchronous copies of the trajectory inputs of level jk into a ring slot.  LOWER selects which
+// half-level pressure goes to field 0: PAPHP1(JK+1) for the forward sweep, PAPHP1(JK) for the
+// reverse sweep (which carries PAPHP1(JK+1) over from the level it has just finished).
+template <bool LOWER>
+__device__ __forceinline__ void stage_traj(double *d, const TrajIn &in, const ColOffsets &o, int jk,
+                                           int klev, int nproma) {
   const size_t l = (size_t)jk * nproma;
-  x.paph1 = ldin(in.paph + o.oh + l + nproma);
-  x.pap = ldin(in.pap + o.o1 + l);
-  x.pt = ldin(in.pt + o.o1 + l);
-  x.pq = ldin(in.pq + o.o1 + l);
-  x.pl = ldin(in.pl + o.ocld + l);
-  x.pi = ldin(in.pi + o.ocld + l);
-  x.plude = ldin(in.plude + o.o1 + l);
-  x.plu1 = (jk < klev - 1) ? ldin(in.plu + o.o1 + l + nproma) : 0.0;
-  x.pmfu = ldin(in.pmfu + o.o1 + l);
-  x.pmfd = ldin(in.pmfd + o.o1 + l);
-  x.gt = ldin(in.gt + o.ocml + l);
-  x.gq = ldin(in.gq + o.ocml + l);
-  x.gl = ldin(in.gl + o.ocml + l);
-  x.gi = ldin(in.gi + o.ocml + l);
-  x.psupsat = ldin(in.psupsat + o.o1 + l);
+  csc2_cp_async8(d + 0 * NT, in.paph + o.oh + l + (LOWER ? 0 : nproma));
+  csc2_cp_async8(d + 1 * NT, in.pap + o.o1 + l);
+  csc2_cp_async8(d + 2 * NT, in.pt + o.o1 + l);
+  csc2_cp_async8(d + 3 * NT, in.pq + o.o1 + l);
+  csc2_cp_async8(d + 4 * NT, in.pl + o.ocld + l);
+  csc2_cp_async8(d + 5 * NT, in.pi + o.ocld + l);
+  csc2_cp_async8(d + 6 * NT, in.plude + o.o1 + l);
+  if (jk < klev - 1) csc2_cp_async8(d + 7 * NT, in.plu + o.o1 + l + nproma);
+  csc2_cp_async8(d + 8 * NT, in.pmfu + o.o1 + l);
+  csc2_cp_async8(d + 9 * NT, in.pmfd + o.o1 + l);
+  csc2_cp_async8(d + 10 * NT, in.gt + o.ocml + l);
+  csc2_cp_async8(d + 11 * NT, in.gq + o.ocml + l);
+  csc2_cp_async8(d + 12 * NT, in.gl + o.ocml + l);
+  csc2_cp_async8(d + 13 * NT, in.gi + o.ocml + l);
+  csc2_cp_async8(d + 14 * NT, in.psupsat + o.o1 + l);
+  if (in.pqs) csc2_cp_async8(d + 15 * NT, in.pqs + o.o1 + l);
+}
+// field 0 is returned through `paph`, LevIn::paph1 is left to the caller
+__device__ __forceinline__ LevIn read_traj(const double *d, int jk, int klev, double &paph) {
+  LevIn x;
+  paph = d[0 * NT];
+  x.pap = d[1 * NT]; x.pt = d[2 * NT]; x.pq = d[3 * NT]; x.pl = d[4 * NT];
+  x.pi = d[5 * NT]; x.plude = d[6 * NT];
+  x.plu1 = (jk < klev - 1) ? d[7 * NT] : 0.0;
+  x.pmfu = d[8 * NT]; x.pmfd = d[9 * NT]; x.gt = d[10 * NT]; x.gq = d[11 * NT]; x.gl = d[12 * NT];
+  x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
   return x;
 }
 
-// read-and-zero of an output adjoint (plain loads: the arrays are read-write in this kernel)
-__device__ __forceinline__ double take(double *p) {
-  const double v = *p;
-  *p = 0.0;
-  return v;
-}
-__device__ __forceinline__ void acc(double *p, double v) { *p += v; }
+// input-adjoint accumulation X = X + dX as a fire-and-forget reduction at the L2 (RED.ADD.F64):
+// no load latency on the thread's critical path, same DRAM traffic as a read-modify-write
+__device__ __forceinline__ void acc(double *p, double v) { atomicAdd(p, v); }
 
 template <bool RV, bool DOT>
 __global__ void __launch_bounds__(CSC2_AD_THREADS)
 k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const ADOpts opt) {
+  extern __shared__ double ring_all[];
+  double *ring = ring_all + threadIdx.x;
   csc2_math_init();
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks || gcol >= g.ngptot) return;
   const int jl = gcol - ibl * g.nproma;
   const int klev = g.klev, nproma = g.nproma;
-  const size_t n2 = (size_t)nproma * klev;
-  ColOffsets o;
-  o.o1 = (size_t)ibl * n2 + jl;
-  o.oh = (size_t)ibl * (n2 + nproma) + jl;
-  o.ocld = (size_t)ibl * in.bs_cld + jl;
-  o.ocml = (size_t)ibl * in.bs_cml + jl;
-  o.oloc = (size_t)ibl * out.bs_loc + jl;
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
   double *ck_r = opt.ckpt + gcol;                                   // [klev][ncol_pad] rain
   double *ck_s = opt.ckpt + (size_t)klev * opt.ncol_pad + gcol;     // [klev][ncol_pad] snow
   const size_t cks = (size_t)opt.ncol_pad;
+  constexpr int SLOT = AD_NF * NT;
+
+  stage_traj<false>(ring, in, o, 0, klev, nproma);
+  csc2_cp_async_commit();
 
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
 
   // ------------------------------ forward (trajectory) sweep --------------------------------
+  double rfl_last, sfl_last;     // flux entering the lowest level: stays in registers
   {
     Carry st;
     st.paph0 = ldin(in.paph + o.oh);
@@ -89,14 +102,20 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
       stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
       stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
     }
-    LevIn cur = load_level(in, o, 0, klev, nproma);
+    int slot = 0;
     for (int jk = 0; jk < klev; ++jk) {
-      LevIn nxt = cur;
-      if (jk + 1 < klev) nxt = load_level(in, o, jk + 1, klev, nproma);
+      if (jk + 1 < klev) stage_traj<false>(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
+      csc2_cp_async_commit();
+      csc2_cp_async_wait<1>();
+      const double *d = ring + slot * SLOT;
+      double paph1;
+      LevIn cur = read_traj(d, jk, klev, paph1);
+      cur.paph1 = paph1;
       ck_r[(size_t)jk * cks] = st.rfl;
       ck_s[(size_t)jk * cks] = st.sfl;
-      const double pqs = in.pqs ? ldin(in.pqs + o.o1 + (size_t)jk * nproma)
-                                : satur_point(c, cur.pt, 1.0 / cur.pap);
+      rfl_last = st.rfl;
+      sfl_last = st.sfl;
+      const double pqs = in.pqs ? d[15 * NT] : satur_point(c, cur.pt, csc2_rcp(cur.pap));
       LevOut y;
       nl_level(c, crh, jk, cur, pqs, st, y);
       if (opt.write_traj) {
@@ -112,35 +131,67 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
         stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);
         stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
       }
-      cur = nxt;
+      slot ^= 1;
     }
   }
 
   // ---------------------------------- reverse sweep ---------------------------------------------
+  // per level: trajectory inputs + the flux check-point + the 9 output adjoints, all staged one
+  // level ahead; output adjoints are zeroed only after their staged copy has landed.
+  auto stage_rev = [&](double *d, int jk) {
+    const size_t l = (size_t)jk * nproma;
+    stage_traj<true>(d, in, o, jk, klev, nproma);
+    csc2_cp_async8(d + 16 * NT, ck_r + (size_t)jk * cks);
+    csc2_cp_async8(d + 17 * NT, ck_s + (size_t)jk * cks);
+    csc2_cp_async8(d + 18 * NT, dout.tent + o.o1 + l);
+    csc2_cp_async8(d + 19 * NT, dout.tenq + o.o1 + l);
+    csc2_cp_async8(d + 20 * NT, dout.tenl + o.o1 + l);
+    csc2_cp_async8(d + 21 * NT, dout.teni + o.o1 + l);
+    csc2_cp_async8(d + 22 * NT, dout.pclc + o.o1 + l);
+    csc2_cp_async8(d + 23 * NT, dout.pfplsl + o.oh + l + nproma);
+    csc2_cp_async8(d + 24 * NT, dout.pfplsn + o.oh + l + nproma);
+    csc2_cp_async8(d + 25 * NT, dout.pfhpsl + o.oh + l + nproma);
+    csc2_cp_async8(d + 26 * NT, dout.pfhpsn + o.oh + l + nproma);
+  };
+  csc2_cp_async_wait<0>();
+  stage_rev(ring, klev - 1);
+  csc2_cp_async_commit();
+
   CarryAD ca;
   ca.rfl = 0.0;
   ca.sfl = 0.0;
   double paph_pending = 0.0;     // contribution of level JK+1 to PAPHP1(JK+1), not yet written
+  double paph_hi5 = ldin(in.paph + o.oh + (size_t)klev * nproma);   // PAPHP15(JK+1)
   double dot = 0.0;
   const double ds = opt.dot_scale;
   const bool zero_sup = opt.zero_psupsat_pert != 0;
+  int slot = 0;
   for (int jk = klev - 1; jk >= 0; --jk) {
     const size_t l = (size_t)jk * nproma;
-    const LevIn x5 = load_level(in, o, jk, klev, nproma);
-    const double paph0 = ldin(in.paph + o.oh + l);
-    const double pqs5 = in.pqs ? ldin(in.pqs + o.o1 + l) : satur_point(c, x5.pt, 1.0 / x5.pap);
-    const double rfl5 = ck_r[(size_t)jk * cks];
-    const double sfl5 = ck_s[(size_t)jk * cks];
+    if (jk > 0) stage_rev(ring + (slot ^ 1) * SLOT, jk - 1);
+    csc2_cp_async_commit();
+    csc2_cp_async_wait<1>();
+    const double *d = ring + slot * SLOT;
+    double paph0;
+    LevIn x5 = read_traj(d, jk, klev, paph0);
+    x5.paph1 = paph_hi5;
+    const double pqs5 = in.pqs ? d[15 * NT] : satur_point(c, x5.pt, csc2_rcp(x5.pap));
+    const double rfl5 = (jk == klev - 1) ? rfl_last : d[16 * NT];
+    const double sfl5 = (jk == klev - 1) ? sfl_last : d[17 * NT];
     LevAdjIn ya;
-    ya.tent = take(dout.tent + o.o1 + l);
-    ya.tenq = take(dout.tenq + o.o1 + l);
-    ya.tenl = take(dout.tenl + o.o1 + l);
-    ya.teni = take(dout.teni + o.o1 + l);
-    ya.pclc = take(dout.pclc + o.o1 + l);
-    dout.pcovptot[o.o1 + l] = 0.0;                                    // :1688-1690
+    ya.tent = d[18 * NT];
+    ya.tenq = d[19 * NT];
+    ya.tenl = d[20 * NT];
+    ya.teni = d[21 * NT];
+    ya.pclc = d[22 * NT];
     // enthalpy-flux adjoints folded into the flux adjoints (:914-921)
-    ya.fl = take(dout.pfplsl + o.oh + l + nproma) - take(dout.pfhpsl + o.oh + l + nproma) * c.rlvtt;
-    ya.fn = take(dout.pfplsn + o.oh + l + nproma) - take(dout.pfhpsn + o.oh + l + nproma) * c.rlstt;
+    ya.fl = d[23 * NT] - d[25 * NT] * c.rlvtt;
+    ya.fn = d[24 * NT] - d[26 * NT] * c.rlstt;
+    // consumed and zeroed (:955-966, :1678-1690)
+    dout.tent[o.o1 + l] = 0.0; dout.tenq[o.o1 + l] = 0.0; dout.tenl[o.o1 + l] = 0.0;
+    dout.teni[o.o1 + l] = 0.0; dout.pclc[o.o1 + l] = 0.0; dout.pcovptot[o.o1 + l] = 0.0;
+    dout.pfplsl[o.oh + l + nproma] = 0.0; dout.pfplsn[o.oh + l + nproma] = 0.0;
+    dout.pfhpsl[o.oh + l + nproma] = 0.0; dout.pfhpsn[o.oh + l + nproma] = 0.0;
 
     LevAdj a;
     ad_level<RV>(c, crh, jk, x5, pqs5, paph0, rfl5, sfl5, ya, ca, a);
@@ -175,6 +226,8 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
       din.psupsat[o.o1 + l] = a.psupsat;                              // assignment, :1733
       if (jk == 0) acc(din.paph + o.oh, paph_pending);
     }
+    paph_hi5 = paph0;
+    slot ^= 1;
   }
   // top flux rows: consumed and zeroed (:917-919, :1677-1679)
   dout.pfplsl[o.oh] = 0.0;
@@ -209,6 +262,22 @@ __global__ void k_ad_finalize(const Geom g, const double *__restrict__ n1, const
 
 }  // namespace
 
+template <bool RV, bool DOT>
+static cudaError_t launch_ad_variant(const KConst &c, const Geom &g, const TrajIn &in,
+                                     const TrajOut &out, const IncIn &din, const IncOut &dout,
+                                     const ADOpts &opt, int grid, cudaStream_t s) {
+  const size_t smem = (size_t)AD_STAGES * AD_NF * NT * sizeof(double);
+  auto kern = k_cloudsc2_ad<RV, DOT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, CSC2_AD_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
+  return cudaGetLastError();
+}
+
 cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            const IncIn &din, const IncOut &dout, const ADOpts &opt, cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
@@ -216,13 +285,11 @@ cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, con
   const bool rv = c.rvtmp2 != 0.0;
   const bool dot = opt.dot_scale != 0.0;
   if (rv) {
-    if (dot) k_cloudsc2_ad<true, true><<<grid, CSC2_AD_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
-    else k_cloudsc2_ad<true, false><<<grid, CSC2_AD_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
-  } else {
-    if (dot) k_cloudsc2_ad<false, true><<<grid, CSC2_AD_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
-    else k_cloudsc2_ad<false, false><<<grid, CSC2_AD_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
+    if (dot) return launch_ad_variant<true, true>(c, g, in, out, din, dout, opt, grid, s);
+    return launch_ad_variant<true, false>(c, g, in, out, din, dout, opt, grid, s);
   }
-  return cudaGetLastError();
+  if (dot) return launch_ad_variant<false, true>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_ad_variant<false, false>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 cudaError_t csc2_launch_ad_finalize(const Geom &g, const double *n1, const double *n2,
