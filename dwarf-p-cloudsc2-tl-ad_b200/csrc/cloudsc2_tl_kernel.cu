@@ -7,6 +7,7 @@
 //                       sum_levels(F - F5) per column and field.
 //  k_taylor_finalize  : ERROR_NORM (:21-31) per block and lambda, max over blocks (:247-252).
 #include "cloudsc2_tl.cuh"
+#include "cloudsc2_stage.cuh"
 #include "cloudsc2_launch.h"
 
 namespace {
@@ -14,22 +15,64 @@ namespace {
 __device__ __forceinline__ double ldin(const double *p) { return __ldg(p); }
 __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 
-struct ColOffsets {
-  size_t o1, oh, ocld, ocml, oloc;
-};
-__device__ __forceinline__ ColOffsets col_offsets(int ibl, int jl, int nproma, int klev,
-                                                  long long bs_cld, long long bs_cml,
-                                                  long long bs_loc) {
-  const size_t n2 = (size_t)nproma * klev;
-  ColOffsets o;
-  o.o1 = (size_t)ibl * n2 + jl;
-  o.oh = (size_t)ibl * (n2 + nproma) + jl;
-  o.ocld = (size_t)ibl * bs_cld + jl;
-  o.ocml = (size_t)ibl * bs_cml + jl;
-  o.oloc = (size_t)ibl * bs_loc + jl;
-  return o;
-}
+constexpr int NT = CSC2_TL_THREADS;
+// fields staged per level: 15 trajectory inputs, PQS (optional), 16 increments
+constexpr int TL_NF = 32;
+constexpr int TL_STAGES = 2;
 
+__device__ __forceinline__ void stage_traj(double *d, const TrajIn &in, const ColOffsets &o, int jk,
+                                           int klev, int nproma) {
+  const size_t l = (size_t)jk * nproma;
+  csc2_cp_async8(d + 0 * NT, in.paph + o.oh + l + nproma);
+  csc2_cp_async8(d + 1 * NT, in.pap + o.o1 + l);
+  csc2_cp_async8(d + 2 * NT, in.pt + o.o1 + l);
+  csc2_cp_async8(d + 3 * NT, in.pq + o.o1 + l);
+  csc2_cp_async8(d + 4 * NT, in.pl + o.ocld + l);
+  csc2_cp_async8(d + 5 * NT, in.pi + o.ocld + l);
+  csc2_cp_async8(d + 6 * NT, in.plude + o.o1 + l);
+  if (jk < klev - 1) csc2_cp_async8(d + 7 * NT, in.plu + o.o1 + l + nproma);
+  csc2_cp_async8(d + 8 * NT, in.pmfu + o.o1 + l);
+  csc2_cp_async8(d + 9 * NT, in.pmfd + o.o1 + l);
+  csc2_cp_async8(d + 10 * NT, in.gt + o.ocml + l);
+  csc2_cp_async8(d + 11 * NT, in.gq + o.ocml + l);
+  csc2_cp_async8(d + 12 * NT, in.gl + o.ocml + l);
+  csc2_cp_async8(d + 13 * NT, in.gi + o.ocml + l);
+  csc2_cp_async8(d + 14 * NT, in.psupsat + o.o1 + l);
+  if (in.pqs) csc2_cp_async8(d + 15 * NT, in.pqs + o.o1 + l);
+}
+// increments from arrays (all plain (NPROMA,KLEV[+1],NBLOCKS)) -> fields 16..31
+__device__ __forceinline__ void stage_incr(double *d, const IncIn &di, const ColOffsets &o, int jk,
+                                           int klev, int nproma) {
+  const size_t l = (size_t)jk * nproma;
+  csc2_cp_async8(d + 16 * NT, di.paph + o.oh + l + nproma);
+  csc2_cp_async8(d + 17 * NT, di.pap + o.o1 + l);
+  csc2_cp_async8(d + 18 * NT, di.pt + o.o1 + l);
+  csc2_cp_async8(d + 19 * NT, di.pq + o.o1 + l);
+  csc2_cp_async8(d + 20 * NT, di.pl + o.o1 + l);
+  csc2_cp_async8(d + 21 * NT, di.pi + o.o1 + l);
+  csc2_cp_async8(d + 22 * NT, di.plude + o.o1 + l);
+  if (jk < klev - 1) csc2_cp_async8(d + 23 * NT, di.plu + o.o1 + l + nproma);
+  csc2_cp_async8(d + 24 * NT, di.pmfu + o.o1 + l);
+  csc2_cp_async8(d + 25 * NT, di.pmfd + o.o1 + l);
+  csc2_cp_async8(d + 26 * NT, di.gt + o.o1 + l);
+  csc2_cp_async8(d + 27 * NT, di.gq + o.o1 + l);
+  csc2_cp_async8(d + 28 * NT, di.gl + o.o1 + l);
+  csc2_cp_async8(d + 29 * NT, di.gi + o.o1 + l);
+  csc2_cp_async8(d + 30 * NT, di.psupsat + o.o1 + l);
+  csc2_cp_async8(d + 31 * NT, di.pqs + o.o1 + l);
+}
+// fields base..base+14 of a slot as a LevIn
+__device__ __forceinline__ LevIn read_level(const double *d, int base, int jk, int klev) {
+  LevIn x;
+  d += base * NT;
+  x.paph1 = d[0 * NT]; x.pap = d[1 * NT]; x.pt = d[2 * NT]; x.pq = d[3 * NT]; x.pl = d[4 * NT];
+  x.pi = d[5 * NT]; x.plude = d[6 * NT];
+  x.plu1 = (jk < klev - 1) ? d[7 * NT] : 0.0;
+  x.pmfu = d[8 * NT]; x.pmfd = d[9 * NT]; x.gt = d[10 * NT]; x.gq = d[11 * NT]; x.gl = d[12 * NT];
+  x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
+  return x;
+}
+// direct (unstaged) loads of one level, used by the Taylor-test kernel
 __device__ __forceinline__ LevIn load_level(const TrajIn &in, const ColOffsets &o, int jk, int klev,
                                             int nproma) {
   LevIn x;
@@ -52,30 +95,6 @@ __device__ __forceinline__ LevIn load_level(const TrajIn &in, const ColOffsets &
   return x;
 }
 
-// increments from arrays (all plain (NPROMA,KLEV[+1],NBLOCKS))
-__device__ __forceinline__ LevIn load_incr(const IncIn &d, const ColOffsets &o, int jk, int klev,
-                                           int nproma, double &dpqs) {
-  LevIn x;
-  const size_t l = (size_t)jk * nproma;
-  x.paph1 = ldin(d.paph + o.oh + l + nproma);
-  x.pap = ldin(d.pap + o.o1 + l);
-  x.pt = ldin(d.pt + o.o1 + l);
-  x.pq = ldin(d.pq + o.o1 + l);
-  x.pl = ldin(d.pl + o.o1 + l);
-  x.pi = ldin(d.pi + o.o1 + l);
-  x.plude = ldin(d.plude + o.o1 + l);
-  x.plu1 = (jk < klev - 1) ? ldin(d.plu + o.o1 + l + nproma) : 0.0;
-  x.pmfu = ldin(d.pmfu + o.o1 + l);
-  x.pmfd = ldin(d.pmfd + o.o1 + l);
-  x.gt = ldin(d.gt + o.o1 + l);
-  x.gq = ldin(d.gq + o.o1 + l);
-  x.gl = ldin(d.gl + o.o1 + l);
-  x.gi = ldin(d.gi + o.o1 + l);
-  x.psupsat = ldin(d.psupsat + o.o1 + l);
-  dpqs = ldin(d.pqs + o.o1 + l);
-  return x;
-}
-
 __device__ __forceinline__ LevIn scale_level(const LevIn &x, double f, bool zero_sup) {
   LevIn d;
   d.paph1 = x.paph1 * f; d.pap = x.pap * f; d.pt = x.pt * f; d.pq = x.pq * f; d.pl = x.pl * f;
@@ -89,15 +108,22 @@ template <bool ONFLY>
 __global__ void __launch_bounds__(CSC2_TL_THREADS)
 k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const TLOpts opt) {
+  extern __shared__ double ring_all[];
+  double *ring = ring_all + threadIdx.x;
   csc2_math_init();
   const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks || gcol >= g.ngptot) return;
   const int jl = gcol - ibl * g.nproma;
   const int klev = g.klev, nproma = g.nproma;
-  const ColOffsets o = col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
   const bool zero_sup = opt.zero_psupsat_pert != 0;
   const bool wr = dout.tent != nullptr;
+  constexpr int SLOT = TL_NF * NT;
+
+  stage_traj(ring, in, o, 0, klev, nproma);
+  if (!ONFLY) stage_incr(ring, din, o, 0, klev, nproma);
+  csc2_cp_async_commit();
 
   // ZTRPAUS from the trajectory only (cloudsc2tl.F90:431-442)
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
@@ -116,18 +142,24 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   double s_t = 0, s_q = 0, s_l = 0, s_i = 0, s_c = 0, s_fl = 0, s_fn = 0, s_hl = 0, s_hn = 0;
   double q_t = 0, q_q = 0, q_l = 0, q_i = 0, q_c = 0, q_fl = 0, q_fn = 0, q_hl = 0, q_hn = 0;
 
-  LevIn cur = load_level(in, o, 0, klev, nproma);
+  int slot = 0;
   for (int jk = 0; jk < klev; ++jk) {
-    LevIn nxt = cur;
-    if (jk + 1 < klev) nxt = load_level(in, o, jk + 1, klev, nproma);
-    const double pqs5 = in.pqs ? ldin(in.pqs + o.o1 + (size_t)jk * nproma)
-                               : satur_point(c, cur.pt, 1.0 / cur.pap);
+    if (jk + 1 < klev) {
+      stage_traj(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
+      if (!ONFLY) stage_incr(ring + (slot ^ 1) * SLOT, din, o, jk + 1, klev, nproma);
+    }
+    csc2_cp_async_commit();
+    csc2_cp_async_wait<1>();
+    const double *d = ring + slot * SLOT;
+    const LevIn cur = read_level(d, 0, jk, klev);
+    const double pqs5 = in.pqs ? d[15 * NT] : satur_point(c, cur.pt, csc2_rcp(cur.pap));
     LevIn dx; double dpqs;
     if (ONFLY) {
       dx = scale_level(cur, opt.pert_scale, zero_sup);
       dpqs = pqs5 * opt.pert_scale;
     } else {
-      dx = load_incr(din, o, jk, klev, nproma, dpqs);
+      dx = read_level(d, 16, jk, klev);
+      dpqs = d[31 * NT];
     }
     LevOut y5, dy;
     tl_level(c, crh, jk, cur, pqs5, dx, dpqs, st5, st, y5, dy);
@@ -153,7 +185,7 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     q_t += dy.tent * dy.tent; q_q += dy.tenq * dy.tenq; q_l += dy.tenl * dy.tenl;
     q_i += dy.teni * dy.teni; q_c += dy.pclc * dy.pclc; q_fl += dy.rfln * dy.rfln;
     q_fn += dy.sfln * dy.sfln; q_hl += hl * hl; q_hn += hn * hn;
-    cur = nxt;
+    slot ^= 1;
   }
   if (opt.colsum) {
     double *s = opt.colsum + gcol;
@@ -183,7 +215,7 @@ k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, con
   const int klev = g.klev, nproma = g.nproma;
   const int ilam = blockIdx.y;
   const double lam = lams.v[ilam];
-  const ColOffsets o = col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, base.bs_loc);
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, base.bs_loc);
 
   // tropopause level of the PERTURBED state (the perturbed run is a plain CLOUDSC2 call)
   double ztrpaus = 0.1;
@@ -276,13 +308,28 @@ __global__ void k_taylor_finalize(const Geom g, const Lambdas lams, const double
 
 }  // namespace
 
+template <bool ONFLY>
+static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajIn &in,
+                                     const TrajOut &out, const IncIn &din, const IncOut &dout,
+                                     const TLOpts &opt, int grid, cudaStream_t s) {
+  const size_t smem = (size_t)TL_STAGES * TL_NF * NT * sizeof(double);
+  auto kern = k_cloudsc2_tl<ONFLY>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, CSC2_TL_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
+  return cudaGetLastError();
+}
+
 cudaError_t csc2_launch_tl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            const IncIn &din, const IncOut &dout, const TLOpts &opt, cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + CSC2_TL_THREADS - 1) / CSC2_TL_THREADS);
-  if (opt.pert_scale != 0.0) k_cloudsc2_tl<true><<<grid, CSC2_TL_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
-  else k_cloudsc2_tl<false><<<grid, CSC2_TL_THREADS, 0, s>>>(c, g, in, out, din, dout, opt);
-  return cudaGetLastError();
+  if (opt.pert_scale != 0.0) return launch_tl_variant<true>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_tl_variant<false>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 static Lambdas make_lambdas() {
