@@ -45,6 +45,11 @@ AD_BYTES_PER_COL = 10564 * 8                                                    
 # what our kernels actually have to move:
 #  TL: 2056 traj in (SATUR fused) + 2193 incr in + 1374 traj out + 1374 incr out
 TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
+# DRAM traffic per column measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch
+# over 163 840 columns, profiles/r1_{nl,tl,ad}_ncu.md) and FP64-pipe utilisation of the same capture
+NCU = {"nl": {"dram_bytes_per_column": 4.737e9 / 163840, "fp64_pipe_pct": 59.6, "profile": "profiles/r1_nl_ncu.md"},
+       "tl": {"dram_bytes_per_column": 9.257e9 / 163840, "fp64_pipe_pct": 49.5, "profile": "profiles/r1_tl_ncu.md"},
+       "ad": {"dram_bytes_per_column": 16.892e9 / 163840, "fp64_pipe_pct": 35.2, "profile": "profiles/r1_ad_ncu.md"}}
 METRIC = "NL columns/s (KLEV=137)"
 UNIT = "columns/s"
 
@@ -109,6 +114,15 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """All host cores this process may use.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which would silently make the CPU arm single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_run(pkg, ob, src, prm, nproma: int, ngptot: int, threads: int, repeats: int):
     """The reference CPU path (oracle restatement of CLOUDSC_DRIVER) on `ngptot` columns.
     Returns best columns/s over `repeats` (the reference times the block loop only)."""
@@ -157,7 +171,7 @@ def main():
         if rank != 0:
             return 0
         from tests import oracle_binding as ob
-        threads = ob.max_threads()
+        threads = host_threads()
         sample = min(ngp, 32768)
         t_steps = []
         st = pkg.ArrayState(src, nproma, sample)
@@ -265,8 +279,14 @@ def main():
     launches = gpu.launch_count() - l0 - args.warmup
     value = ngp * world / (ms_nl * 1e-3)
     nl_gbs = NL_BYTES_PER_COL * ngp / (ms_nl * 1e-3) / 1e9
+    def ncu_part(mode, ms):
+        n = NCU[mode]
+        return {"dram_gbs_actual": n["dram_bytes_per_column"] * ngp / (ms * 1e-3) / 1e9,
+                "fp64_pipe_pct_ncu": n["fp64_pipe_pct"], "ncu_profile": n["profile"]}
+
     results["nl"] = {"columns_per_s": value, "ms_per_step": ms_nl, "gbs_per_gpu": nl_gbs,
-                     "frac_of_hbm": nl_gbs / peak, "bytes_per_column": NL_BYTES_PER_COL}
+                     "frac_of_hbm": nl_gbs / peak, "bytes_per_column": NL_BYTES_PER_COL,
+                     **ncu_part("nl", ms_nl)}
 
     # ---- TL / AD ------------------------------------------------------------------------------
     if "tl" in modes or "ad" in modes:
@@ -297,7 +317,8 @@ def main():
             results["tl"] = {"columns_per_s": ngp * world / (ms_tl * 1e-3), "ms_per_step": ms_tl,
                              "gbs_per_gpu": gbs, "frac_of_hbm": gbs / peak,
                              "bytes_per_column": TL_BYTES_PER_COL,
-                             "note": "CLOUDSC2TL as written: 16+16 arrays in, 10+10 out"}
+                             "note": "CLOUDSC2TL as written: 16+16 arrays in, 10+10 out",
+                             **ncu_part("tl", ms_tl)}
         if "ad" in modes:
             try:
                 for n in pkg._abi.INCR_OUT:
@@ -310,7 +331,8 @@ def main():
                 results["ad"] = {"columns_per_s": ngp * world / (ms_ad * 1e-3), "ms_per_step": ms_ad,
                                  "gbs_per_gpu": gbs, "frac_of_hbm": gbs / peak,
                                  "bytes_per_column": AD_BYTES_PER_COL,
-                                 "note": "CLOUDSC2AD as written: traj in/out, adjoints RMW"}
+                                 "note": "CLOUDSC2AD as written: traj in/out, adjoints RMW",
+                                 **ncu_part("ad", ms_ad)}
             except pkg.Cloudsc2Error as e:
                 results["ad"] = {"error": str(e)}
         for p in list(din.values()) + list(dout.values()):
@@ -352,7 +374,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from tests import oracle_binding as ob
-        threads = ob.max_threads()
+        threads = host_threads()
         sample = min(ngp, 65536)
         cps, _ = cpu_reference_run(pkg, ob, src, prm, nproma, sample, threads, repeats=3)
         cps4, _ = cpu_reference_run(pkg, ob, src, prm, 32, min(sample, 32768), min(4, threads), repeats=2)
@@ -367,9 +389,14 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "impl": "b200",
                 "roofline": {"bound": "hbm", "achieved": nl_gbs, "peak": peak, "unit": "GB/s",
-                             "frac": nl_gbs / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "k_cloudsc2_nl<false>",
-                             "algorithmic_bytes_per_column": NL_BYTES_PER_COL},
+                             "frac": nl_gbs / peak,
+                             "traffic": NCU["nl"]["dram_bytes_per_column"] * ngp,
+                             "traffic_note": "bytes per launch; ncu dram__bytes_read+write of one launch at "
+                                             "163 840 columns scaled by NGPTOT (profiles/r1_nl_ncu.md)",
+                             "peak_source": peak_src, "kernel": "k_cloudsc2_nl",
+                             "algorithmic_bytes_per_column": NL_BYTES_PER_COL,
+                             "algorithmic_bytes_per_launch": NL_BYTES_PER_COL * ngp,
+                             "fp64_pipe_pct_ncu": NCU["nl"]["fp64_pipe_pct"]},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
                 "modes": results}
         print(json.dumps(line))
