@@ -101,6 +101,7 @@ def _declare(lib):
         "cloudsc2_gpu_memset": (i, [vp, i, C.c_ulonglong]),
         "cloudsc2_gpu_sync": (i, []),
         "cloudsc2_gpu_math_probe": (i, [i, c_double_p, c_double_p, i]),
+        "cloudsc2_gpu_set_option": (i, [C.c_char_p, i]),
         # include/cloudsc2_host.h
         "cloudsc2_default_params": (None, [P]),
         "cloudsc2_source_synth": (i, [C.POINTER(Source), C.c_ulonglong, i, i, P]),

@@ -67,7 +67,9 @@ __device__ __forceinline__ LevIn read_traj(const double *d, int jk, int klev, do
 __device__ __forceinline__ void acc(double *p, double v) { atomicAdd(p, v); }
 
 template <bool RV, bool DOT>
-__global__ void __launch_bounds__(CSC2_AD_THREADS)
+// 3 CTAs/SM (168 registers, ~0.5 kB/thread of spills in L1) beats 2 CTAs/SM at 255 registers:
+// 3.67 vs 3.80 ms -- the reverse sweep is latency-bound, not register-bound
+__global__ void __launch_bounds__(CSC2_AD_THREADS, 3)
 k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const ADOpts opt) {
   extern __shared__ double ring_all[];

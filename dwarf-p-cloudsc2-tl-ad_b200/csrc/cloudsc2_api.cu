@@ -68,6 +68,20 @@ struct Ctx {
 };
 Ctx g;
 
+// Tuning options: defaults from the environment, changeable through cloudsc2_gpu_set_option.
+struct Options {
+  int e2e_mode = 0;         // 0/1 staged copies, 2 zero-copy kernel on mapped host arrays
+  int e2e_chunk_mb = 256;   // cap of the staging chunk size
+  bool loaded = false;
+  void load() {
+    if (loaded) return;
+    loaded = true;
+    if (const char *e = getenv("CSC2_E2E_MODE")) e2e_mode = atoi(e);
+    if (const char *e = getenv("CSC2_E2E_CHUNK_MB")) if (atoi(e) > 0) e2e_chunk_mb = atoi(e);
+  }
+};
+Options opts;
+
 int require_init() {
   if (!g.init) return fail(2, "cloudsc2_gpu_init has not been called");
   return 0;
@@ -204,6 +218,32 @@ int download_outputs(const cloudsc2_fields *h, const DevProblem &dp) {
 
 inline long long pad_cols(long long n) { return (n + 127) / 128 * 128; }
 
+// Device-side aliases of page-locked, mapped host arrays; false if any array is not mapped.
+bool map_host_fields(const cloudsc2_fields &h, cloudsc2_fields &d) {
+  int can = 0;
+  if (cudaDeviceGetAttribute(&can, cudaDevAttrCanMapHostMemory, g.device) != cudaSuccess || !can) return false;
+  auto map = [](const void *p, void **out) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *out = a.devicePointer;
+    return true;
+  };
+  void *p[18];
+  const void *src[18] = {h.pt, h.pq, h.pap, h.paph, h.plu, h.plude, h.pmfu, h.pmfd, h.psupsat, h.pclv,
+                         h.b_cml, h.b_loc, h.pa, h.pcovptot, h.pfplsl, h.pfplsn, h.pfhpsl, h.pfhpsn};
+  for (int i = 0; i < 18; ++i)
+    if (!map(src[i], &p[i])) return false;
+  d.pt = (const double *)p[0]; d.pq = (const double *)p[1]; d.pap = (const double *)p[2];
+  d.paph = (const double *)p[3]; d.plu = (const double *)p[4]; d.plude = (const double *)p[5];
+  d.pmfu = (const double *)p[6]; d.pmfd = (const double *)p[7]; d.psupsat = (const double *)p[8];
+  d.pclv = (const double *)p[9]; d.b_cml = (const double *)p[10];
+  d.b_loc = (double *)p[11]; d.pa = (double *)p[12]; d.pcovptot = (double *)p[13];
+  d.pfplsl = (double *)p[14]; d.pfplsn = (double *)p[15]; d.pfhpsl = (double *)p[16];
+  d.pfhpsn = (double *)p[17];
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -289,7 +329,7 @@ int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes) {
 }
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes) {
   if (int rc = require_init()) return rc;
-  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   return 0;
 }
 int cloudsc2_gpu_host_unregister(void *ptr) {
@@ -301,6 +341,15 @@ int cloudsc2_gpu_sync(void) {
   CK(cudaStreamSynchronize(g.stream));
   for (int i = 0; i < kStreams; ++i) CK(cudaStreamSynchronize(g.pipe[i]));
   return 0;
+}
+
+int cloudsc2_gpu_set_option(const char *name, int value) {
+  opts.load();
+  if (!name) return fail(3, "option name is NULL");
+  if (!strcmp(name, "e2e_mode")) { opts.e2e_mode = value; return 0; }
+  if (!strcmp(name, "e2e_chunk_mb") && value > 0) { opts.e2e_chunk_mb = value; return 0; }
+  if (!strcmp(name, "nl_variant")) { csc2_set_nl_variant(value); return 0; }
+  return fail(3, "unknown option '%s' (or bad value %d)", name, value);
 }
 
 int cloudsc2_gpu_math_probe(int fn, const double *x, double *y, int n) {
@@ -343,6 +392,31 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   const int nblocks = nblocks_of(ngptot, nproma);
+  // Zero-copy path: when every array is page-locked and mapped (cloudsc2_gpu_host_register), the
+  // kernel streams its inputs from, and its outputs to, host memory directly over PCIe -- one
+  // launch, both directions busy at once, no staging copies, and only the slabs the kernel
+  // touches cross the bus.  Opt-in (CSC2_E2E_MODE=2): measured on B200 / PCIe Gen5 it reaches only
+  // ~23 GB/s (8-byte-per-thread reads of system memory) against ~50 GB/s per direction for the
+  // copy engines, i.e. 116 ms vs 59 ms at 163 840 columns; it wins only for tiny problems.
+  opts.load();
+  if (opts.e2e_mode == 2) {
+    cloudsc2_fields d;
+    if (map_host_fields(*h, d)) {
+      Geom geo{nproma, klev, ngptot, nblocks};
+      TrajIn in; TrajOut out;
+      views_from_fields(d, nproma, klev, in, out);
+      CK(cudaEventRecord(g.ev[0], g.stream));
+      CK(csc2_launch_nl(make_kconst(ptsphy), geo, in, out, g.stream));
+      g.launches += 1;
+      CK(cudaEventRecord(g.ev[1], g.stream));
+      CK(cudaEventSynchronize(g.ev[1]));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+      if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
+      if (elapsed_kernel_s) *elapsed_kernel_s = ms * 1e-3;
+      return 0;
+    }
+  }
   const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
   const size_t D = sizeof(double);
   // compact device layout: [8 plain | paph | cld(2) | cml(4)] and [loc(5) | pa | pcov | 4 flux]
@@ -361,9 +435,37 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
          *d_hn = d_hl + n2h * nb;
 
   // chunking: ~48 MB of input per chunk, at least 1 block, at most 64 chunks
-  size_t blocks_per_chunk = std::max<size_t>(1, (48u << 20) / (in_blk * D));
-  size_t nchunks = (nb + blocks_per_chunk - 1) / blocks_per_chunk;
-  if (nchunks > 64) { nchunks = 64; blocks_per_chunk = (nb + 63) / 64; nchunks = (nb + blocks_per_chunk - 1) / blocks_per_chunk; }
+  // Chunk plan: each async copy costs ~10 us of host enqueue time, so chunks should be large
+  // (measured at 163 840 columns: 8-48 MB chunks 68-69 ms, 128 MB 61 ms, 400 MB 59 ms), but the
+  // first H2D and the last D2H are not overlapped with anything, so the plan ramps up from 16 MB,
+  // doubling to the cap (CSC2_E2E_CHUNK_MB, default 256), and ramps down again at the end.
+  const size_t chunk_mb = (size_t)opts.e2e_chunk_mb;
+  std::vector<size_t> plan;            // blocks per chunk
+  {
+    const size_t blk_bytes = in_blk * D;
+    auto blocks_of = [&](size_t mb) { return std::max<size_t>(1, (mb << 20) / blk_bytes); };
+    std::vector<size_t> up;
+    for (size_t mb = 16; mb < chunk_mb; mb *= 2) up.push_back(blocks_of(mb));
+    size_t ramp = 0;
+    for (size_t b : up) ramp += b;
+    if (2 * ramp >= nb) {
+      // small problem: equal chunks of at most 16 MB, at least 3 so that the streams overlap
+      const size_t per = std::max<size_t>(1, std::min(blocks_of(16), (nb + 2) / 3));
+      for (size_t b0 = 0; b0 < nb; b0 += per) plan.push_back(std::min(per, nb - b0));
+    } else {
+      for (size_t b : up) plan.push_back(b);
+      size_t mid = nb - 2 * ramp;
+      const size_t cap = blocks_of(chunk_mb);
+      const size_t nmid = (mid + cap - 1) / cap;
+      for (size_t i = 0; i < nmid; ++i) {
+        const size_t b = mid / (nmid - i);
+        plan.push_back(b);
+        mid -= b;
+      }
+      for (size_t i = up.size(); i-- > 0;) plan.push_back(up[i]);
+    }
+  }
+  const size_t nchunks = plan.size();
   const KConst kc = make_kconst(ptsphy);
 
   std::vector<cudaEvent_t> k0(nchunks), k1(nchunks);
@@ -371,9 +473,10 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
   CK(cudaEventRecord(g.ev[0], g.stream));
   for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(g.pipe[i], g.ev[0], 0));
 
-  for (size_t ic = 0; ic < nchunks; ++ic) {
+  size_t b0 = 0;
+  for (size_t ic = 0; ic < nchunks; b0 += plan[ic], ++ic) {
     cudaStream_t s = g.pipe[ic % kStreams];
-    const size_t b0 = ic * blocks_per_chunk, cb = std::min(blocks_per_chunk, nb - b0);
+    const size_t cb = plan[ic];
     auto h2d = [&](double *dst, const double *src, size_t per_blk) {
       return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyHostToDevice, s);
     };

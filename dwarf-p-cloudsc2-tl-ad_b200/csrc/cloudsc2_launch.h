@@ -61,3 +61,5 @@ cudaError_t csc2_launch_ad_finalize(const Geom &g, const double *n1, const doubl
 // Accuracy probe of cloudsc2_math.cuh: y[i] = fn(x[i]); fn 0 rcp, 1 exp, 2 expn, 3 sqrt,
 // 4 tanh+1, 5 sech^2 (device pointers).
 cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cudaStream_t s);
+// NL launch configuration (see csc2_launch_nl); also settable with CSC2_NL_VARIANT.
+void csc2_set_nl_variant(int v);

@@ -186,14 +186,15 @@ static cudaError_t launch_nl_variant(const KConst &c, const Geom &g, const TrajI
 }
 
 // CSC2_NL_VARIANT (tuning knob, read once): CTA size / CTAs per SM / ring depth
+static int g_nl_variant = -1;
 static int nl_variant() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_nl_variant < 0) {
     const char *e = getenv("CSC2_NL_VARIANT");
-    v = e ? atoi(e) : 0;
+    g_nl_variant = e ? atoi(e) : 0;
   }
-  return v;
+  return g_nl_variant;
 }
+void csc2_set_nl_variant(int v) { g_nl_variant = v < 0 ? 0 : v; }
 
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {

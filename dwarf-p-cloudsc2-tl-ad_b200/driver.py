@@ -276,6 +276,10 @@ class Cloudsc2:
         self._check(self.lib.cloudsc2_gpu_expand_shard_dev(src_ptr, nlon, nlev, ndim, dst_ptr,
                                                            nproma, ngptot, gcol0, stream))
 
+    def set_option(self, name: str, value: int):
+        """cloudsc2_gpu_set_option: 'e2e_mode', 'e2e_chunk_mb', 'nl_variant'."""
+        self._check(self.lib.cloudsc2_gpu_set_option(name.encode(), int(value)))
+
     def math_probe(self, fn: int, x: np.ndarray) -> np.ndarray:
         """Evaluate one of the kernels' elementary functions (csrc/cloudsc2_math.cuh) on the GPU."""
         self._bind()

@@ -178,6 +178,16 @@ int cloudsc2_gpu_sync(void);
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes);
 int cloudsc2_gpu_host_unregister(void *ptr);
 
+/* ---- tuning ------------------------------------------------------------------------------- */
+/* Integer tuning options (defaults come from the environment variables in parentheses):
+ *   "e2e_mode"     (CSC2_E2E_MODE)     0/1 = staged chunked copies in the host-pointer entry points,
+ *                                      2 = zero-copy: the kernel reads/writes page-locked, mapped
+ *                                      host arrays directly (cloudsc2_gpu_host_register)
+ *   "e2e_chunk_mb" (CSC2_E2E_CHUNK_MB) cap of the staging chunk size in MB (default 256)
+ *   "nl_variant"   (CSC2_NL_VARIANT)   launch shape of the NL kernel (csrc/cloudsc2_nl_kernel.cu)
+ * Nothing like this exists in the reference (its only knobs are NUMOMP and NPROMA). */
+int cloudsc2_gpu_set_option(const char *name, int value);
+
 /* ---- diagnostics -------------------------------------------------------------------------- */
 /* Evaluate one of the kernels' branch-free FP64 elementary functions (csrc/cloudsc2_math.cuh,
  * the replacements of the Fortran intrinsics EXP/TANH/COSH/SQRT and of "/" used by

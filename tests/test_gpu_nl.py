@@ -181,3 +181,44 @@ def test_device_shard_expansion_and_sharded_tests(pkg, src100, gpu_nl):
     z, sh1 = pkg.sharded_taylor(gpu_nl, src100, 32, 100, 0, 1)
     z2, _ = gpu_nl.tl_taylor(pkg.ArrayState(src100, 32, 100))
     assert np.array_equal(z, z2) and sh1.ngptot == 100
+
+
+@pytest.mark.parametrize("nproma,ngptot", [(32, 1000), (128, 4096), (7, 23)])
+def test_nl_zero_copy_path_equals_staged_path(pkg, src100, gpu_nl, nproma, ngptot):
+    """cloudsc2_gpu_nl with option e2e_mode=2 on page-locked + mapped host arrays lets the kernel
+    stream from / to host memory directly; it must give exactly the staged-copy result,
+    incl. the untouched padding columns and B_LOC slabs."""
+    staged = pkg.ArrayState(src100, nproma, ngptot)
+    direct = pkg.ArrayState(src100, nproma, ngptot)
+    for s in (staged, direct):
+        s.reset_outputs(fill=-1.5)
+    gpu_nl.nl(staged)
+    for a in direct.a.values():
+        gpu_nl.pin(a)
+    gpu_nl.set_option("e2e_mode", 2)
+    try:
+        tk, tt = gpu_nl.nl(direct)
+        assert tk == tt > 0          # one launch, no separate copies
+    finally:
+        gpu_nl.set_option("e2e_mode", 0)
+        for a in direct.a.values():
+            gpu_nl.unpin(a)
+    for n, a in staged.a.items():
+        assert np.array_equal(a, direct.a[n]), n
+
+
+def test_nl_staged_chunk_plan_covers_every_block(pkg, src100, gpu_nl):
+    """The ramped chunk plan of the staged host path (16 MB doubling to the cap and back) must
+    tile the blocks exactly for any cap; results do not depend on the plan."""
+    st = pkg.ArrayState(src100, 32, 20000)         # 625 blocks, 330 kB of input each = 206 MB
+    gpu_nl.nl(st)
+    want = {k: v.copy() for k, v in st.outputs().items()}
+    try:
+        for cap in (1, 17, 64):
+            gpu_nl.set_option("e2e_chunk_mb", cap)
+            st.reset_outputs(fill=3.0)
+            gpu_nl.nl(st)
+            for k, v in st.outputs().items():
+                assert np.array_equal(v, want[k]), (cap, k)
+    finally:
+        gpu_nl.set_option("e2e_chunk_mb", 256)
