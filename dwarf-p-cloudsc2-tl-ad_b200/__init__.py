@@ -9,8 +9,9 @@ the library or a CUDA device is missing.
 from ._abi import load_library, Params, Fields, IncrIn, IncrOut, NCLV, NSTATE, LIB_PATH
 from .state import (ArrayState, SourceColumns, default_params, expand, nblocks, synth_source,
                     read_h5_f8, read_h5_i4, validate)
-from . import driver, sharding
-from .sharding import Shard, allreduce_norms, shard_blocks, sharded_adjoint, sharded_taylor
+from . import driver, pyapi, report, sharding
+from .sharding import (Shard, allreduce_norms, allreduce_validation, shard_blocks, sharded_adjoint,
+                       sharded_taylor)
 from .driver import (Cloudsc2, Cloudsc2Error, DeviceState, adjoint_verdict, gpu_available,
                      taylor_verdict)
 
@@ -20,5 +21,5 @@ __all__ = [
     "read_h5_f8", "read_h5_i4", "validate",
     "Cloudsc2", "Cloudsc2Error", "DeviceState", "adjoint_verdict", "gpu_available",
     "taylor_verdict", "driver", "sharding", "Shard", "allreduce_norms", "shard_blocks",
-    "sharded_adjoint", "sharded_taylor",
+    "sharded_adjoint", "sharded_taylor", "allreduce_validation", "pyapi", "report",
 ]

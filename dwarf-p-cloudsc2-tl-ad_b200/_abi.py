@@ -102,6 +102,8 @@ def _declare(lib):
         "cloudsc2_gpu_sync": (i, []),
         "cloudsc2_gpu_math_probe": (i, [i, c_double_p, c_double_p, i]),
         "cloudsc2_gpu_set_option": (i, [C.c_char_p, i]),
+        "cloudsc2_gpu_satur": (i, [C.c_longlong, c_double_p, c_double_p, c_double_p]),
+        "cloudsc2_gpu_validate_dev": (i, [vp, i, vp, i, i, i, i, C.c_longlong, c_double_p]),
         # include/cloudsc2_host.h
         "cloudsc2_default_params": (None, [P]),
         "cloudsc2_source_synth": (i, [C.POINTER(Source), C.c_ulonglong, i, i, P]),

@@ -343,6 +343,37 @@ int cloudsc2_gpu_sync(void) {
   return 0;
 }
 
+int cloudsc2_gpu_satur(long long n, const double *pap, const double *pt, double *pqsat) {
+  if (int rc = require_init()) return rc;
+  if (!pap || !pt || !pqsat || n <= 0) return fail(3, "bad arguments to cloudsc2_gpu_satur");
+  if (int rc = g.work.reserve(3 * (size_t)n * sizeof(double))) return rc;
+  double *d_pap = g.work.d(), *d_pt = d_pap + n, *d_q = d_pt + n;
+  CK(cudaMemcpyAsync(d_pap, pap, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(d_pt, pt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  CK(csc2_launch_satur(make_kconst(1.0), d_pap, d_pt, d_q, n, g.stream));
+  g.launches += 1;
+  CK(cudaMemcpyAsync(pqsat, d_q, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int cloudsc2_gpu_validate_dev(const double *ref_src, int nlon, const double *field, int nproma,
+                              int nlev, int ndim, int ngptot, long long gcol0, double out[5]) {
+  if (int rc = require_init()) return rc;
+  if (!ref_src || !field || !out) return fail(3, "NULL argument to cloudsc2_gpu_validate_dev");
+  if (nlon <= 0 || nproma <= 0 || nlev <= 0 || ndim <= 0 || ngptot <= 0 || gcol0 < 0)
+    return fail(3, "bad dimensions in cloudsc2_gpu_validate_dev");
+  if (int rc = g.res.reserve(csc2_validate_scratch_bytes() + 8 * sizeof(double))) return rc;
+  double *d_out = g.res.d();
+  void *scratch = d_out + 8;
+  CK(csc2_launch_validate(ref_src, nlon, field, nproma, (long long)nlev * ndim, ngptot,
+                          nblocks_of(ngptot, nproma), gcol0, scratch, d_out, g.stream));
+  g.launches += 2;
+  CK(cudaMemcpyAsync(out, d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 int cloudsc2_gpu_set_option(const char *name, int value) {
   opts.load();
   if (!name) return fail(3, "option name is NULL");

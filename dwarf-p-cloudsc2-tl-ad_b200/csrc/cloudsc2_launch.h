@@ -63,3 +63,15 @@ cudaError_t csc2_launch_ad_finalize(const Geom &g, const double *n1, const doubl
 cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cudaStream_t s);
 // NL launch configuration (see csc2_launch_nl); also settable with CSC2_NL_VARIANT.
 void csc2_set_nl_variant(int v);
+
+// Device-side validation statistics (cloudsc2_validate_kernel.cu): out5 = min(field), max(field),
+// max|err|, sum|err|, sum|ref| against the un-expanded reference columns ref_src (nlon, rows).
+#define CSC2_VALIDATE_MAX_CTAS (148 * 8)
+size_t csc2_validate_scratch_bytes();
+cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *field, int nproma,
+                                 long long rows, int ngptot, int nblocks, long long gcol0,
+                                 void *scratch, double *out5, cudaStream_t s);
+
+// SATUR alone, elementwise over n points (device pointers).
+cudaError_t csc2_launch_satur(const KConst &c, const double *pap, const double *pt, double *pqsat,
+                              long long n, cudaStream_t s);

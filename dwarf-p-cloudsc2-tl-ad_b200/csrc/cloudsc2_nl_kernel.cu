@@ -143,6 +143,15 @@ __global__ void k_expand(const double *__restrict__ src, int nlon, long long row
   }
 }
 
+// SATUR on its own (satur.F90:106-123, LDPHYLIN branch): elementwise over n points
+__global__ void k_satur(const __grid_constant__ KConst c, const double *__restrict__ pap,
+                        const double *__restrict__ pt, double *__restrict__ pqsat, long long n) {
+  csc2_math_init();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pqsat[i] = satur_point(c, pt[i], csc2_rcp(pap[i]));
+}
+
 // accuracy probe of the branch-free elementary functions (tests/test_gpu_math.py)
 __global__ void k_math_probe(int fn, const double *__restrict__ x, double *__restrict__ y, int n) {
   csc2_math_init();
@@ -162,6 +171,12 @@ __global__ void k_math_probe(int fn, const double *__restrict__ x, double *__res
 }
 
 }  // namespace
+
+cudaError_t csc2_launch_satur(const KConst &c, const double *pap, const double *pt, double *pqsat,
+                              long long n, cudaStream_t s) {
+  k_satur<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c, pap, pt, pqsat, n);
+  return cudaGetLastError();
+}
 
 cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cudaStream_t s) {
   k_math_probe<<<(n + 127) / 128, 128, 0, s>>>(fn, x, y, n);

@@ -1,0 +1,106 @@
+// cloudsc2_validate_kernel.cu -- device-side validation statistics.
+// Replaces VALIDATE_R2 / VALIDATE_R3 of the reference (common/module/validate_mod.F90:165-261):
+// per field  min / max of the computed field over whole blocks (incl. the padding of the last
+// block, as MINVAL(FIELD(:,:,B)) does), and max|err|, sum|err|, sum|ref| over the BSIZE valid
+// columns of each block.  The reference compares against an EXPANDED copy of reference.h5; here the
+// reference values are read straight from the un-expanded source columns through the cyclic map
+// of expand_mod.F90:270-302 (global column g <- source column g mod nlon), so validating
+// 100+ GB of results needs neither a device->host copy nor an expanded reference array.
+// Deterministic: per-CTA partials (warp shuffles + shared memory), then one CTA folds the partials
+// in a fixed order.
+#include "cloudsc2_launch.h"
+
+namespace {
+
+struct Stats {
+  double vmin, vmax, maxerr, sumerr, sumref;
+};
+__device__ __forceinline__ void fold(Stats &a, const Stats &b) {
+  a.vmin = fmin(a.vmin, b.vmin);
+  a.vmax = fmax(a.vmax, b.vmax);
+  a.maxerr = fmax(a.maxerr, b.maxerr);
+  a.sumerr += b.sumerr;
+  a.sumref += b.sumref;
+}
+__device__ __forceinline__ Stats shfl_down(const Stats &s, int off) {
+  Stats r;
+  r.vmin = __shfl_down_sync(0xffffffffu, s.vmin, off);
+  r.vmax = __shfl_down_sync(0xffffffffu, s.vmax, off);
+  r.maxerr = __shfl_down_sync(0xffffffffu, s.maxerr, off);
+  r.sumerr = __shfl_down_sync(0xffffffffu, s.sumerr, off);
+  r.sumref = __shfl_down_sync(0xffffffffu, s.sumref, off);
+  return r;
+}
+__device__ __forceinline__ Stats identity() {
+  return Stats{1.7976931348623157e308, -1.7976931348623157e308, 0.0, 0.0, 0.0};
+}
+// CTA-wide fold; the result is valid in thread 0
+__device__ Stats block_fold(Stats s) {
+  __shared__ Stats sh[32];
+  for (int off = 16; off > 0; off >>= 1) fold(s, shfl_down(s, off));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = s;
+  __syncthreads();
+  if (w == 0) {
+    s = (l < (int)((blockDim.x + 31) >> 5)) ? sh[l] : identity();
+    for (int off = 16; off > 0; off >>= 1) fold(s, shfl_down(s, off));
+  }
+  return s;
+}
+
+// field: (nproma, rows, nblocks) with rows = nlev*ndim ; ref_src: (nlon, rows)
+__global__ void __launch_bounds__(256)
+k_validate_partial(const double *__restrict__ ref_src, int nlon, const double *__restrict__ field,
+                   int nproma, long long rows, int ngptot, long long gcol0, long long total,
+                   Stats *__restrict__ partial) {
+  Stats s = identity();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int jl = (int)(idx % nproma);
+    const long long t = idx / nproma;
+    const long long r = t % rows;
+    const long long b = t / rows;
+    const long long col = b * nproma + jl;
+    const double v = __ldcs(field + idx);
+    s.vmin = fmin(s.vmin, v);
+    s.vmax = fmax(s.vmax, v);
+    if (col < ngptot) {
+      const double ref = __ldg(ref_src + r * nlon + (gcol0 + col) % nlon);
+      const double d = fabs(v - ref);
+      s.maxerr = fmax(s.maxerr, d);
+      s.sumerr += d;
+      s.sumref += fabs(ref);
+    }
+  }
+  s = block_fold(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_validate_final(const Stats *__restrict__ partial, int n, double *__restrict__ out) {
+  Stats s = identity();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) fold(s, partial[i]);
+  s = block_fold(s);
+  if (threadIdx.x == 0) {
+    out[0] = s.vmin; out[1] = s.vmax; out[2] = s.maxerr; out[3] = s.sumerr; out[4] = s.sumref;
+  }
+}
+
+}  // namespace
+
+size_t csc2_validate_scratch_bytes() { return (size_t)CSC2_VALIDATE_MAX_CTAS * sizeof(Stats); }
+
+cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *field, int nproma,
+                                 long long rows, int ngptot, int nblocks, long long gcol0,
+                                 void *scratch, double *out5, cudaStream_t s) {
+  const long long total = (long long)nproma * rows * nblocks;
+  long long ctas = (total + 255) / 256;
+  if (ctas > CSC2_VALIDATE_MAX_CTAS) ctas = CSC2_VALIDATE_MAX_CTAS;
+  if (ctas < 1) ctas = 1;
+  k_validate_partial<<<(int)ctas, 256, 0, s>>>(ref_src, nlon, field, nproma, rows, ngptot, gcol0,
+                                               total, static_cast<Stats *>(scratch));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_validate_final<<<1, 256, 0, s>>>(static_cast<const Stats *>(scratch), (int)ctas, out5);
+  return cudaGetLastError();
+}

@@ -276,6 +276,28 @@ class Cloudsc2:
         self._check(self.lib.cloudsc2_gpu_expand_shard_dev(src_ptr, nlon, nlev, ndim, dst_ptr,
                                                            nproma, ngptot, gcol0, stream))
 
+    def validate_dev(self, ref_src_ptr: int, nlon: int, field_ptr: int, nproma: int, nlev: int,
+                     ndim: int, ngptot: int, gcol0: int = 0) -> np.ndarray:
+        """validate_mod.F90:165-261 on the device -> [min, max, max|err|, sum|err|, sum|ref|]."""
+        self._bind()
+        out = np.zeros(5)
+        self._check(self.lib.cloudsc2_gpu_validate_dev(ref_src_ptr, nlon, field_ptr, nproma, nlev,
+                                                       ndim, ngptot, gcol0,
+                                                       out.ctypes.data_as(_abi.c_double_p)))
+        return out
+
+    def satur(self, pap: np.ndarray, pt: np.ndarray) -> np.ndarray:
+        """SATUR (satur.F90:106-123) elementwise on the GPU."""
+        self._bind()
+        pap = np.ascontiguousarray(pap, dtype=np.float64)
+        pt = np.ascontiguousarray(pt, dtype=np.float64)
+        assert pap.shape == pt.shape
+        out = np.empty_like(pt)
+        dp = _abi.c_double_p
+        self._check(self.lib.cloudsc2_gpu_satur(pt.size, pap.ctypes.data_as(dp), pt.ctypes.data_as(dp),
+                                                out.ctypes.data_as(dp)))
+        return out
+
     def set_option(self, name: str, value: int):
         """cloudsc2_gpu_set_option: 'e2e_mode', 'e2e_chunk_mb', 'nl_variant'."""
         self._check(self.lib.cloudsc2_gpu_set_option(name.encode(), int(value)))

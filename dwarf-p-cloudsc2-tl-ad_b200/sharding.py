@@ -72,3 +72,14 @@ def sharded_adjoint(gpu, src, nproma: int, ngptot_global: int, rank: int, world:
         st = ArrayState(src, nproma, sh.ngptot, gcol0=sh.gcol0)
         zn, _ = gpu.ad_test(st)
     return float(allreduce_norms([zn], "max", device)[0]), sh
+
+
+def allreduce_validation(stats, device=None):
+    """Combine per-rank validation statistics [min, max, max|err|, sum|err|, sum|ref|] the way the
+    reference does (CLOUDSC_MPI_REDUCE_MIN / _MAX / _SUM, validate_mod.F90:197-199)."""
+    s = np.asarray(stats, dtype=np.float64)
+    out = np.empty(5)
+    out[0] = allreduce_norms(s[0:1], "min", device)[0]
+    out[1:3] = allreduce_norms(s[1:3], "max", device)
+    out[3:5] = allreduce_norms(s[3:5], "sum", device)
+    return out

@@ -104,6 +104,11 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy,
 int cloudsc2_gpu_nl_dev(int nproma, int klev, int ngptot, double ptsphy,
                         const cloudsc2_fields *dev, const double *pqs, void *stream);
 
+/* SATUR alone (satur.F90:10, LDPHYLIN branch :106-123, called with KFLAG=2 at
+ * cloudsc_driver_mod.F90:91-92): pqsat[i] = qsat(pt[i], pap[i]) for n points of any layout.
+ * HOST pointers; for users of the CLOUDSC2-call semantics who need PQS explicitly. */
+int cloudsc2_gpu_satur(long long n, const double *pap, const double *pt, double *pqsat);
+
 /* ---- tangent linear / adjoint on full fields ---------------------------------------- */
 
 /* CLOUDSC2TL (cloudsc2_tl/cloudsc2tl.F90:10-24) preceded by SATUR for the trajectory PQS
@@ -164,6 +169,21 @@ int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim,
  * (gcol0 + j) mod nlon, for the ngptot local columns of this shard. */
 int cloudsc2_gpu_expand_shard_dev(const double *src, int nlon, int nlev, int ndim, double *dst,
                                   int nproma, int ngptot, long long gcol0, void *stream);
+
+/* ---- device-side validation (next row 8f-2) ------------------------------------------------ */
+
+/* Error statistics of one computed field against reference columns, "in the L1 norm sense":
+ * replaces VALIDATE_R2 / VALIDATE_R3 (common/module/validate_mod.F90:165-261).
+ *   ref_src : DEVICE pointer, un-expanded reference columns (nlon, nlev, ndim) column-major (the
+ *             layout of reference.h5); global column g is compared with source column
+ *             (gcol0 + g) mod nlon, i.e. with what EXPAND of the reference would have produced
+ *   field   : DEVICE pointer, blocked (nproma, nlev, ndim, nblocks)
+ *   out[5]  : HOST: min(field), max(field) over whole blocks; max|err|, sum|err|, sum|ref| over
+ *             the valid columns (same five numbers ERROR_PRINT receives, :263-296).
+ * For a block-sharded run reduce out[] over ranks with min, max, max, sum, sum (the reference's
+ * CLOUDSC_MPI_REDUCE_MIN/MAX/SUM, :197-199). Synchronous. */
+int cloudsc2_gpu_validate_dev(const double *ref_src, int nlon, const double *field, int nproma,
+                              int nlev, int ndim, int ngptot, long long gcol0, double out[5]);
 
 /* ---- device memory helpers for non-torch hosts ------------------------------------------ */
 int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes);

@@ -52,7 +52,15 @@ def _worker(rank, world, port, nproma, ngptot, q):
         be_ad = OracleBackend(ob, pkg.default_params(lregcl=True), src.ceta)
         zn, _ = pkg.sharded_adjoint(be_ad, src, nproma, ngptot, rank, world)
         s = pkg.allreduce_norms([float(sh.ngptot), float(sh.nblocks)], "sum")
-        q.put((rank, z, zn, s, sh))
+        # validation statistics of this rank's shard of PT against the source columns, combined as
+        # validate_mod.F90:197-199 does (min / max / sum over ranks)
+        st = pkg.ArrayState(src, nproma, max(sh.ngptot, 1), gcol0=sh.gcol0)
+        v = pkg.validate(st.a["pt"] + 1e-3 * (rank + 1), st.a["pt"], max(sh.ngptot, 1))
+        loc = [v["min"], v["max"], v["max_abs_err"], v["sum_abs_err"], v["sum_abs_ref"]]
+        if sh.ngptot == 0:
+            loc = [np.inf, -np.inf, 0.0, 0.0, 0.0]
+        vs = pkg.allreduce_validation(loc)
+        q.put((rank, z, zn, s, sh, vs, loc))
     finally:
         dist.destroy_process_group()
 
@@ -74,11 +82,15 @@ def test_sharded_tests_world2_gloo(pkg, ob, src100, nproma, ngptot):
     z_all, _, _ = ob.driver_tl(pkg.default_params(lregcl=False), src100.ceta, st, numomp=2)
     zn_all, _, _ = ob.driver_ad(pkg.default_params(lregcl=True), src100.ceta,
                                 pkg.ArrayState(src100, nproma, ngptot), numomp=2)
-    for rank, z, zn, s, sh in res:
+    for rank, z, zn, s, sh, vs, loc in res:
         assert np.array_equal(z, z_all)              # max over blocks is order independent: exact
         assert zn == zn_all
         assert s[0] == ngptot and s[1] == st.nblocks  # shards tile the problem
     assert res[0][4].gcol0 == 0 and res[1][4].gcol0 == res[0][4].ngptot
+    locs = np.array([r[6] for r in res])
+    want = [locs[:, 0].min(), locs[:, 1].max(), locs[:, 2].max(), locs[:, 3].sum(), locs[:, 4].sum()]
+    for r in res:
+        assert np.allclose(r[5], want, rtol=1e-15, atol=0)
 
 
 def test_shard_blocks_tiles_every_problem(pkg):
