@@ -236,20 +236,7 @@ def main():
     assert stream != 0
 
     # device-resident problem: upload the 100 source columns once, expand on the device
-    ds = pkg.DeviceState(gpu, nproma=nproma, klev=KLEV, ngptot=ngp)
-    srcmap = {"pt": "pt", "pq": "pq", "pap": "pap", "paph": "paph", "plu": "plu", "plude": "plude",
-              "pmfu": "pmfu", "pmfd": "pmfd", "psupsat": "psupsat", "pa": "pa", "pclv": "pclv",
-              "b_cml": "tend_cml"}
-    for dst, s in srcmap.items():
-        a = np.ascontiguousarray(src.f[s])
-        nlev = a.shape[-2]
-        ndim = a.size // (nlev * 100)
-        p = gpu.malloc(a.nbytes)
-        gpu.h2d(p, a)
-        gpu.expand_dev(p, 100, nlev, ndim, ds.ptr[dst], nproma, ngp, stream=stream, gcol0=sh.gcol0)
-        torch.cuda.synchronize()
-        gpu.free(p)
-    ds.zero(("b_loc", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn"))
+    ds = pkg.DeviceState.from_source(gpu, src, nproma, ngp, gcol0=sh.gcol0, stream=stream)
     torch.cuda.synchronize()
 
     peak, peak_src = load_peaks()

@@ -136,13 +136,13 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double zcor5 = csc2_rcp(1.0 - c.retv * zesdp5);
   const double zdqsdtemp5 = zfac5 * zcor5 * pqs5;
 
-  const double zcrh2 = crit_rh(crh, c.ceta[jk], c.sq1mceta[jk]);
+  const double zcrh2 = crit_rh(crh, CSC2_CETA(jk), CSC2_SQ1MCETA(jk));
   const bool vcold = ztp25 < c.rtice;
   const double zsupsat5 = vcold ? (1.8 - 3.e-03 * ztp25) : 1.0;
   const double zqsat5 = pqs5 * zsupsat5;
   const double zqcrit5 = zcrh2 * zqsat5;
 
-  const double zscalm = c.zscalm[jk];
+  const double zscalm = CSC2_ZSCALM(jk);
   const double zqt5 = zqp25 + zl5 + zi5;
   int cbranch;                                             // 0 clear, 1 overcast, 2 partial
   double zclc5, zqc15, zqpd5 = 0.0, zqcd5 = 0.0, zsqrt5 = 1.0, den5_inv = 0.0;

@@ -303,3 +303,8 @@ cudaError_t csc2_launch_ad_finalize(const Geom &g, const double *n1, const doubl
   k_ad_finalize<<<grid, 128, 0, s>>>(g, n1, n2, norms_col, znormg);
   return cudaGetLastError();
 }
+
+cudaError_t csc2_upload_levels_ad(const double *ceta, const double *zscalm, const double *sq1mceta,
+                                  int klev, cudaStream_t s) {
+  return csc2_upload_levels_impl(ceta, zscalm, sq1mceta, klev, s);
+}

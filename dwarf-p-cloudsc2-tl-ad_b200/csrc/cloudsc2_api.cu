@@ -116,9 +116,6 @@ KConst make_kconst(double ptsphy) {
   c.klev = g.klev;
   c.kwin0 = g.kwin0;
   c.kwin1 = g.kwin1;
-  std::memcpy(c.ceta, g.ceta, sizeof(double) * g.klev);
-  std::memcpy(c.zscalm, g.zscalm, sizeof(double) * g.klev);
-  for (int k = 0; k < g.klev; ++k) c.sq1mceta[k] = std::sqrt(std::max(1.0 - g.ceta[k], 0.0));
   return c;
 }
 
@@ -288,6 +285,14 @@ int cloudsc2_gpu_init(const cloudsc2_params *params, int klev, const double *cet
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (int i = 0; i < kStreams; ++i) CK(cudaStreamCreateWithFlags(&g.pipe[i], cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&g.ev[i]));
+  {
+    // per-level constants -> __constant__ tables of the three kernel translation units
+    std::vector<double> sq(klev);
+    for (int k = 0; k < klev; ++k) sq[k] = std::sqrt(std::max(1.0 - ceta[k], 0.0));   // cloudsc2.F90:398
+    CK(csc2_upload_levels_nl(g.ceta, g.zscalm, sq.data(), klev, g.stream));
+    CK(csc2_upload_levels_tl(g.ceta, g.zscalm, sq.data(), klev, g.stream));
+    CK(csc2_upload_levels_ad(g.ceta, g.zscalm, sq.data(), klev, g.stream));
+  }
   g.launches = 0;
   g.init = true;
   return 0;
@@ -315,16 +320,27 @@ int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes) {
   return 0;
 }
 int cloudsc2_gpu_free(void *ptr) { CK(cudaFree(ptr)); return 0; }
+// The helpers are synchronous AND ordered with the library's (non-blocking) streams: a plain
+// cudaMemset / cudaMemcpy runs on the legacy default stream, with which non-blocking streams do
+// not synchronise -- a cudaMemset of an output array could then land after the kernel that was
+// launched later on the library stream (seen at NGPTOT = 1.3 M: zeroed flux arrays).
 int cloudsc2_gpu_memcpy_h2d(void *dst, const void *src, unsigned long long bytes) {
-  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  if (int rc = require_init()) return rc;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
   return 0;
 }
 int cloudsc2_gpu_memcpy_d2h(void *dst, const void *src, unsigned long long bytes) {
-  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  if (int rc = require_init()) return rc;
+  CK(cudaDeviceSynchronize());      // results may have been produced on a caller stream
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
   return 0;
 }
 int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes) {
-  CK(cudaMemset(dst, value, bytes));
+  if (int rc = require_init()) return rc;
+  CK(cudaMemsetAsync(dst, value, bytes, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
   return 0;
 }
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes) {
@@ -338,8 +354,7 @@ int cloudsc2_gpu_host_unregister(void *ptr) {
 }
 int cloudsc2_gpu_sync(void) {
   if (int rc = require_init()) return rc;
-  CK(cudaStreamSynchronize(g.stream));
-  for (int i = 0; i < kStreams; ++i) CK(cudaStreamSynchronize(g.pipe[i]));
+  CK(cudaDeviceSynchronize());     // library streams and any caller stream handed to the _dev entries
   return 0;
 }
 

@@ -11,7 +11,7 @@
 #include "../../include/cloudsc2_b200.h"
 #include "cloudsc2_math.cuh"
 
-#define CSC2_KLEV_MAX 192   // KLEV of the dwarf is 137; bound so that KConst fits the param space
+#define CSC2_KLEV_MAX 256   // KLEV of the dwarf is 137
 
 // Constants of one run, passed by value to every kernel (lives in the constant bank).
 struct KConst {
@@ -30,10 +30,36 @@ struct KConst {
   int lregcl;              // YRNCL%LREGCL
   int klev;
   int kwin0, kwin1;        // bounding range of levels with 0.1 < CETA < 0.4 (tropopause window)
-  double ceta[CSC2_KLEV_MAX];    // YRECLD%CETA
-  double zscalm[CSC2_KLEV_MAX];  // ZSCAL*MAX(CETA-0.2,ZEPS1)**0.2  (cloudsc2.F90:266)
-  double sq1mceta[CSC2_KLEV_MAX];  // SQRT(MAX(1-CETA,0)), factor of the lowest ZCRH2 segment (:398)
 };
+
+// Per-level constants of one run, in __constant__ memory (one copy per translation unit, uploaded
+// by csc2_upload_levels at cloudsc2_gpu_init):
+//   [0] YRECLD%CETA   [1] ZSCALM = ZSCAL*MAX(CETA-0.2,ZEPS1)**0.2 (cloudsc2.F90:266)
+//   [2] SQRT(MAX(1-CETA,0)), factor of the lowest ZCRH2 segment (:398)
+// They were part of the by-value KConst kernel parameter at first; that made the parameter block
+// 4.9 KB, and on this stack (sm_100a, driver 580, CUDA 12.9) parameters beyond byte 4096 were
+// read WRONG by a few CTAs of large grids (found by tests/test_gpu_next_rows.py at 655 360
+// columns: wrong SQRT(1-CETA) at levels >= 111).  All kernel parameter blocks are now < 1 KB
+// (static_assert below).
+static __constant__ double csc2_lev[3][CSC2_KLEV_MAX];
+#define CSC2_CETA(jk) csc2_lev[0][jk]
+#define CSC2_ZSCALM(jk) csc2_lev[1][jk]
+#define CSC2_SQ1MCETA(jk) csc2_lev[2][jk]
+static_assert(sizeof(KConst) <= 512, "keep the kernel parameter block small");
+
+// host side, one instance per translation unit that contains kernels (see cloudsc2_launch.h)
+static inline cudaError_t csc2_upload_levels_impl(const double *ceta, const double *zscalm,
+                                                  const double *sq1mceta, int klev, cudaStream_t s) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(csc2_lev, ceta, klev * sizeof(double), 0, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbolAsync(csc2_lev, zscalm, klev * sizeof(double), CSC2_KLEV_MAX * sizeof(double),
+                                cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = cudaMemcpyToSymbolAsync(csc2_lev, sq1mceta, klev * sizeof(double), 2 * CSC2_KLEV_MAX * sizeof(double),
+                                cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  return e;
+}
 
 // Addressing of the blocked arrays: element (jl, jk, ibl) of a field with block stride bs is
 // p[ibl*bs + jk*nproma + jl].  The same kernels serve the reference's host layout
@@ -121,7 +147,7 @@ __device__ __forceinline__ double tropopause_eta(const KConst &c, const double *
   double t_hi = pt[o_pt + (size_t)c.kwin0 * nproma] + c.ptsphy * gt[o_gt + (size_t)c.kwin0 * nproma];
   for (int jk = c.kwin0; jk <= c.kwin1; ++jk) {       // kwin1 <= klev-2
     double t_lo = pt[o_pt + (size_t)(jk + 1) * nproma] + c.ptsphy * gt[o_gt + (size_t)(jk + 1) * nproma];
-    double e = c.ceta[jk];
+    double e = CSC2_CETA(jk);
     if (e > 0.1 && e < 0.4 && t_hi > t_lo) ztrpaus = e;
     t_hi = t_lo;
   }

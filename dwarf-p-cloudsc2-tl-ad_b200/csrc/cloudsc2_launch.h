@@ -75,3 +75,12 @@ cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *
 // SATUR alone, elementwise over n points (device pointers).
 cudaError_t csc2_launch_satur(const KConst &c, const double *pap, const double *pt, double *pqsat,
                               long long n, cudaStream_t s);
+
+// Upload CETA / ZSCALM / SQRT(1-CETA) (klev values each, host pointers) into the __constant__
+// level table of each kernel translation unit.  Called by cloudsc2_gpu_init.
+cudaError_t csc2_upload_levels_nl(const double *ceta, const double *zscalm, const double *sq1mceta,
+                                  int klev, cudaStream_t s);
+cudaError_t csc2_upload_levels_tl(const double *ceta, const double *zscalm, const double *sq1mceta,
+                                  int klev, cudaStream_t s);
+cudaError_t csc2_upload_levels_ad(const double *ceta, const double *zscalm, const double *sq1mceta,
+                                  int klev, cudaStream_t s);

@@ -85,13 +85,13 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   const double zdqsdtemp = zfac * zcor * pqs;
 
   // critical humidity, ice supersaturation (:384-408)
-  const double zcrh2 = crit_rh(crh, c.ceta[jk], c.sq1mceta[jk]);
+  const double zcrh2 = crit_rh(crh, CSC2_CETA(jk), CSC2_SQ1MCETA(jk));
   const double zsupsat = (ztp1 < c.rtice) ? (1.8 - 3.e-03 * ztp1) : 1.0;
   const double zqsat = pqs * zsupsat;
   const double zqcrit = zcrh2 * zqsat;
 
   // uniform total-water distribution (:412-427)
-  const double zscalm = c.zscalm[jk];
+  const double zscalm = CSC2_ZSCALM(jk);
   const double zqt = zqp1 + zl + zi;
   double pclc, zqc;
   {

@@ -234,3 +234,8 @@ cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, doub
   k_expand<<<(int)blocks, 256, 0, s>>>(src, nlon, rows, dst, nproma, ngptot, gcol0, total);
   return cudaGetLastError();
 }
+
+cudaError_t csc2_upload_levels_nl(const double *ceta, const double *zscalm, const double *sq1mceta,
+                                  int klev, cudaStream_t s) {
+  return csc2_upload_levels_impl(ceta, zscalm, sq1mceta, klev, s);
+}

@@ -105,7 +105,7 @@ __device__ __forceinline__ void tl_level(const KConst &c, const CritRH &crh, int
   const double zdqsdtemp5 = zfac5 * zcor5 * pqs5;
 
   // critical humidity, ice supersaturation (:505-539)
-  const double zcrh2 = crit_rh(crh, c.ceta[jk], c.sq1mceta[jk]);
+  const double zcrh2 = crit_rh(crh, CSC2_CETA(jk), CSC2_SQ1MCETA(jk));
   const bool vcold = ztp15 < c.rtice;
   const double zsupsat5 = vcold ? 1.8 - 3.e-03 * ztp15 : 1.0;
   const double zsupsat = vcold ? -3.e-03 * ztp1 : 0.0;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void tl_level(const KConst &c, const CritRH &crh, int
   const double zqcrit5 = zcrh2 * zqsat5, zqcrit = zcrh2 * zqsat;
 
   // uniform distribution (:543-593)
-  const double zscalm = c.zscalm[jk];
+  const double zscalm = CSC2_ZSCALM(jk);
   const double zqt = zqp1 + zl + zi, zqt5 = zqp15 + zl5 + zi5;
   double pclc, pclc5, zqc, zqc5;
   {

@@ -227,7 +227,7 @@ k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, con
     double t_hi = tfg(c.kwin0);
     for (int jk = c.kwin0; jk <= c.kwin1; ++jk) {
       const double t_lo = tfg(jk + 1);
-      const double e = c.ceta[jk];
+      const double e = CSC2_CETA(jk);
       if (e > 0.1 && e < 0.4 && t_hi > t_lo) ztrpaus = e;
       t_hi = t_lo;
     }
@@ -356,4 +356,9 @@ cudaError_t csc2_launch_taylor_finalize(const Geom &g, const double *tlsum, cons
   k_taylor_finalize<<<(n + 127) / 128, 128, 0, s>>>(g, make_lambdas(), tlsum, diffsum, ncol_pad,
                                                     ratios_blk, znormg, degenerate);
   return cudaGetLastError();
+}
+
+cudaError_t csc2_upload_levels_tl(const double *ceta, const double *zscalm, const double *sq1mceta,
+                                  int klev, cudaStream_t s) {
+  return csc2_upload_levels_impl(ceta, zscalm, sq1mceta, klev, s);
 }

@@ -86,6 +86,33 @@ class DeviceState:
         if st is not None:
             self.upload(st)
 
+    # input.h5 dataset -> member of the blocked state (cloudsc2_array_state_mod.F90:153-203)
+    SOURCE_MAP = {"pt": "pt", "pq": "pq", "pap": "pap", "paph": "paph", "plu": "plu",
+                  "plude": "plude", "pmfu": "pmfu", "pmfd": "pmfd", "psupsat": "psupsat", "pa": "pa",
+                  "pclv": "pclv", "b_cml": "tend_cml"}
+
+    @classmethod
+    def from_source(cls, gpu: "Cloudsc2", src, nproma: int, ngptot: int, gcol0: int = 0,
+                    stream: int | None = None) -> "DeviceState":
+        """CLOUDSC2_ARRAY_STATE%LOAD with the expansion done ON THE DEVICE: upload the un-expanded
+        source columns (a few MB) and replicate them cyclically into NGPTOT columns
+        (expand_mod.F90:270-335 -> cloudsc2_gpu_expand_shard_dev); outputs are zeroed."""
+        ds = cls(gpu, nproma=nproma, klev=src.klev, ngptot=ngptot)
+        for dst, name in cls.SOURCE_MAP.items():
+            a = np.ascontiguousarray(src.f[name])
+            nlev = a.shape[-2]
+            ndim = a.size // (nlev * src.klon)
+            p = gpu.malloc(a.nbytes)
+            try:
+                gpu.h2d(p, a)
+                gpu.expand_dev(p, src.klon, nlev, ndim, ds.ptr[dst], nproma, ngptot, stream=stream,
+                               gcol0=gcol0)
+                gpu.sync()
+            finally:
+                gpu.free(p)
+        ds.zero(("b_loc", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn"))
+        return ds
+
     def upload(self, st: ArrayState, names=None):
         for n in names or self.sizes:
             self.gpu.h2d(self.ptr[n], st.a[n])

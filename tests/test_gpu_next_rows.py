@@ -101,3 +101,72 @@ def test_nl_results_validate_clean_against_a_second_run(pkg, src100, gpu_nl):
             gpu_nl.free(dfld)
         assert st[2] == 0.0 and st[3] == 0.0 and st[4] > 0.0, n
         assert pkg.report.error_print(n, st, 4000).split()[1] in ("2D1",)
+
+
+def _validate_outputs_against_small_run(pkg, gpu, ds, small, ngptot, nproma, names):
+    for n, nlev in names:
+        ref_src = np.ascontiguousarray(small.a[n][0])
+        dsrc = gpu.malloc(ref_src.nbytes)
+        try:
+            gpu.h2d(dsrc, ref_src)
+            st = gpu.validate_dev(dsrc, 100, ds.ptr[n], nproma, nlev, 1, ngptot)
+        finally:
+            gpu.free(dsrc)
+        assert st[2] == 0.0 and st[3] == 0.0 and st[4] > 0.0, (n, st)
+        assert st[0] == small.a[n][0].min() and st[1] == small.a[n][0].max(), n
+
+
+def test_nl_scaling_size_on_device(pkg, src100, gpu_nl):
+    """BASELINE config 5 size: NGPTOT = 1 310 720, NPROMA = 128, everything device-resident (device
+    expansion, kernel, device validation).  Size-independent property: the expansion is cyclic, so
+    every output must equal the 100-column run bit for bit -> zero validation error."""
+    nproma, ngptot = 128, 1310720
+    small = pkg.ArrayState(src100, 100, 100)
+    gpu_nl.nl(small)
+    ds = pkg.DeviceState.from_source(gpu_nl, src100, nproma, ngptot)
+    try:
+        gpu_nl.nl_dev(ds, src100.ptsphy)
+        gpu_nl.sync()
+        _validate_outputs_against_small_run(pkg, gpu_nl, ds, small, ngptot, nproma,
+                                            (("pa", 137), ("pfplsl", 138), ("pfplsn", 138),
+                                             ("pfhpsl", 138), ("pfhpsn", 138), ("pcovptot", 137)) [:5])
+        # the four tendency slabs of B_LOC: slab s of block b sits at (b*8 + s) * 137 * 128
+        loc = np.empty((ds.nblocks, 8, 137, nproma))
+        # only the first 4 blocks are brought back (1280 x 8 slabs would be 11.5 GB)
+        part = np.empty((4, 8, 137, nproma))
+        gpu_nl.d2h(part, ds.ptr["b_loc"])
+        del loc
+        cols = np.arange(4 * nproma) % 100
+        for slab in (0, 2, 3, 4):
+            got = np.ascontiguousarray(np.transpose(part[:, slab], (1, 0, 2))).reshape(137, -1)
+            assert np.array_equal(got, small.a["b_loc"][0, slab][:, cols]), slab
+    finally:
+        ds.free()
+
+
+def test_taylor_and_adjoint_tests_at_throughput_size(pkg, src100):
+    """The reference's two self-tests at NGPTOT = 163 840 / NPROMA = 128 (bench size), device
+    resident: same verdicts, and -- the columns being cyclic copies -- the same ZNORMG as the
+    100-column problems, exactly (max over identical per-block / per-column values)."""
+    nproma, ngptot = 128, 163840
+    with pkg.Cloudsc2(pkg.default_params(lregcl=False), 137, src100.ceta) as gpu:
+        ds = pkg.DeviceState.from_source(gpu, src100, nproma, ngptot)
+        try:
+            z, rb = gpu.tl_taylor(ds, src100.ptsphy)
+        finally:
+            ds.free()
+        pen, istart = pkg.taylor_verdict(z)
+        assert 0 <= pen <= 5, (pen, z)
+        # blocks repeat with period lcm(128, 100) / 128 = 25 blocks
+        assert np.array_equal(rb[:25], rb[25:50]) and np.array_equal(rb[:25], rb[1250:1275])
+    with pkg.Cloudsc2(pkg.default_params(lregcl=True), 137, src100.ceta) as gpu:
+        ds = pkg.DeviceState.from_source(gpu, src100, nproma, ngptot)
+        try:
+            zn, nc = gpu.ad_test(ds, src100.ptsphy)
+        finally:
+            ds.free()
+        assert pkg.adjoint_verdict(zn), zn
+        small = pkg.ArrayState(src100, 100, 100)
+        zn100, nc100 = gpu.ad_test(small)
+        assert zn == zn100
+        assert np.array_equal(nc[:100], nc100) and np.array_equal(nc[100:200], nc100)
