@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the NPROMA sweep of BASELINE config 4")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -325,6 +326,18 @@ def main():
         for p in list(din.values()) + list(dout.values()):
             gpu.free(p)
 
+    # ---- NPROMA sweep (BASELINE config 4: NGPTOT = 160 000, NPROMA 32..256), NL kernel only ---
+    sweep = None
+    if not args.no_sweep and world == 1:
+        sweep = {}
+        for npr in (32, 64, 128, 256):
+            d2 = pkg.DeviceState.from_source(gpu, src, npr, 160000, stream=stream)
+            torch.cuda.synchronize()
+            ms = timed(lambda: gpu.nl_dev(d2, src.ptsphy, stream=stream), 5, 3)
+            sweep[str(npr)] = {"columns_per_s": 160000 / (ms * 1e-3), "ms_per_step": ms,
+                               "frac_of_hbm": NL_BYTES_PER_COL * 160000 / (ms * 1e-3) / 1e9 / peak}
+            d2.free()
+
     # ---- e2e through the host-pointer C ABI call ----------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -385,7 +398,7 @@ def main():
                              "algorithmic_bytes_per_launch": NL_BYTES_PER_COL * ngp,
                              "fp64_pipe_pct_ncu": NCU["nl"]["fp64_pipe_pct"]},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
-                "modes": results}
+                "modes": results, "nproma_sweep_ngptot160000": sweep}
         print(json.dumps(line))
     ds.free()
     gpu.close()
