@@ -243,6 +243,16 @@ bool map_host_fields(const cloudsc2_fields &h, cloudsc2_fields &d) {
 
 }  // namespace
 
+// context access for the per-block Fortran-ABI shims (cloudsc2_fortran_shims.cu)
+int csc2_shim_context(KConst *kc, double ptsphy, int klev, cudaStream_t *stream, long long *launches) {
+  if (!g.init || klev != g.klev) return 1;
+  *kc = make_kconst(ptsphy);
+  *stream = g.stream;
+  *launches = g.launches;
+  return 0;
+}
+void csc2_shim_count_launch() { g.launches += 1; }
+
 extern "C" {
 
 const char *cloudsc2_gpu_last_error(void) { return g_err; }

@@ -69,12 +69,14 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
 
   if (gcol >= g.ngptot) {
-    // padding column of the last block: the driver zeroes whole blocks (driver_mod.F90:87-88),
-    // the kernel itself never computes columns beyond ICEND.
-    for (int jk = 0; jk < klev; ++jk) {
-      stout(out.pcovptot + o.o1 + (size_t)jk * nproma, 0.0);
-      if (out.loc_last) stout(out.loc_last + o.oloc + (size_t)jk * nproma, 0.0);
-    }
+    // padding column of the last block: the DRIVER zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV)
+    // of whole blocks (driver_mod.F90:87-88); CLOUDSC2 itself never touches columns beyond ICEND.
+    // loc_last != NULL marks the driver-level call (NULL: plain CLOUDSC2 semantics, e.g. cloudsc2_).
+    if (out.loc_last)
+      for (int jk = 0; jk < klev; ++jk) {
+        stout(out.pcovptot + o.o1 + (size_t)jk * nproma, 0.0);
+        stout(out.loc_last + o.oloc + (size_t)jk * nproma, 0.0);
+      }
     return;
   }
 

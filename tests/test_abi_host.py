@@ -30,6 +30,10 @@ def test_header_symbols_are_exported(pkg):
     exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
     missing = [n for n in declared if n not in exported]
     assert not missing, missing
+    # Fortran-ABI per-block shims (include/cloudsc2_fortran.h)
+    for n in ("satur_", "cloudsc2_", "cloudsc2tl_", "cloudsc2ad_"):
+        assert n in exported, n
+        assert n + "(" in (ROOT / "include" / "cloudsc2_fortran.h").read_text()
     for n in declared:
         assert getattr(lib, n) is not None
     # and the ctypes table covers exactly the header
