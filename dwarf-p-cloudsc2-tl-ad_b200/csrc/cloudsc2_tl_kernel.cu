@@ -6,6 +6,8 @@
 //                       slice per lambda, perturbation applied on load, emitting only
 //                       sum_levels(F - F5) per column and field.
 //  k_taylor_finalize  : ERROR_NORM (:21-31) per block and lambda, max over blocks (:247-252).
+#include <cstdlib>
+
 #include "cloudsc2_tl.cuh"
 #include "cloudsc2_stage.cuh"
 #include "cloudsc2_launch.h"
@@ -18,7 +20,6 @@ __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 constexpr int NT = CSC2_TL_THREADS;
 // fields staged per level: 15 trajectory inputs, PQS (optional), 16 increments
 constexpr int TL_NF = 32;
-constexpr int TL_STAGES = 2;
 
 __device__ __forceinline__ void stage_traj(double *d, const TrajIn &in, const ColOffsets &o, int jk,
                                            int klev, int nproma) {
@@ -104,7 +105,7 @@ __device__ __forceinline__ LevIn scale_level(const LevIn &x, double f, bool zero
   return d;
 }
 
-template <bool ONFLY>
+template <bool ONFLY, int STAGES>
 __global__ void __launch_bounds__(CSC2_TL_THREADS)
 k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const TLOpts opt) {
@@ -121,9 +122,14 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const bool wr = dout.tent != nullptr;
   constexpr int SLOT = TL_NF * NT;
 
-  stage_traj(ring, in, o, 0, klev, nproma);
-  if (!ONFLY) stage_incr(ring, din, o, 0, klev, nproma);
-  csc2_cp_async_commit();
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < klev) {
+      stage_traj(ring + s * SLOT, in, o, s, klev, nproma);
+      if (!ONFLY) stage_incr(ring + s * SLOT, din, o, s, klev, nproma);
+    }
+    csc2_cp_async_commit();
+  }
 
   // ZTRPAUS from the trajectory only (cloudsc2tl.F90:431-442)
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
@@ -142,14 +148,15 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   double s_t = 0, s_q = 0, s_l = 0, s_i = 0, s_c = 0, s_fl = 0, s_fn = 0, s_hl = 0, s_hn = 0;
   double q_t = 0, q_q = 0, q_l = 0, q_i = 0, q_c = 0, q_fl = 0, q_fn = 0, q_hl = 0, q_hn = 0;
 
-  int slot = 0;
+  int slot = 0, pslot = STAGES - 1;
   for (int jk = 0; jk < klev; ++jk) {
-    if (jk + 1 < klev) {
-      stage_traj(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
-      if (!ONFLY) stage_incr(ring + (slot ^ 1) * SLOT, din, o, jk + 1, klev, nproma);
+    const int pf = jk + STAGES - 1;
+    if (pf < klev) {
+      stage_traj(ring + pslot * SLOT, in, o, pf, klev, nproma);
+      if (!ONFLY) stage_incr(ring + pslot * SLOT, din, o, pf, klev, nproma);
     }
     csc2_cp_async_commit();
-    csc2_cp_async_wait<1>();
+    csc2_cp_async_wait<STAGES - 1>();
     const double *d = ring + slot * SLOT;
     const LevIn cur = read_level(d, 0, jk, klev);
     const double pqs5 = in.pqs ? d[15 * NT] : satur_point(c, cur.pt, csc2_rcp(cur.pap));
@@ -185,7 +192,8 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     q_t += dy.tent * dy.tent; q_q += dy.tenq * dy.tenq; q_l += dy.tenl * dy.tenl;
     q_i += dy.teni * dy.teni; q_c += dy.pclc * dy.pclc; q_fl += dy.rfln * dy.rfln;
     q_fn += dy.sfln * dy.sfln; q_hl += hl * hl; q_hn += hn * hn;
-    slot ^= 1;
+    slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+    pslot = (pslot + 1 == STAGES) ? 0 : pslot + 1;
   }
   if (opt.colsum) {
     double *s = opt.colsum + gcol;
@@ -308,12 +316,12 @@ __global__ void k_taylor_finalize(const Geom g, const Lambdas lams, const double
 
 }  // namespace
 
-template <bool ONFLY>
+template <bool ONFLY, int STAGES>
 static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajIn &in,
                                      const TrajOut &out, const IncIn &din, const IncOut &dout,
                                      const TLOpts &opt, int grid, cudaStream_t s) {
-  const size_t smem = (size_t)TL_STAGES * TL_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_tl<ONFLY>;
+  const size_t smem = (size_t)STAGES * TL_NF * NT * sizeof(double);
+  auto kern = k_cloudsc2_tl<ONFLY, STAGES>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -324,12 +332,20 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
   return cudaGetLastError();
 }
 
+static int g_tl_stages = 0;
+void csc2_set_tl_stages(int v) { g_tl_stages = v; }
+
 cudaError_t csc2_launch_tl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            const IncIn &din, const IncOut &dout, const TLOpts &opt, cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + CSC2_TL_THREADS - 1) / CSC2_TL_THREADS);
-  if (opt.pert_scale != 0.0) return launch_tl_variant<true>(c, g, in, out, din, dout, opt, grid, s);
-  return launch_tl_variant<false>(c, g, in, out, din, dout, opt, grid, s);
+  if (g_tl_stages == 0) {
+    const char *e = getenv("CSC2_TL_STAGES");
+    g_tl_stages = e && atoi(e) == 3 ? 3 : 2;
+  }
+  if (opt.pert_scale != 0.0) return launch_tl_variant<true, 2>(c, g, in, out, din, dout, opt, grid, s);
+  if (g_tl_stages == 3) return launch_tl_variant<false, 3>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_tl_variant<false, 2>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 static Lambdas make_lambdas() {
