@@ -26,42 +26,6 @@ constexpr int NT = CSC2_AD_THREADS;
 constexpr int AD_NF = 27;
 constexpr int AD_STAGES = 2;
 
-// Asynchronous copies of the trajectory inputs of level jk into a ring slot.  LOWER selects which
-// half-level pressure goes to field 0: PAPHP1(JK+1) for the forward sweep, PAPHP1(JK) for the
-// reverse sweep (which carries PAPHP1(JK+1) over from the level it has just finished).
-template <bool LOWER>
-__device__ __forceinline__ void stage_traj(double *d, const TrajIn &in, const ColOffsets &o, int jk,
-                                           int klev, int nproma) {
-  const size_t l = (size_t)jk * nproma;
-  csc2_cp_async8(d + 0 * NT, in.paph + o.oh + l + (LOWER ? 0 : nproma));
-  csc2_cp_async8(d + 1 * NT, in.pap + o.o1 + l);
-  csc2_cp_async8(d + 2 * NT, in.pt + o.o1 + l);
-  csc2_cp_async8(d + 3 * NT, in.pq + o.o1 + l);
-  csc2_cp_async8(d + 4 * NT, in.pl + o.ocld + l);
-  csc2_cp_async8(d + 5 * NT, in.pi + o.ocld + l);
-  csc2_cp_async8(d + 6 * NT, in.plude + o.o1 + l);
-  if (jk < klev - 1) csc2_cp_async8(d + 7 * NT, in.plu + o.o1 + l + nproma);
-  csc2_cp_async8(d + 8 * NT, in.pmfu + o.o1 + l);
-  csc2_cp_async8(d + 9 * NT, in.pmfd + o.o1 + l);
-  csc2_cp_async8(d + 10 * NT, in.gt + o.ocml + l);
-  csc2_cp_async8(d + 11 * NT, in.gq + o.ocml + l);
-  csc2_cp_async8(d + 12 * NT, in.gl + o.ocml + l);
-  csc2_cp_async8(d + 13 * NT, in.gi + o.ocml + l);
-  csc2_cp_async8(d + 14 * NT, in.psupsat + o.o1 + l);
-  if (in.pqs) csc2_cp_async8(d + 15 * NT, in.pqs + o.o1 + l);
-}
-// field 0 is returned through `paph`, LevIn::paph1 is left to the caller
-__device__ __forceinline__ LevIn read_traj(const double *d, int jk, int klev, double &paph) {
-  LevIn x;
-  paph = d[0 * NT];
-  x.pap = d[1 * NT]; x.pt = d[2 * NT]; x.pq = d[3 * NT]; x.pl = d[4 * NT];
-  x.pi = d[5 * NT]; x.plude = d[6 * NT];
-  x.plu1 = (jk < klev - 1) ? d[7 * NT] : 0.0;
-  x.pmfu = d[8 * NT]; x.pmfd = d[9 * NT]; x.gt = d[10 * NT]; x.gq = d[11 * NT]; x.gl = d[12 * NT];
-  x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
-  return x;
-}
-
 // input-adjoint accumulation X = X + dX as a fire-and-forget reduction at the L2 (RED.ADD.F64):
 // no load latency on the thread's critical path, same DRAM traffic as a read-modify-write
 __device__ __forceinline__ void acc(double *p, double v) { atomicAdd(p, v); }
@@ -86,7 +50,7 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const size_t cks = (size_t)opt.ncol_pad;
   constexpr int SLOT = AD_NF * NT;
 
-  stage_traj<false>(ring, in, o, 0, klev, nproma);
+  csc2_stage_traj<NT, false>(ring, in, o, 0, klev, nproma);
   csc2_cp_async_commit();
 
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
@@ -106,13 +70,11 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     }
     int slot = 0;
     for (int jk = 0; jk < klev; ++jk) {
-      if (jk + 1 < klev) stage_traj<false>(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
+      if (jk + 1 < klev) csc2_stage_traj<NT, false>(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
       csc2_cp_async_commit();
       csc2_cp_async_wait<1>();
       const double *d = ring + slot * SLOT;
-      double paph1;
-      LevIn cur = read_traj(d, jk, klev, paph1);
-      cur.paph1 = paph1;
+      const LevIn cur = csc2_read_level<NT>(d, jk, klev);
       ck_r[(size_t)jk * cks] = st.rfl;
       ck_s[(size_t)jk * cks] = st.sfl;
       rfl_last = st.rfl;
@@ -142,7 +104,7 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   // level ahead; output adjoints are zeroed only after their staged copy has landed.
   auto stage_rev = [&](double *d, int jk) {
     const size_t l = (size_t)jk * nproma;
-    stage_traj<true>(d, in, o, jk, klev, nproma);
+    csc2_stage_traj<NT, true>(d, in, o, jk, klev, nproma);
     csc2_cp_async8(d + 16 * NT, ck_r + (size_t)jk * cks);
     csc2_cp_async8(d + 17 * NT, ck_s + (size_t)jk * cks);
     csc2_cp_async8(d + 18 * NT, dout.tent + o.o1 + l);
@@ -174,8 +136,8 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     csc2_cp_async_commit();
     csc2_cp_async_wait<1>();
     const double *d = ring + slot * SLOT;
-    double paph0;
-    LevIn x5 = read_traj(d, jk, klev, paph0);
+    LevIn x5 = csc2_read_level<NT>(d, jk, klev);   // field 0 is PAPHP15(JK) in the reverse sweep
+    const double paph0 = x5.paph1;
     x5.paph1 = paph_hi5;
     const double pqs5 = in.pqs ? d[15 * NT] : satur_point(c, x5.pt, csc2_rcp(x5.pap));
     const double rfl5 = (jk == klev - 1) ? rfl_last : d[16 * NT];

@@ -17,42 +17,7 @@ namespace {
 __device__ __forceinline__ double ldin(const double *p) { return __ldg(p); }
 __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 
-constexpr int NL_NF = 16;      // staged fields per level: 15 inputs + optional PQS
-
-// issue the asynchronous copies of level jk of this thread's column into ring slot `slot`
-template <bool HAS_PQS, int NT>
-__device__ __forceinline__ void stage_level(double *ring, int slot, const TrajIn &in,
-                                            const ColOffsets &o, int jk, int klev, int nproma) {
-  double *d = ring + (size_t)slot * (NL_NF * NT);
-  const size_t l = (size_t)jk * nproma;
-  csc2_cp_async8(d + 0 * NT, in.paph + o.oh + l + nproma);
-  csc2_cp_async8(d + 1 * NT, in.pap + o.o1 + l);
-  csc2_cp_async8(d + 2 * NT, in.pt + o.o1 + l);
-  csc2_cp_async8(d + 3 * NT, in.pq + o.o1 + l);
-  csc2_cp_async8(d + 4 * NT, in.pl + o.ocld + l);
-  csc2_cp_async8(d + 5 * NT, in.pi + o.ocld + l);
-  csc2_cp_async8(d + 6 * NT, in.plude + o.o1 + l);
-  if (jk < klev - 1) csc2_cp_async8(d + 7 * NT, in.plu + o.o1 + l + nproma);
-  csc2_cp_async8(d + 8 * NT, in.pmfu + o.o1 + l);
-  csc2_cp_async8(d + 9 * NT, in.pmfd + o.o1 + l);
-  csc2_cp_async8(d + 10 * NT, in.gt + o.ocml + l);
-  csc2_cp_async8(d + 11 * NT, in.gq + o.ocml + l);
-  csc2_cp_async8(d + 12 * NT, in.gl + o.ocml + l);
-  csc2_cp_async8(d + 13 * NT, in.gi + o.ocml + l);
-  csc2_cp_async8(d + 14 * NT, in.psupsat + o.o1 + l);
-  if (HAS_PQS) csc2_cp_async8(d + 15 * NT, in.pqs + o.o1 + l);
-}
-template <int NT>
-__device__ __forceinline__ LevIn read_level(const double *ring, int slot, int jk, int klev) {
-  const double *d = ring + (size_t)slot * (NL_NF * NT);
-  LevIn x;
-  x.paph1 = d[0 * NT]; x.pap = d[1 * NT]; x.pt = d[2 * NT]; x.pq = d[3 * NT]; x.pl = d[4 * NT];
-  x.pi = d[5 * NT]; x.plude = d[6 * NT];
-  x.plu1 = (jk < klev - 1) ? d[7 * NT] : 0.0;
-  x.pmfu = d[8 * NT]; x.pmfd = d[9 * NT]; x.gt = d[10 * NT]; x.gq = d[11 * NT]; x.gl = d[12 * NT];
-  x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
-  return x;
-}
+constexpr int NL_NF = CSC2_NTRAJ;   // staged fields per level: 15 inputs + optional PQS
 
 // STAGES = depth of the shared-memory ring (levels in flight + the one being computed)
 template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
@@ -83,7 +48,7 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   // start the pipeline before the tropopause pre-pass so that its latency is covered
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < klev) stage_level<HAS_PQS, NT>(ring, s, in, o, s, klev, nproma);
+    if (s < klev) csc2_stage_traj<NT, false, HAS_PQS ? 1 : 0>(ring + s * (NL_NF * NT), in, o, s, klev, nproma);
     csc2_cp_async_commit();
   }
 
@@ -102,10 +67,10 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   int slot = 0, pslot = STAGES - 1;
   for (int jk = 0; jk < klev; ++jk) {
     const int pf = jk + STAGES - 1;
-    if (pf < klev) stage_level<HAS_PQS, NT>(ring, pslot, in, o, pf, klev, nproma);
+    if (pf < klev) csc2_stage_traj<NT, false, HAS_PQS ? 1 : 0>(ring + pslot * (NL_NF * NT), in, o, pf, klev, nproma);
     csc2_cp_async_commit();
     csc2_cp_async_wait<STAGES - 1>();
-    const LevIn cur = read_level<NT>(ring, slot, jk, klev);
+    const LevIn cur = csc2_read_level<NT>(ring + slot * (NL_NF * NT), jk, klev);
     const double pqs = HAS_PQS ? ring[(size_t)slot * (NL_NF * NT) + 15 * NT]
                                : satur_point(c, cur.pt, csc2_rcp(cur.pap));
     LevOut y;

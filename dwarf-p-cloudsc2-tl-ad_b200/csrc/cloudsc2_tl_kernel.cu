@@ -21,26 +21,6 @@ constexpr int NT = CSC2_TL_THREADS;
 // fields staged per level: 15 trajectory inputs, PQS (optional), 16 increments
 constexpr int TL_NF = 32;
 
-__device__ __forceinline__ void stage_traj(double *d, const TrajIn &in, const ColOffsets &o, int jk,
-                                           int klev, int nproma) {
-  const size_t l = (size_t)jk * nproma;
-  csc2_cp_async8(d + 0 * NT, in.paph + o.oh + l + nproma);
-  csc2_cp_async8(d + 1 * NT, in.pap + o.o1 + l);
-  csc2_cp_async8(d + 2 * NT, in.pt + o.o1 + l);
-  csc2_cp_async8(d + 3 * NT, in.pq + o.o1 + l);
-  csc2_cp_async8(d + 4 * NT, in.pl + o.ocld + l);
-  csc2_cp_async8(d + 5 * NT, in.pi + o.ocld + l);
-  csc2_cp_async8(d + 6 * NT, in.plude + o.o1 + l);
-  if (jk < klev - 1) csc2_cp_async8(d + 7 * NT, in.plu + o.o1 + l + nproma);
-  csc2_cp_async8(d + 8 * NT, in.pmfu + o.o1 + l);
-  csc2_cp_async8(d + 9 * NT, in.pmfd + o.o1 + l);
-  csc2_cp_async8(d + 10 * NT, in.gt + o.ocml + l);
-  csc2_cp_async8(d + 11 * NT, in.gq + o.ocml + l);
-  csc2_cp_async8(d + 12 * NT, in.gl + o.ocml + l);
-  csc2_cp_async8(d + 13 * NT, in.gi + o.ocml + l);
-  csc2_cp_async8(d + 14 * NT, in.psupsat + o.o1 + l);
-  if (in.pqs) csc2_cp_async8(d + 15 * NT, in.pqs + o.o1 + l);
-}
 // increments from arrays (all plain (NPROMA,KLEV[+1],NBLOCKS)) -> fields 16..31
 __device__ __forceinline__ void stage_incr(double *d, const IncIn &di, const ColOffsets &o, int jk,
                                            int klev, int nproma) {
@@ -61,17 +41,6 @@ __device__ __forceinline__ void stage_incr(double *d, const IncIn &di, const Col
   csc2_cp_async8(d + 29 * NT, di.gi + o.o1 + l);
   csc2_cp_async8(d + 30 * NT, di.psupsat + o.o1 + l);
   csc2_cp_async8(d + 31 * NT, di.pqs + o.o1 + l);
-}
-// fields base..base+14 of a slot as a LevIn
-__device__ __forceinline__ LevIn read_level(const double *d, int base, int jk, int klev) {
-  LevIn x;
-  d += base * NT;
-  x.paph1 = d[0 * NT]; x.pap = d[1 * NT]; x.pt = d[2 * NT]; x.pq = d[3 * NT]; x.pl = d[4 * NT];
-  x.pi = d[5 * NT]; x.plude = d[6 * NT];
-  x.plu1 = (jk < klev - 1) ? d[7 * NT] : 0.0;
-  x.pmfu = d[8 * NT]; x.pmfd = d[9 * NT]; x.gt = d[10 * NT]; x.gq = d[11 * NT]; x.gl = d[12 * NT];
-  x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
-  return x;
 }
 // direct (unstaged) loads of one level, used by the Taylor-test kernel
 __device__ __forceinline__ LevIn load_level(const TrajIn &in, const ColOffsets &o, int jk, int klev,
@@ -125,7 +94,7 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < klev) {
-      stage_traj(ring + s * SLOT, in, o, s, klev, nproma);
+      csc2_stage_traj<NT, false>(ring + s * SLOT, in, o, s, klev, nproma);
       if (!ONFLY) stage_incr(ring + s * SLOT, din, o, s, klev, nproma);
     }
     csc2_cp_async_commit();
@@ -152,20 +121,20 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   for (int jk = 0; jk < klev; ++jk) {
     const int pf = jk + STAGES - 1;
     if (pf < klev) {
-      stage_traj(ring + pslot * SLOT, in, o, pf, klev, nproma);
+      csc2_stage_traj<NT, false>(ring + pslot * SLOT, in, o, pf, klev, nproma);
       if (!ONFLY) stage_incr(ring + pslot * SLOT, din, o, pf, klev, nproma);
     }
     csc2_cp_async_commit();
     csc2_cp_async_wait<STAGES - 1>();
     const double *d = ring + slot * SLOT;
-    const LevIn cur = read_level(d, 0, jk, klev);
+    const LevIn cur = csc2_read_level<NT>(d, jk, klev);
     const double pqs5 = in.pqs ? d[15 * NT] : satur_point(c, cur.pt, csc2_rcp(cur.pap));
     LevIn dx; double dpqs;
     if (ONFLY) {
       dx = scale_level(cur, opt.pert_scale, zero_sup);
       dpqs = pqs5 * opt.pert_scale;
     } else {
-      dx = read_level(d, 16, jk, klev);
+      dx = csc2_read_level<NT>(d + 16 * NT, jk, klev);
       dpqs = d[31 * NT];
     }
     LevOut y5, dy;
@@ -281,13 +250,17 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
   atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
-__global__ void k_taylor_finalize(const Geom g, const Lambdas lams, const double *__restrict__ tlsum,
-                                  const double *__restrict__ diffsum, const long long ncol_pad,
-                                  double *__restrict__ ratios_blk, double *__restrict__ znormg,
-                                  int *__restrict__ degenerate) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.nblocks * 10) return;
-  const int ibl = t / 10, ilam = t - ibl * 10;
+// One WARP per (block, lambda): lanes stride over the block's columns, the two sums of ERROR_NORM
+// (SUM(PTL), SUM(PNL-PNL5), cloudsc_driver_tl_mod.F90:21-31) are reduced with warp shuffles in a
+// fixed order (deterministic), lane 0 folds the ten fields and publishes the block's ratio.
+__global__ void __launch_bounds__(128)
+k_taylor_finalize(const Geom g, const Lambdas lams, const double *__restrict__ tlsum,
+                  const double *__restrict__ diffsum, const long long ncol_pad,
+                  double *__restrict__ ratios_blk, double *__restrict__ znormg,
+                  int *__restrict__ degenerate) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= g.nblocks * 10) return;               // whole warps leave together
+  const int ibl = w / 10, ilam = w - ibl * 10;
   const double lam = lams.v[ilam];
   const int c0 = ibl * g.nproma;
   int icend = g.ngptot - c0;
@@ -297,13 +270,18 @@ __global__ void k_taylor_finalize(const Geom g, const Lambdas lams, const double
     double s_tl = 0.0, s_d = 0.0;
     const double *a = tlsum + (size_t)f * ncol_pad + c0;
     const double *b = diffsum + ((size_t)ilam * 10 + f) * ncol_pad + c0;
-    for (int jl = 0; jl < icend; ++jl) { s_tl += a[jl]; s_d += b[jl]; }
+    for (int jl = lane; jl < icend; jl += 32) { s_tl += a[jl]; s_d += b[jl]; }
+    for (int off = 16; off > 0; off >>= 1) {
+      s_tl += __shfl_xor_sync(0xffffffffu, s_tl, off);
+      s_d += __shfl_xor_sync(0xffffffffu, s_d, off);
+    }
     const double den = s_tl * lam;
     if (fabs(den) > 2.220446049250313e-16) {   // EPSILON(ZLAMBDA)
       zcount += 1.0;
       znorm += fabs(s_d / den);
     }
   }
+  if (lane != 0) return;
   if (znorm == 0.0 || zcount == 0.0) {
     atomicAdd(degenerate, 1);
     ratios_blk[(size_t)ibl * 10 + ilam] = nan("");
@@ -368,8 +346,8 @@ cudaError_t csc2_launch_taylor_finalize(const Geom &g, const double *tlsum, cons
                                         int *degenerate, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(znormg, 0, 16 * sizeof(double), s);   // znormg[10] + flag
   if (e != cudaSuccess) return e;
-  const int n = g.nblocks * 10;
-  k_taylor_finalize<<<(n + 127) / 128, 128, 0, s>>>(g, make_lambdas(), tlsum, diffsum, ncol_pad,
+  const long long n = (long long)g.nblocks * 10 * 32;      // one warp per (block, lambda)
+  k_taylor_finalize<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, make_lambdas(), tlsum, diffsum, ncol_pad,
                                                     ratios_blk, znormg, degenerate);
   return cudaGetLastError();
 }
