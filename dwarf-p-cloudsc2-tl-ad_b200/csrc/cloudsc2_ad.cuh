@@ -105,12 +105,12 @@ __device__ __forceinline__ void cuadjtqsad_adj(const KConst &c, const AdjTraj &t
 //   ya            : output adjoints of the level
 //   ca            : carried flux adjoints (in: of the flux leaving the level, out: entering it)
 //   g             : the level's input adjoints
-template <bool RV /* RVTMP2 != 0 */>
+template <bool RV /* RVTMP2 != 0 */, bool LREG /* YRNCL%LREGCL */>
 __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int jk, const LevIn &x5,
                                          double pqs5, double paph0_5, double rfl5, double sfl5,
                                          const LevAdjIn &ya, CarryAD &ca, LevAdj &g) {
   const double dt = c.ptsphy;
-  const bool lreg = c.lregcl != 0;
+  constexpr bool lreg = LREG;
   // ================= trajectory of the level (same arithmetic as nl_level) =================
   const double ztp25 = x5.pt + dt * x5.gt;                 // pre-melt T (ZTP25)
   const double zqp25 = x5.pq + dt * x5.gq + x5.psupsat;    // first-guess q (ZQP25)

@@ -30,7 +30,7 @@ constexpr int AD_STAGES = 2;
 // no load latency on the thread's critical path, same DRAM traffic as a read-modify-write
 __device__ __forceinline__ void acc(double *p, double v) { atomicAdd(p, v); }
 
-template <bool RV, bool DOT>
+template <bool RV, bool DOT, bool LREG>
 // 3 CTAs/SM (168 registers, ~0.5 kB/thread of spills in L1) beats 2 CTAs/SM at 255 registers:
 // 3.67 vs 3.80 ms -- the reverse sweep is latency-bound, not register-bound
 __global__ void __launch_bounds__(CSC2_AD_THREADS, 3)
@@ -81,7 +81,7 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
       sfl_last = st.sfl;
       const double pqs = in.pqs ? d[15 * NT] : satur_point(c, cur.pt, csc2_rcp(cur.pap));
       LevOut y;
-      nl_level(c, crh, jk, cur, pqs, st, y);
+      nl_level<RV>(c, crh, jk, cur, pqs, st, y);
       if (opt.write_traj) {
         const size_t l = (size_t)jk * nproma;
         stout(out.tent + o.oloc + l, y.tent);
@@ -158,7 +158,7 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     dout.pfhpsl[o.oh + l + nproma] = 0.0; dout.pfhpsn[o.oh + l + nproma] = 0.0;
 
     LevAdj a;
-    ad_level<RV>(c, crh, jk, x5, pqs5, paph0, rfl5, sfl5, ya, ca, a);
+    ad_level<RV, LREG>(c, crh, jk, x5, pqs5, paph0, rfl5, sfl5, ya, ca, a);
 
     const double paph_hi = a.paph_hi + paph_pending;                  // total for PAPHP1(JK+1)
     paph_pending = a.paph_lo;
@@ -226,12 +226,12 @@ __global__ void k_ad_finalize(const Geom g, const double *__restrict__ n1, const
 
 }  // namespace
 
-template <bool RV, bool DOT>
-static cudaError_t launch_ad_variant(const KConst &c, const Geom &g, const TrajIn &in,
-                                     const TrajOut &out, const IncIn &din, const IncOut &dout,
-                                     const ADOpts &opt, int grid, cudaStream_t s) {
+template <bool RV, bool DOT, bool LREG>
+static cudaError_t launch_ad_k(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                               const IncIn &din, const IncOut &dout, const ADOpts &opt, int grid,
+                               cudaStream_t s) {
   const size_t smem = (size_t)AD_STAGES * AD_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_ad<RV, DOT>;
+  auto kern = k_cloudsc2_ad<RV, DOT, LREG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -240,6 +240,13 @@ static cudaError_t launch_ad_variant(const KConst &c, const Geom &g, const TrajI
   }
   kern<<<grid, CSC2_AD_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
+}
+template <bool RV, bool DOT>
+static cudaError_t launch_ad_variant(const KConst &c, const Geom &g, const TrajIn &in,
+                                     const TrajOut &out, const IncIn &din, const IncOut &dout,
+                                     const ADOpts &opt, int grid, cudaStream_t s) {
+  if (c.lregcl) return launch_ad_k<RV, DOT, true>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_ad_k<RV, DOT, false>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,

@@ -51,22 +51,48 @@ __device__ __forceinline__ void cuadjtqs_point(const KConst &c, double zqp /*1/p
   }
 }
 
-// One level.  `pqs` is the saturation humidity of the level (SATUR output or caller-supplied).
-// Straight-line code: every data-dependent IF of the reference is a select on values that are
-// computed unconditionally with guarded operands, so that the compiler can overlap the
-// independent exp / reciprocal chains of a level (the kernel is FP64-issue bound, not HBM bound).
-__device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int jk,
-                                         const LevIn &x, double pqs, Carry &st, LevOut &y) {
+// One level in two phases:
+//   nl_local : everything that depends only on the level's own inputs (first guess, dqs/dT factor,
+//              cloud cover, convective detrainment, subsidence, condensation rates, liquid
+//              autoconversion, the temperature-independent part of the ice autoconversion) -- ~60 %
+//              of the FP64 work, with plenty of independent exp / reciprocal chains;
+//   nl_tail  : the part chained to the rain/snow flux arriving from the level above (melting ->
+//              post-melt T -> ice autoconversion -> precipitation -> saturation adjustment -> fluxes)
+//              -- one long dependent chain.
+// (Software-pipelining nl_local(JK+1) with nl_tail(JK) in one loop iteration was tried to give
+// each thread two instruction streams: 1.01 ms against 0.925 ms for the plain order at 163 840
+// columns -- ptxas does not interleave them and the carried LevLocal costs registers -- so the
+// kernels run the phases back to back.)  `pqs` is the saturation humidity of the level (SATUR
+// output or caller-supplied).  Straight-line code: every data-dependent IF of the reference is a
+// select on values that are computed unconditionally with guarded operands.
+struct LevLocal {
+  double ztp1, zqp1, zl, zi;          // first guess (pre-melt T)
+  double zc2dp, zgdp, pap_inv;        // ZCONS2*ZDP, RG/ZDP, 1/PAPP1
+  double zcons, zcons_inv;            // ZCONS2*ZDP/ZLFDCP and its inverse (melting)
+  double zlsdcp, zlvdcp, zfwat, zldcpw;
+  double pclc, zqlwc, zqiwc, zprr;    // cover, liquid after / ice before autoconversion, rain source
+  double zcondl, zcondi, plude;
+  double ice_fac, picld;              // ZCKCODTI*(1-EXP(-(ZCLDI/ZLCRIT)**2)), PCLC*ZCLDI (:525-529)
+  double paph1;
+};
+
+// RV = (RVTMP2 != 0), a compile-time switch so that the level is ONE basic block (a run-time test,
+// even a warp-uniform one, splits it and stops the scheduler from interleaving across the split;
+// RVTMP2 is 0 in this dwarf: it is never loaded, yoethf.F90:30 vs :79-99).
+template <bool RV>
+__device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh, int jk,
+                                             const LevIn &x, double pqs, double paph0) {
+  LevLocal L;
   const double dt = c.ptsphy;
   // first guess (cloudsc2.F90:253-260)
-  double ztp1 = x.pt + dt * x.gt;
-  double zqp1 = x.pq + dt * x.gq + x.psupsat;
+  const double ztp1 = x.pt + dt * x.gt;
+  const double zqp1 = x.pq + dt * x.gq + x.psupsat;
   const double zl = x.pl + dt * x.gl;
   const double zi = x.pi + dt * x.gi;
   // :268-278
-  const double zdp = x.paph1 - st.paph0;
+  const double zdp = x.paph1 - paph0;
   double zzz = c.rcpd_inv;
-  if (c.rvtmp2 != 0.0) zzz = csc2_rcp(c.rcpd + c.rcpd * c.rvtmp2 * zqp1);
+  if (RV) zzz = csc2_rcp(c.rcpd + c.rcpd * c.rvtmp2 * zqp1);
   const double zlfdcp = c.rlmlt * zzz, zlsdcp = c.rlstt * zzz, zlvdcp = c.rlvtt * zzz;
   const double pap_inv = csc2_rcp(x.pap);
   const double zdp_inv = csc2_rcp(zdp);
@@ -118,11 +144,11 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   }
 
   // compensating subsidence (:448-460)
+  const double zldcp = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;
   {
     const double zfac1 = csc2_rcp(c.rd * ztp1);
     const double zrho = x.pap * zfac1;
     const double zrodqsdp = -zrho * pqs * zfac2;
-    const double zldcp = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;
     const double zfac3 = csc2_rcp(1.0 + zldcp * zdqsdtemp);
     const double dtdzmo = c.rg * (c.rcpd_inv - zldcp * zrodqsdp) * zfac3;
     const double zdqsdz = zdqsdtemp * dtdzmo - c.rg * zrodqsdp;
@@ -133,26 +159,19 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
 
   // new condensate and condensation rates (:464-469)
   double zqlwc = zqc * zfwat;
-  double zqiwc = zqc * (1.0 - zfwat);
-  double zcondl = (zqlwc - zl) * c.zqtmst;
-  double zcondi = (zqiwc - zi) * c.zqtmst;
+  const double zqiwc = zqc * (1.0 - zfwat);
+  L.zcondl = (zqlwc - zl) * c.zqtmst;
+  L.zcondi = (zqiwc - zi) * c.zqtmst;
 
-  // melting of incoming snow (:487-498); with ZSFL == 0 the statements reduce to the identity
-  double zrfln, zsfln;
+  // melting of incoming snow (:487-498): the level-local factors
   {
     // ZCONS = ZCONS2*ZDP/ZLFDCP and its inverse without a division: 1/ZLFDCP = (1/RLMLT)/ZZZ
-    const double zzz_inv = (c.rvtmp2 != 0.0) ? c.rcpd + c.rcpd * c.rvtmp2 * zqp1 : c.rcpd;
-    const double lf_inv = c.rlmlt_inv * zzz_inv;
-    const double zcons = c.zcons2 * zdp * lf_inv;
-    const double zcons_inv = c.zcons2_inv * zdp_inv * zlfdcp;
-    const double zsnmlt = dmin_(st.sfl, zcons * dmax_(0.0, ztp1 - c.zmeltp2));
-    zrfln = st.rfl + zsnmlt;
-    zsfln = st.sfl - zsnmlt;
-    ztp1 = ztp1 - zsnmlt * zcons_inv;
+    const double zzz_inv = RV ? c.rcpd + c.rcpd * c.rvtmp2 * zqp1 : c.rcpd;
+    L.zcons = c.zcons2 * zdp * (c.rlmlt_inv * zzz_inv);
+    L.zcons_inv = c.zcons2_inv * zdp_inv * zlfdcp;
   }
 
-  // autoconversion liquid / ice (:504-534)
-  double zprr, zprs;
+  // autoconversion (:504-534): liquid completely, ice up to the factor that needs the post-melt T
   {
     const bool cloudy = pclc > CSC2_ZEPS2;
     const double pclc_inv = csc2_rcp(cloudy ? pclc : 1.0);
@@ -162,42 +181,63 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
     const double zlnew = pclc * zcldl * csc2_exp(-zdl);
     const double zcldi = zqiwc * pclc_inv;
     const double rr = zcldi * c.rlcrit_inv;
-    const double zdi = c.zckcodti * csc2_exp(0.025 * (ztp1 - c.rtt)) * (1.0 - csc2_expn(-(rr * rr)));
-    const double zinew = pclc * zcldi * csc2_exp(-zdi);
-    zprr = cloudy ? zqlwc - zlnew : 0.0;
-    zprs = cloudy ? zqiwc - zinew : 0.0;
-    zqlwc = zqlwc - zprr;
-    zqiwc = zqiwc - zprs;
+    L.zprr = cloudy ? zqlwc - zlnew : 0.0;
+    zqlwc = zqlwc - L.zprr;
+    // not cloudy: ice_fac = 0 and picld = ZQIWC make ZINEW = ZQIWC, i.e. ZPRS = 0 exactly
+    L.ice_fac = cloudy ? c.zckcodti * (1.0 - csc2_expn(-(rr * rr))) : 0.0;
+    L.picld = cloudy ? pclc * zcldi : zqiwc;
   }
+  L.ztp1 = ztp1; L.zqp1 = zqp1; L.zl = zl; L.zi = zi;
+  L.zc2dp = c.zcons2 * zdp; L.zgdp = zgdp; L.pap_inv = pap_inv;
+  L.zlsdcp = zlsdcp; L.zlvdcp = zlvdcp; L.zfwat = zfwat; L.zldcpw = zldcp;   // as written at :609-610
+  L.pclc = pclc; L.zqlwc = zqlwc; L.zqiwc = zqiwc; L.plude = x.plude;
+  L.paph1 = x.paph1;
+  return L;
+}
+
+__device__ __forceinline__ void nl_tail(const KConst &c, const LevLocal &L, Carry &st, LevOut &y) {
+  const double dt = c.ptsphy;
+  double ztp1 = L.ztp1, zqp1 = L.zqp1;
+  // melting of incoming snow (:487-498); with ZSFL == 0 the statements reduce to the identity
+  const double zsnmlt = dmin_(st.sfl, L.zcons * dmax_(0.0, ztp1 - c.zmeltp2));
+  double zrfln = st.rfl + zsnmlt;
+  double zsfln = st.sfl - zsnmlt;
+  ztp1 = ztp1 - zsnmlt * L.zcons_inv;
+
+  // ice autoconversion on the post-melt T (:522-533)
+  const double zdi = L.ice_fac * csc2_exp(0.025 * (ztp1 - c.rtt));
+  const double zinew = L.picld * csc2_exp(-zdi);
+  const double zprs = L.zqiwc - zinew;
+  const double zqiwc = L.zqiwc - zprs;
 
   // new precipitation, rain/snow split on the post-melt T (:538-552)
-  const double zc2dp = c.zcons2 * zdp;
-  const double zdr = zc2dp * (zprr + zprs);
+  const double zdr = L.zc2dp * (L.zprr + zprs);
   const bool frz1 = ztp1 < c.rtt;
-  double zrfreeze = frz1 ? zc2dp * zprr : 0.0;
+  double zrfreeze = frz1 ? L.zc2dp * L.zprr : 0.0;
   zsfln += frz1 ? zdr : 0.0;
   zrfln += frz1 ? 0.0 : zdr;
 
   // first-guess T and q after the tendencies (:601-618)
-  const double zldcpw = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;   // as written at :609-610
+  double zcondl = L.zcondl, zcondi = L.zcondi;
+  const double plude_gdp = L.plude * L.zgdp;
   {
-    const double zdqdt = -(zcondl + zcondi) + x.plude * zgdp;
-    const double zdtdt = zlvdcp * zcondl + zlsdcp * zcondi -
-                         (x.plude * zldcpw - (zlsdcp - zlvdcp) * zrfreeze) * zgdp;
+    const double zdqdt = -(zcondl + zcondi) + plude_gdp;
+    const double zdtdt = L.zlvdcp * zcondl + L.zlsdcp * zcondi -
+                         (L.plude * L.zldcpw - (L.zlsdcp - L.zlvdcp) * zrfreeze) * L.zgdp;
     ztp1 = ztp1 + dt * zdtdt;
     zqp1 = zqp1 + dt * zdqdt;
   }
   const double zqold = zqp1;
 
   // saturation adjustment (:622-670)
-  cuadjtqs_point(c, pap_inv, ztp1, zqp1);
+  cuadjtqs_point(c, L.pap_inv, ztp1, zqp1);
 
   // excess water to precipitation (:672-692)
   {
     const double zdq = dmax_(0.0, zqold - zqp1);
-    const double zdr2 = zc2dp * zdq;
+    const double zdr2 = L.zc2dp * zdq;
     const bool frz2 = ztp1 < c.rtt;
-    zrfreeze += frz2 ? zfwat * zdr2 : 0.0;
+    zrfreeze += frz2 ? L.zfwat * zdr2 : 0.0;
     zcondi += frz2 ? zdq * c.zqtmst : 0.0;
     zcondl += frz2 ? 0.0 : zdq * c.zqtmst;
     zsfln += frz2 ? zdr2 : 0.0;
@@ -205,16 +245,24 @@ __device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int
   }
 
   // final tendencies and fluxes (:694-716)
-  y.tenq = -(zcondl + zcondi) + x.plude * zgdp;
-  y.tent = zlvdcp * zcondl + zlsdcp * zcondi -
-           (x.plude * zldcpw - (zlsdcp - zlvdcp) * zrfreeze) * zgdp;
-  y.tenl = (zqlwc - zl) * c.zqtmst;
-  y.teni = (zqiwc - zi) * c.zqtmst;
-  y.pclc = pclc;
+  y.tenq = -(zcondl + zcondi) + plude_gdp;
+  y.tent = L.zlvdcp * zcondl + L.zlsdcp * zcondi -
+           (L.plude * L.zldcpw - (L.zlsdcp - L.zlvdcp) * zrfreeze) * L.zgdp;
+  y.tenl = (L.zqlwc - L.zl) * c.zqtmst;
+  y.teni = (zqiwc - L.zi) * c.zqtmst;
+  y.pclc = L.pclc;
   y.rfln = zrfln;
   y.sfln = zsfln;
   // carry (:720-723)
   st.rfl = zrfln;
   st.sfl = zsfln;
-  st.paph0 = x.paph1;
+  st.paph0 = L.paph1;
+}
+
+// Both phases back to back (AD forward sweep, Taylor-test kernel).
+template <bool RV>
+__device__ __forceinline__ void nl_level(const KConst &c, const CritRH &crh, int jk,
+                                         const LevIn &x, double pqs, Carry &st, LevOut &y) {
+  const LevLocal L = nl_local<RV>(c, crh, jk, x, pqs, st.paph0);
+  nl_tail(c, L, st, y);
 }

@@ -20,7 +20,7 @@ __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 constexpr int NL_NF = CSC2_NTRAJ;   // staged fields per level: 15 inputs + optional PQS
 
 // STAGES = depth of the shared-memory ring (levels in flight + the one being computed)
-template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV>
 __global__ void __maxnreg__(MAXREG)
 k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out) {
   extern __shared__ double ring_all[];
@@ -74,7 +74,7 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     const double pqs = HAS_PQS ? ring[(size_t)slot * (NL_NF * NT) + 15 * NT]
                                : satur_point(c, cur.pt, csc2_rcp(cur.pap));
     LevOut y;
-    nl_level(c, crh, jk, cur, pqs, st, y);
+    nl_level<RV>(c, crh, jk, cur, pqs, st, y);
 
     const size_t l = (size_t)jk * nproma;
     stout(out.tent + o.oloc + l, y.tent);
@@ -150,13 +150,13 @@ cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cu
   return cudaGetLastError();
 }
 
-template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
-static cudaError_t launch_nl_variant(const KConst &c, const Geom &g, const TrajIn &in,
-                                     const TrajOut &out, cudaStream_t s) {
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV>
+static cudaError_t launch_nl_rv(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + NT - 1) / NT);
   const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG>;
+  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -165,6 +165,13 @@ static cudaError_t launch_nl_variant(const KConst &c, const Geom &g, const TrajI
   }
   kern<<<grid, NT, smem, s>>>(c, g, in, out);
   return cudaGetLastError();
+}
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
+static cudaError_t launch_nl_variant(const KConst &c, const Geom &g, const TrajIn &in,
+                                     const TrajOut &out, cudaStream_t s) {
+  // RVTMP2 != 0 (never the case in this dwarf) runs the default shape only
+  if (c.rvtmp2 != 0.0) return launch_nl_rv<HAS_PQS, 2, 128, 168, true>(c, g, in, out, s);
+  return launch_nl_rv<HAS_PQS, STAGES, NT, MAXREG, false>(c, g, in, out, s);
 }
 
 // CSC2_NL_VARIANT (tuning knob, read once): CTA size / CTAs per SM / ring depth

@@ -51,11 +51,13 @@ __device__ __forceinline__ void cuadjtqstl_point(const KConst &c, double psp5_in
 
 // x5/pqs5 : trajectory inputs ; dx/dpqs : perturbations.  y5/dy : outputs.
 // Straight-line like nl_level: the reference's IFs (which all test trajectory values) are selects.
+// RV = (RVTMP2 != 0), LREG = YRNCL%LREGCL: compile-time so that the level is one basic block.
+template <bool RV, bool LREG>
 __device__ __forceinline__ void tl_level(const KConst &c, const CritRH &crh, int jk,
                                          const LevIn &x5, double pqs5, const LevIn &dx, double dpqs,
                                          Carry &st5, CarryTL &st, LevOut &y5, LevOut &dy) {
   const double dt = c.ptsphy;
-  const bool lreg = c.lregcl != 0;
+  constexpr bool lreg = LREG;
   // first guess (cloudsc2tl.F90:342-353)
   double ztp1 = dx.pt + dt * dx.gt;
   double ztp15 = x5.pt + dt * x5.gt;
@@ -67,7 +69,7 @@ __device__ __forceinline__ void tl_level(const KConst &c, const CritRH &crh, int
   const double zdp = dx.paph1 - st.paph0;
   const double zdp5 = x5.paph1 - st5.paph0;
   double zzz5 = c.rcpd_inv, zzz = 0.0;
-  if (c.rvtmp2 != 0.0) {
+  if (RV) {
     zzz5 = csc2_rcp(c.rcpd + c.rcpd * c.rvtmp2 * zqp15);
     zzz = -c.rcpd * c.rvtmp2 * zqp1 * (zzz5 * zzz5);
   }

@@ -74,7 +74,7 @@ __device__ __forceinline__ LevIn scale_level(const LevIn &x, double f, bool zero
   return d;
 }
 
-template <bool ONFLY, int STAGES>
+template <bool ONFLY, int STAGES, bool RV, bool LREG>
 __global__ void __launch_bounds__(CSC2_TL_THREADS)
 k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const TLOpts opt) {
@@ -138,7 +138,7 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
       dpqs = d[31 * NT];
     }
     LevOut y5, dy;
-    tl_level(c, crh, jk, cur, pqs5, dx, dpqs, st5, st, y5, dy);
+    tl_level<RV, LREG>(c, crh, jk, cur, pqs5, dx, dpqs, st5, st, y5, dy);
 
     const size_t l = (size_t)jk * nproma;
     // trajectory outputs, re-emitted like the reference (cloudsc2tl.F90:1079-1091)
@@ -227,7 +227,8 @@ k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, con
     x.pmfd = pert(x.pmfd, lam); x.gt = pert(x.gt, lam); x.gq = pert(x.gq, lam);
     x.gl = pert(x.gl, lam); x.gi = pert(x.gi, lam); x.psupsat = pert(x.psupsat, lam);
     LevOut y;
-    nl_level(c, crh, jk, x, pqs5, st, y);
+    if (c.rvtmp2 != 0.0) nl_level<true>(c, crh, jk, x, pqs5, st, y);
+    else nl_level<false>(c, crh, jk, x, pqs5, st, y);
     const size_t l = (size_t)jk * nproma;
     d_t += ldin(base.tent + o.oloc + l) - y.tent;
     d_q += ldin(base.tenq + o.oloc + l) - y.tenq;
@@ -294,12 +295,12 @@ k_taylor_finalize(const Geom g, const Lambdas lams, const double *__restrict__ t
 
 }  // namespace
 
-template <bool ONFLY, int STAGES>
-static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajIn &in,
-                                     const TrajOut &out, const IncIn &din, const IncOut &dout,
-                                     const TLOpts &opt, int grid, cudaStream_t s) {
+template <bool ONFLY, int STAGES, bool RV, bool LREG>
+static cudaError_t launch_tl_k(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                               const IncIn &din, const IncOut &dout, const TLOpts &opt, int grid,
+                               cudaStream_t s) {
   const size_t smem = (size_t)STAGES * TL_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_tl<ONFLY, STAGES>;
+  auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -308,6 +309,20 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
   }
   kern<<<grid, CSC2_TL_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
+}
+// dispatch on the two run-time switches that are compile-time in the kernel
+template <bool ONFLY, int STAGES>
+static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajIn &in,
+                                     const TrajOut &out, const IncIn &din, const IncOut &dout,
+                                     const TLOpts &opt, int grid, cudaStream_t s) {
+  const bool rv = c.rvtmp2 != 0.0, lreg = c.lregcl != 0;
+  if (rv) {
+    // RVTMP2 != 0 never happens in this dwarf: one shape only
+    if (lreg) return launch_tl_k<ONFLY, 2, true, true>(c, g, in, out, din, dout, opt, grid, s);
+    return launch_tl_k<ONFLY, 2, true, false>(c, g, in, out, din, dout, opt, grid, s);
+  }
+  if (lreg) return launch_tl_k<ONFLY, STAGES, false, true>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_tl_k<ONFLY, STAGES, false, false>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 static int g_tl_stages = 0;
