@@ -49,7 +49,7 @@ __device__ __forceinline__ void adj_iter_fwd(const KConst &c, const AdjTraj &tr,
   it.foeew = c.r2es * csc2_exp(tr.z3es * (t5 - c.rtt) * it.r);
   it.qs_raw = zqp5 * it.foeew;
   it.cap = it.qs_raw > CSC2_ZQMAX;
-  if (it.cap) it.qs_raw = CSC2_ZQMAX;
+  it.qs_raw = it.cap ? CSC2_ZQMAX : it.qs_raw;
   it.cor = csc2_rcp(1.0 - c.retv * it.qs_raw);
   it.qs = it.qs_raw * it.cor;
   it.z2s = tr.z5alcp * (it.r * it.r);
@@ -82,7 +82,7 @@ __device__ __forceinline__ void adj_iter_bwd(const KConst &c, const AdjTraj &tr,
   double ztarg = -2.0 * z2s * it.z2s * it.r;                // 2*Z2S*Z5ALCP/(T-Z4ES)**3
   zcor += zqsat * it.qs_raw;
   zqsat = zqsat * it.cor + zcor * c.retv * (it.cor * it.cor);
-  if (it.cap) zqsat = 0.0;
+  zqsat = it.cap ? 0.0 : zqsat;
   const double zfoeew = zqsat * zqp5;
   zqp_ += zqsat * it.foeew;
   // R2ES*EXP(..) of :581/:629 is the stored ZFOEEW5 of the iteration
@@ -144,32 +144,25 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
 
   const double zscalm = CSC2_ZSCALM(jk);
   const double zqt5 = zqp25 + zl5 + zi5;
-  int cbranch;                                             // 0 clear, 1 overcast, 2 partial
-  double zclc5, zqc15, zqpd5 = 0.0, zqcd5 = 0.0, zsqrt5 = 1.0, den5_inv = 0.0;
-  if (zqt5 <= zqcrit5) {
-    cbranch = 0; zclc5 = 0.0; zqc15 = 0.0;
-  } else if (zqt5 >= zqsat5) {
-    cbranch = 1; zclc5 = 1.0; zqc15 = (1.0 - zscalm) * (zqsat5 - zqcrit5);
-  } else {
-    cbranch = 2;
-    zqpd5 = zqsat5 - zqt5; zqcd5 = zqsat5 - zqcrit5;
-    den5_inv = csc2_rcp(zqcd5 - zscalm * (zqt5 - zqcrit5));
-    zsqrt5 = csc2_sqrt(zqpd5 * den5_inv);
-    zclc5 = 1.0 - zsqrt5;
-    zqc15 = (zscalm * zqpd5 + (1.0 - zscalm) * zqcd5) * (zclc5 * zclc5);
-  }
+  // three-way branch of :543-593 as selects; outside the partial branch the operands of the square
+  // root and the reciprocals are replaced by 1 (their results are not used there)
+  const bool overcast5 = zqt5 >= zqsat5;
+  const bool partial5 = !(zqt5 <= zqcrit5) && !overcast5;
+  const double zqpd5 = zqsat5 - zqt5, zqcd5 = zqsat5 - zqcrit5;
+  const double den5_inv = csc2_rcp(partial5 ? zqcd5 - zscalm * (zqt5 - zqcrit5) : 1.0);
+  const double zsqrt5 = csc2_sqrt((partial5 ? zqpd5 : 1.0) * den5_inv);
+  const double zclc5 = partial5 ? 1.0 - zsqrt5 : (overcast5 ? 1.0 : 0.0);
+  const double zqc15 = partial5 ? (zscalm * zqpd5 + (1.0 - zscalm) * zqcd5) * (zclc5 * zclc5)
+                                : (overcast5 ? (1.0 - zscalm) * zqcd5 : 0.0);
 
   const double zdp5_inv = csc2_rcp(zdp5);
   const double zgdp5 = c.rg * zdp5_inv;
   const double zlude5 = x5.plude * dt * zgdp5;
   const bool llo1 = (jk < c.klev - 1) && zlude5 >= c.rlmin && x5.plu1 >= CSC2_ZEPS2;
-  double pclc5 = zclc5, zqc25 = zqc15, econv = 0.0, plu_inv = 0.0;
-  if (llo1) {
-    plu_inv = csc2_rcp(x5.plu1);
-    econv = csc2_expn(-zlude5 * plu_inv);
-    pclc5 = zclc5 + (1.0 - zclc5) * (1.0 - econv);
-    zqc25 = zqc15 + zlude5;
-  }
+  const double plu_inv = csc2_rcp(llo1 ? x5.plu1 : 1.0);
+  const double econv = csc2_expn(-zlude5 * plu_inv);
+  const double pclc5 = llo1 ? zclc5 + (1.0 - zclc5) * (1.0 - econv) : zclc5;
+  const double zqc25 = llo1 ? zqc15 + zlude5 : zqc15;
 
   const double zfac1 = csc2_rcp(c.rd * ztp25);
   const double zrho5 = x5.pap * zfac1;
@@ -193,32 +186,28 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
 
   // melting (:633-651)
   const bool melt = sfl5 != 0.0;
-  double ztp15 = ztp25, zcons5 = 0.0, zcons5_inv = 0.0, zz2s5 = 0.0, zsnmlt5 = 0.0;
   const bool warm2 = (ztp25 - c.zmeltp2) > 0.0;
-  if (melt) {
-    zcons5 = c.zcons2 * zdp5 * csc2_rcp(zlfdcp5);
-    zcons5_inv = csc2_rcp(zcons5);
-    zz2s5 = warm2 ? zcons5 * (ztp25 - c.zmeltp2) : 0.0;
-    zsnmlt5 = (sfl5 <= zz2s5) ? sfl5 : zz2s5;
-    ztp15 = ztp25 - zsnmlt5 * zcons5_inv;
-  }
+  // ZCONS5 = ZCONS2*ZDP5/ZLFDCP5 and its inverse without divisions: 1/ZLFDCP5 = (1/RLMLT)/ZZZ5
+  const double lf5_inv = c.rlmlt_inv * (RV ? c.rcpd + c.rcpd * c.rvtmp2 * zqp25 : c.rcpd);
+  const double zcons5 = c.zcons2 * zdp5 * lf5_inv;
+  const double zcons5_inv = c.zcons2_inv * zdp5_inv * zlfdcp5;
+  const double zz2s5 = warm2 ? zcons5 * (ztp25 - c.zmeltp2) : 0.0;
+  const bool melt_all = sfl5 <= zz2s5;
+  const double zsnmlt5 = melt ? (melt_all ? sfl5 : zz2s5) : 0.0;
+  const double ztp15 = ztp25 - zsnmlt5 * zcons5_inv;
 
   // autoconversion (:655-722)
   const bool cloudy = pclc5 > CSC2_ZEPS2;
-  double pclc5_inv = 0.0, zcldl5 = 0.0, zexp35 = 0.0, zexpdl5 = 0.0, zprr5 = 0.0;
-  double zcldi5 = 0.0, zexp15 = 0.0, zexp25 = 0.0, zexpdi5 = 0.0, zprs5 = 0.0;
-  if (cloudy) {
-    pclc5_inv = csc2_rcp(pclc5);
-    zcldl5 = zqlwc15 * pclc5_inv;
-    zexp35 = csc2_expn(-SQA_(zcldl5 * c.rlcrit_inv));
-    zexpdl5 = csc2_exp(-(c.zckcodtl * (1.0 - zexp35)));
-    zprr5 = zqlwc15 - pclc5 * zcldl5 * zexpdl5;
-    zcldi5 = zqiwc15 * pclc5_inv;
-    zexp15 = csc2_exp(0.025 * (ztp15 - c.rtt));
-    zexp25 = csc2_expn(-SQA_(zcldi5 * c.rlcrit_inv));
-    zexpdi5 = csc2_exp(-(c.zckcodti * zexp15 * (1.0 - zexp25)));
-    zprs5 = zqiwc15 - pclc5 * zcldi5 * zexpdi5;
-  }
+  const double pclc5_inv = csc2_rcp(cloudy ? pclc5 : 1.0);
+  const double zcldl5 = zqlwc15 * pclc5_inv;
+  const double zexp35 = csc2_expn(-SQA_(zcldl5 * c.rlcrit_inv));
+  const double zexpdl5 = csc2_exp(-(c.zckcodtl * (1.0 - zexp35)));
+  const double zprr5 = cloudy ? zqlwc15 - pclc5 * zcldl5 * zexpdl5 : 0.0;
+  const double zcldi5 = zqiwc15 * pclc5_inv;
+  const double zexp15 = csc2_exp(0.025 * (ztp15 - c.rtt));
+  const double zexp25 = csc2_expn(-SQA_(zcldi5 * c.rlcrit_inv));
+  const double zexpdi5 = csc2_exp(-(c.zckcodti * zexp15 * (1.0 - zexp25)));
+  const double zprs5 = cloudy ? zqiwc15 - pclc5 * zcldi5 * zexpdi5 : 0.0;
   const double zc2dp5 = c.zcons2 * zdp5;
   const double zdr15 = zc2dp5 * (zprr5 + zprs5);
   const bool frz1 = ztp15 < c.rtt;
@@ -282,20 +271,13 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     const double zrfreeze2 = zrfreeze_;
     double zdq = (zcondi_ * (1.0 - zfwatr25) + zcondl_ * zfwatr25) * c.zqtmst;
     double zdr2 = (1.0 - zfwatr25) * zsfln + zfwatr25 * zrfln;
-    if (frz2) {
-      zfwat_ += zdr25 * zrfreeze2;
-      zdr2 += zfwat5 * zrfreeze2;
-    }
+    zfwat_ += frz2 ? zdr25 * zrfreeze2 : 0.0;
+    zdr2 += frz2 ? zfwat5 * zrfreeze2 : 0.0;
     zdq += zc2dp5 * zdr2;
     zdp_ = c.zcons2 * zdq5 * zdr2;
-    if (exc) {
-      if (lreg) zdq *= 0.7;
-      zqold_ = zdq;
-      zqp1_ = -zdq;
-    } else {
-      zqold_ = 0.0;
-      zqp1_ = 0.0;
-    }
+    if (lreg) zdq *= 0.7;
+    zqold_ = exc ? zdq : 0.0;
+    zqp1_ = exc ? -zdq : 0.0;
   }
 
   // saturation adjustment (:1069-1072), on the stored two-iteration trajectory
@@ -327,67 +309,55 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   // new precipitation and autoconversion (:1128-1358)
   {
     const double zdr = (1.0 - zfwatr15) * zsfln + zfwatr15 * zrfln;
-    double zprr = 0.0, zprs = 0.0;
-    if (frz1) {                                            // :1284-1288
-      zdp_ += zrfreeze_ * c.zcons2 * zprr5;
-      zprr += zrfreeze_ * zc2dp5;
-      zrfreeze_ = 0.0;
-    }
+    // :1284-1288 (freezing rain source) as selects
+    zdp_ += frz1 ? zrfreeze_ * c.zcons2 * zprr5 : 0.0;
+    double zprr = frz1 ? zrfreeze_ * zc2dp5 : 0.0;
+    double zprs = 0.0;
+    zrfreeze_ = frz1 ? 0.0 : zrfreeze_;
     zprr += zc2dp5 * zdr;
     zprs += zc2dp5 * zdr;
     zdp_ += c.zcons2 * (zprr5 + zprs5) * zdr;
-    if (cloudy) {
+    {
+      // the adjoint of the autoconversion (:1298-1356) acts only where PCLC5 > ZEPS2; it is
+      // evaluated unconditionally (all its trajectory factors are finite) and masked at the end
       const double rl2 = c.rlcrit_inv * c.rlcrit_inv;
-      {                                                    // ice :1298-1327
-        zprs -= zqiwc_;
-        zqiwc_ += zprs;
-        const double zinew = -zprs;
-        pclc_ += zinew * zcldi5 * zexpdi5;
-        double zcldi = zinew * pclc5 * zexpdi5;
-        const double zdi = -zinew * pclc5 * zcldi5 * zexpdi5;
-        const double k = lreg ? c.zckcodtia : c.zckcodti;
-        ztp1_ += k * zexp15 * (1.0 - zexp25) * 0.025 * zdi;
-        zcldi += (k * zexp15 * zexp25 * 2.0 * zcldi5 * rl2) * zdi;
-        zqiwc_ += zcldi * pclc5_inv;
-        pclc_ -= zqiwc15 * zcldi * (pclc5_inv * pclc5_inv);
-      }
-      {                                                    // liquid :1332-1356
-        zprr -= zqlwc_;
-        zqlwc_ += zprr;
-        const double zlnew = -zprr;
-        pclc_ += zlnew * zcldl5 * zexpdl5;
-        double zcldl = zlnew * pclc5 * zexpdl5;
-        const double zdl = -zlnew * pclc5 * zcldl5 * zexpdl5;
-        const double k = lreg ? c.zckcodtla : c.zckcodtl;
-        zcldl += (2.0 * k * rl2) * zexp35 * zcldl5 * zdl;
-        zqlwc_ += zcldl * pclc5_inv;
-        pclc_ -= zqlwc15 * zcldl * (pclc5_inv * pclc5_inv);
-      }
+      // ice :1298-1327
+      const double zprs_c = zprs - zqiwc_;
+      const double zinew = -zprs_c;
+      const double zdi = -zinew * pclc5 * zcldi5 * zexpdi5;
+      const double ki = lreg ? c.zckcodtia : c.zckcodti;
+      const double zcldi = zinew * pclc5 * zexpdi5 + (ki * zexp15 * zexp25 * 2.0 * zcldi5 * rl2) * zdi;
+      const double zqiwc_c = zqiwc_ + zprs_c + zcldi * pclc5_inv;
+      const double ztp1_c = ztp1_ + ki * zexp15 * (1.0 - zexp25) * 0.025 * zdi;
+      double pclc_c = pclc_ + zinew * zcldi5 * zexpdi5 - zqiwc15 * zcldi * (pclc5_inv * pclc5_inv);
+      // liquid :1332-1356
+      const double zprr_c = zprr - zqlwc_;
+      const double zlnew = -zprr_c;
+      const double zdl = -zlnew * pclc5 * zcldl5 * zexpdl5;
+      const double kl = lreg ? c.zckcodtla : c.zckcodtl;
+      const double zcldl = zlnew * pclc5 * zexpdl5 + (2.0 * kl * rl2) * zexp35 * zcldl5 * zdl;
+      const double zqlwc_c = zqlwc_ + zprr_c + zcldl * pclc5_inv;
+      pclc_c += zlnew * zcldl5 * zexpdl5 - zqlwc15 * zcldl * (pclc5_inv * pclc5_inv);
+      zqiwc_ = cloudy ? zqiwc_c : zqiwc_;
+      zqlwc_ = cloudy ? zqlwc_c : zqlwc_;
+      ztp1_ = cloudy ? ztp1_c : ztp1_;
+      pclc_ = cloudy ? pclc_c : pclc_;
     }
   }
 
   // melting of incoming snow (:1362-1400)
-  double zsfl_ = 0.0, zrfl_ = 0.0;
-  if (melt) {
+  double zsfl_ = zsfln;
+  const double zrfl_ = zrfln;
+  {
     double zsnmlt = -ztp1_ * zcons5_inv;
     double zcons = ztp1_ * zsnmlt5 * (zcons5_inv * zcons5_inv);
-    zsfl_ = zsfln;
-    zsnmlt -= zsfln;
-    zrfl_ = zrfln;
-    zsnmlt += zrfln;
-    double zz2s = 0.0;
-    if (sfl5 <= zz2s5) zsfl_ += zsnmlt;
-    else zz2s = zsnmlt;
-    if (warm2) {
-      ztp1_ += zcons5 * zz2s;
-      zcons += (ztp25 - c.zmeltp2) * zz2s;
-    }
-    const double lf5_inv = csc2_rcp(zlfdcp5);
-    zdp_ += c.zcons2 * zcons * lf5_inv;
-    if (RV) zlfdcp_ -= zc2dp5 * zcons * (lf5_inv * lf5_inv);
-  } else {
-    zsfl_ = zsfln;
-    zrfl_ = zrfln;
+    zsnmlt = zsnmlt - zsfln + zrfln;
+    const double zz2s = melt_all ? 0.0 : zsnmlt;
+    zcons += warm2 ? (ztp25 - c.zmeltp2) * zz2s : 0.0;
+    zsfl_ += (melt && melt_all) ? zsnmlt : 0.0;
+    ztp1_ += (melt && warm2) ? zcons5 * zz2s : 0.0;
+    zdp_ += melt ? c.zcons2 * zcons * lf5_inv : 0.0;
+    if (RV) zlfdcp_ -= melt ? zc2dp5 * zcons * (lf5_inv * lf5_inv) : 0.0;
   }
   ca.sfl = zsfl_;
   ca.rfl = zrfl_;
@@ -406,15 +376,12 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   // compensating subsidence (:1446-1496)
   double zfoeew_, zdqsdtemp_, pqs_, pmf_ = 0.0;
   {
-    double zdqc = -zqc_, zdqsdz = 0.0, zrho = 0.0;
-    if (llo3) {
-      if (lreg) zdqc *= 0.1;
-      zdqsdz = zdqc * dt * mf5 * zfac4;
-      pmf_ = zdqc * dt * zdqsdz5 * zfac4;
-      zrho = -zdqc * zdqc5 * zfac4;
-    } else {
-      zqc_ += zdqc;                                        // = 0
-    }
+    double zdqc = -zqc_;
+    zqc_ = llo3 ? zqc_ : 0.0;                              // LLO3 false: ZQC = ZQC + ZDQC = 0
+    if (lreg) zdqc *= 0.1;
+    const double zdqsdz = llo3 ? zdqc * dt * mf5 * zfac4 : 0.0;
+    pmf_ = llo3 ? zdqc * dt * zdqsdz5 * zfac4 : 0.0;
+    double zrho = llo3 ? -zdqc * zdqc5 * zfac4 : 0.0;
     const double dtdzmo = zdqsdz * zdqsdtemp5;
     zdqsdtemp_ = zdqsdz * dtdzmo5;
     double zrodqsdp = -zdqsdz * c.rg;
@@ -438,42 +405,36 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   // convective component (:1500-1527)
   double plu1_ = 0.0, paph_g;
   {
-    double zlude = 0.0;
-    if (llo1) {
-      zlude = zqc_;
-      zlude += ((1.0 - zclc5) * plu_inv) * econv * pclc_;
-      plu1_ = -((1.0 - zclc5) * zlude5 * (plu_inv * plu_inv)) * econv * pclc_;
-      pclc_ = pclc_ * (1.0 - (1.0 - econv));
-    }
+    const double zlude = llo1 ? zqc_ + ((1.0 - zclc5) * plu_inv) * econv * pclc_ : 0.0;
+    plu1_ = llo1 ? -((1.0 - zclc5) * zlude5 * (plu_inv * plu_inv)) * econv * pclc_ : 0.0;
+    pclc_ = llo1 ? pclc_ * (1.0 - (1.0 - econv)) : pclc_;
     plude_ += dt * zgdp5 * zlude;
     zgdp_ += dt * x5.plude * zlude;
     paph_g = c.rg * zgdp_ * (zdp5_inv * zdp5_inv);         // -> -PAPHP1(JK+1), +PAPHP1(JK)
   }
 
   // uniform total-water distribution (:1531-1583)
-  double zqsat_ = 0.0, zqcrit_ = 0.0, zqt_ = 0.0;
-  if (cbranch == 1) {
-    zqsat_ = (1.0 - zscalm) * zqc_;
-    zqcrit_ = -(1.0 - zscalm) * zqc_;
-  } else if (cbranch == 2) {
+  double zqsat_, zqcrit_, zqt_;
+  {
+    // partial branch (:1545-1583), evaluated with the guarded trajectory values and selected
     double zqpd = zscalm * zqc_ * (zclc5 * zclc5);
     double zqcd = (1.0 - zscalm) * zqc_ * (zclc5 * zclc5);
-    pclc_ += (zscalm * zqpd5 + (1.0 - zscalm) * zqcd5) * 2.0 * zclc5 * zqc_;
+    double pc_ = pclc_ + (zscalm * zqpd5 + (1.0 - zscalm) * zqcd5) * 2.0 * zclc5 * zqc_;
     if (lreg) {                                            // :1554-1559
-      const double zrat = zqpd5 * csc2_rcp(zqcd5);
+      const double zrat = (partial5 ? zqpd5 : 1.0) * csc2_rcp(partial5 ? zqcd5 : 1.0);
       const double b = 1.0 - zscalm * (1.0 - zrat);
       const double zyyy = dmin_(0.3, 3.5 * csc2_sqrt(zrat * (b * b * b)) * csc2_rcp(1.0 - zscalm));
-      pclc_ = zyyy * pclc_;
+      pc_ = zyyy * pc_;
     }
-    const double h = (0.5 * csc2_rcp(zsqrt5)) * pclc_ * den5_inv;
+    const double h = (0.5 * csc2_rcp(zsqrt5)) * pc_ * den5_inv;
     zqpd -= h;
     const double h2 = h * zqpd5 * den5_inv;
     zqcd += h2;
-    zqt_ = -h2 * zscalm;
-    zqcrit_ = h2 * zscalm;
-    zqsat_ = zqcd + zqpd;
-    zqcrit_ -= zqcd;
-    zqt_ -= zqpd;
+    const double ov = (1.0 - zscalm) * zqc_;               // overcast branch (:1536-1540)
+    zqt_ = partial5 ? -h2 * zscalm - zqpd : 0.0;
+    zqcrit_ = partial5 ? h2 * zscalm - zqcd : (overcast5 ? -ov : 0.0);
+    zqsat_ = partial5 ? zqcd + zqpd : (overcast5 ? ov : 0.0);
+    pclc_ = partial5 ? pc_ : pclc_;
   }
   zqp1_ += zqt_;
   zl_ += zqt_;
@@ -484,7 +445,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     zqsat_ += zqcrit_ * zcrh2;
     pqs_ += zqsat_ * zsupsat5;
     const double zsupsat = zqsat_ * pqs5;
-    if (vcold) ztp1_ -= zsupsat * 3.e-03;
+    ztp1_ -= vcold ? zsupsat * 3.e-03 : 0.0;
     pqs_ += zfac5 * zcor5 * zdqsdtemp_;
     const double zcor = zfac5 * pqs5 * zdqsdtemp_;
     const double zfac = zcor5 * pqs5 * zdqsdtemp_;
@@ -494,15 +455,12 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     zfwat_ += (zfacw5 - zfaci5) * zfac;
     ztp1_ -= 2.0 * zfaci5 * ri * zfaci;                    // 2*R5IES*ZFACI/(T-R4IES)**3
     ztp1_ -= 2.0 * zfacw5 * rw * zfacw;
-    if (zesdp15 > CSC2_ZQMAX) zesdp = 0.0;
+    zesdp = (zesdp15 > CSC2_ZQMAX) ? 0.0 : zesdp;
     zfoeew_ += zesdp * pap5_inv;
     pap_ -= zesdp * zfoeew5 * (pap5_inv * pap5_inv);
-    if (cold) {
-      ztp1_ += c.r3ies * (c.rtt - c.r4ies) * zfoeew_ * zfoeew5 * (ri * ri);
-      ztp1_ += (0.545 * 0.17) * zfwat_ * sech2;
-    } else {
-      ztp1_ += c.r3les * (c.rtt - c.r4les) * zfoeew_ * zfoeew5 * (rw * rw);
-    }
+    const double rsel = cold ? ri : rw;
+    ztp1_ += (cold ? c.r3ies * (c.rtt - c.r4ies) : c.r3les * (c.rtt - c.r4les)) * zfoeew_ * zfoeew5 * (rsel * rsel);
+    ztp1_ += cold ? (0.545 * 0.17) * zfwat_ * sech2 : 0.0;
   }
 
   // epilogue of the level (:1701-1740)

@@ -2,16 +2,20 @@
 // src/cloudsc2_ad/cloudsc2ad.F90:10-1746) and the reduction of the adjoint (dot-product) test
 // (cloudsc_driver_ad_mod.F90:184-267).
 //
-// One thread per column, two sweeps in one launch:
-//   forward  JK = 1..KLEV : fused SATUR + nonlinear level (identical device function to the NL
-//            kernel), writing the trajectory outputs like the reference (:842-864) and
-//            check-pointing ONLY the rain/snow flux entering each level (2 doubles per level,
-//            instead of the reference's 116 stored (KLON,KLEV) arrays);
-//   reverse  JK = KLEV..1 : reload the level's inputs, recompute its local trajectory, run the
-//            adjoint statements (ad_level), and finish the level's 16 input adjoints at once --
-//            either accumulated into the caller's arrays (X = X + ..., PSUPSAT assigned, :1733)
-//            or contracted on the fly with dx = dot_scale * x for the adjoint test (ZNORM2).
+// One thread per column, two sweeps in two launches:
+//   forward  JK = 1..KLEV : the NL kernel itself (cloudsc2_nl_kernel.cu, csc2_launch_nl_ckpt: fused
+//            SATUR + nonlinear level at the NL kernel's occupancy), writing the trajectory outputs
+//            like the reference (:842-864) and check-pointing ONLY the rain/snow flux entering
+//            each level (2 doubles per level, instead of the reference's 116 stored (KLON,KLEV)
+//            arrays);
+//   reverse  JK = KLEV..1 : k_cloudsc2_ad below -- reload the level's inputs, recompute its local
+//            trajectory, run the adjoint statements (ad_level), and finish the level's 16 input
+//            adjoints at once -- either accumulated into the caller's arrays (X = X + ..., PSUPSAT
+//            assigned, :1733) or contracted on the fly with dx = dot_scale * x for the adjoint
+//            test (ZNORM2).
 // Output adjoints are consumed AND zeroed as the reference does (:917-919, :955-966, :1678-1690).
+#include <cstdlib>
+
 #include "cloudsc2_ad.cuh"
 #include "cloudsc2_stage.cuh"
 #include "cloudsc2_launch.h"
@@ -30,10 +34,10 @@ constexpr int AD_STAGES = 2;
 // no load latency on the thread's critical path, same DRAM traffic as a read-modify-write
 __device__ __forceinline__ void acc(double *p, double v) { atomicAdd(p, v); }
 
-template <bool RV, bool DOT, bool LREG>
-// 3 CTAs/SM (168 registers, ~0.5 kB/thread of spills in L1) beats 2 CTAs/SM at 255 registers:
-// 3.67 vs 3.80 ms -- the reverse sweep is latency-bound, not register-bound
-__global__ void __launch_bounds__(CSC2_AD_THREADS, 3)
+// MINB = CTAs per SM: the straight-line adjoint level wants the full 255 registers (2 CTAs/SM,
+// 3.36 ms); at 168 registers (3 CTAs/SM) it spills ~450 B/thread and takes 3.79 ms.
+template <bool RV, bool DOT, bool LREG, int MINB>
+__global__ void __launch_bounds__(CSC2_AD_THREADS, MINB)
 k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const ADOpts opt) {
   extern __shared__ double ring_all[];
@@ -50,54 +54,7 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const size_t cks = (size_t)opt.ncol_pad;
   constexpr int SLOT = AD_NF * NT;
 
-  csc2_stage_traj<NT, false>(ring, in, o, 0, klev, nproma);
-  csc2_cp_async_commit();
-
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
-
-  // ------------------------------ forward (trajectory) sweep --------------------------------
-  double rfl_last, sfl_last;     // flux entering the lowest level: stays in registers
-  {
-    Carry st;
-    st.paph0 = ldin(in.paph + o.oh);
-    st.rfl = 0.0;
-    st.sfl = 0.0;
-    if (opt.write_traj) {
-      stout(out.pfplsl + o.oh, 0.0);
-      stout(out.pfplsn + o.oh, 0.0);
-      stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
-      stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
-    }
-    int slot = 0;
-    for (int jk = 0; jk < klev; ++jk) {
-      if (jk + 1 < klev) csc2_stage_traj<NT, false>(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
-      csc2_cp_async_commit();
-      csc2_cp_async_wait<1>();
-      const double *d = ring + slot * SLOT;
-      const LevIn cur = csc2_read_level<NT>(d, jk, klev);
-      ck_r[(size_t)jk * cks] = st.rfl;
-      ck_s[(size_t)jk * cks] = st.sfl;
-      rfl_last = st.rfl;
-      sfl_last = st.sfl;
-      const double pqs = in.pqs ? d[15 * NT] : satur_point(c, cur.pt, csc2_rcp(cur.pap));
-      LevOut y;
-      nl_level<RV>(c, crh, jk, cur, pqs, st, y);
-      if (opt.write_traj) {
-        const size_t l = (size_t)jk * nproma;
-        stout(out.tent + o.oloc + l, y.tent);
-        stout(out.tenq + o.oloc + l, y.tenq);
-        stout(out.tenl + o.oloc + l, y.tenl);
-        stout(out.teni + o.oloc + l, y.teni);
-        stout(out.pclc + o.o1 + l, y.pclc);
-        stout(out.pcovptot + o.o1 + l, 0.0);
-        stout(out.pfplsl + o.oh + l + nproma, y.rfln);
-        stout(out.pfplsn + o.oh + l + nproma, y.sfln);
-        stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);
-        stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
-      }
-      slot ^= 1;
-    }
-  }
 
   // ---------------------------------- reverse sweep ---------------------------------------------
   // per level: trajectory inputs + the flux check-point + the 9 output adjoints, all staged one
@@ -117,7 +74,6 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     csc2_cp_async8(d + 25 * NT, dout.pfhpsl + o.oh + l + nproma);
     csc2_cp_async8(d + 26 * NT, dout.pfhpsn + o.oh + l + nproma);
   };
-  csc2_cp_async_wait<0>();
   stage_rev(ring, klev - 1);
   csc2_cp_async_commit();
 
@@ -140,8 +96,8 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     const double paph0 = x5.paph1;
     x5.paph1 = paph_hi5;
     const double pqs5 = in.pqs ? d[15 * NT] : satur_point(c, x5.pt, csc2_rcp(x5.pap));
-    const double rfl5 = (jk == klev - 1) ? rfl_last : d[16 * NT];
-    const double sfl5 = (jk == klev - 1) ? sfl_last : d[17 * NT];
+    const double rfl5 = d[16 * NT];
+    const double sfl5 = d[17 * NT];
     LevAdjIn ya;
     ya.tent = d[18 * NT];
     ya.tenq = d[19 * NT];
@@ -226,18 +182,22 @@ __global__ void k_ad_finalize(const Geom g, const double *__restrict__ n1, const
 
 }  // namespace
 
-template <bool RV, bool DOT, bool LREG>
+template <bool RV, bool DOT, bool LREG, int MINB>
 static cudaError_t launch_ad_k(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                                const IncIn &din, const IncOut &dout, const ADOpts &opt, int grid,
                                cudaStream_t s) {
   const size_t smem = (size_t)AD_STAGES * AD_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_ad<RV, DOT, LREG>;
+  auto kern = k_cloudsc2_ad<RV, DOT, LREG, MINB>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  // forward (trajectory) sweep: its own launch at the NL kernel's occupancy (12 warps/SM instead of
+  // the 8 the adjoint level allows), check-pointing the fluxes the reverse sweep restarts from
+  cudaError_t e = csc2_launch_nl_ckpt(c, g, in, out, opt.ckpt, opt.ncol_pad, opt.write_traj, s);
+  if (e != cudaSuccess) return e;
   kern<<<grid, CSC2_AD_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
 }
@@ -245,8 +205,13 @@ template <bool RV, bool DOT>
 static cudaError_t launch_ad_variant(const KConst &c, const Geom &g, const TrajIn &in,
                                      const TrajOut &out, const IncIn &din, const IncOut &dout,
                                      const ADOpts &opt, int grid, cudaStream_t s) {
-  if (c.lregcl) return launch_ad_k<RV, DOT, true>(c, g, in, out, din, dout, opt, grid, s);
-  return launch_ad_k<RV, DOT, false>(c, g, in, out, din, dout, opt, grid, s);
+  static const int minb = [] { const char *e = getenv("CSC2_AD_MINB"); return e ? atoi(e) : 2; }();
+  if (minb == 2) {
+    if (c.lregcl) return launch_ad_k<RV, DOT, true, 2>(c, g, in, out, din, dout, opt, grid, s);
+    return launch_ad_k<RV, DOT, false, 2>(c, g, in, out, din, dout, opt, grid, s);
+  }
+  if (c.lregcl) return launch_ad_k<RV, DOT, true, 3>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_ad_k<RV, DOT, false, 3>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,

@@ -660,7 +660,7 @@ int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const c
   ADOpts opt{0.0, 0, nullptr, g.work.d(), ncp, 1};
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
   CK(csc2_launch_ad(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
-  g.launches += 1;
+  g.launches += 2;      // forward (NL + check-points) and reverse sweep
   return 0;
 }
 
@@ -811,7 +811,7 @@ int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
   ADOpts aopt{0.01, 1, n2, ckpt, ncp, 1};
   CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
   CK(csc2_launch_ad_finalize(geo, n1, n2, d_norms, d_z, s));
-  g.launches += 3;
+  g.launches += 4;      // TL, AD forward, AD reverse, finalize
   double hz;
   CK(cudaMemcpyAsync(&hz, d_z, sizeof(double), cudaMemcpyDeviceToHost, s));
   if (norms_col)

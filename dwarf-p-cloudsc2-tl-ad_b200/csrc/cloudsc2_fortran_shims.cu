@@ -203,6 +203,7 @@ static void tlad(bool is_ad, const int *kidia, const int *kfdia, const int *klon
   if (is_ad) {
     ADOpts opt{0.0, 0, nullptr, m.next, (long long)ncp, 1};
     CKA(csc2_launch_ad(kc, g, in, out, din, dout, opt, s));
+    csc2_shim_count_launch();      // forward + reverse sweep = two launches
   } else {
     TLOpts opt{0.0, 0, nullptr, nullptr, 0};
     CKA(csc2_launch_tl(kc, g, in, out, din, dout, opt, s));

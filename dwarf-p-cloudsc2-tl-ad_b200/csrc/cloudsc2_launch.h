@@ -84,3 +84,9 @@ cudaError_t csc2_upload_levels_tl(const double *ceta, const double *zscalm, cons
                                   int klev, cudaStream_t s);
 cudaError_t csc2_upload_levels_ad(const double *ceta, const double *zscalm, const double *sq1mceta,
                                   int klev, cudaStream_t s);
+
+// Forward sweep of the adjoint as its own launch (cloudsc2_nl_kernel.cu): NL kernel that also
+// writes the rain/snow flux entering each level to ckpt ([2][klev][ncol_pad]); trajectory outputs
+// are written only if write_traj != 0.  Columns beyond ngptot are not touched.
+cudaError_t csc2_launch_nl_ckpt(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                double *ckpt, long long ncol_pad, int write_traj, cudaStream_t s);

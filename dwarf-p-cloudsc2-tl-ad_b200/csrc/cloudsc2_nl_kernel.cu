@@ -20,9 +20,18 @@ __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 constexpr int NL_NF = CSC2_NTRAJ;   // staged fields per level: 15 inputs + optional PQS
 
 // STAGES = depth of the shared-memory ring (levels in flight + the one being computed)
-template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV>
+// CKPT: forward (trajectory) sweep of the adjoint -- additionally check-points the rain / snow flux
+// ENTERING every level ([2][klev][ncol_pad]) and writes the trajectory outputs only on request.
+struct NLCkpt {
+  double *ckpt;
+  long long ncol_pad;
+  int write_traj;
+};
+
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV, bool CKPT>
 __global__ void __maxnreg__(MAXREG)
-k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out) {
+k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
+              const NLCkpt ck) {
   extern __shared__ double ring_all[];
   double *ring = ring_all + threadIdx.x;
   csc2_math_init();
@@ -33,6 +42,7 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const int klev = g.klev, nproma = g.nproma;
   const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
 
+  if (CKPT && gcol >= g.ngptot) return;
   if (gcol >= g.ngptot) {
     // padding column of the last block: the DRIVER zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV)
     // of whole blocks (driver_mod.F90:87-88); CLOUDSC2 itself never touches columns beyond ICEND.
@@ -58,11 +68,19 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   st.paph0 = ldin(in.paph + o.oh);
   st.rfl = 0.0;
   st.sfl = 0.0;
+  const bool wr = !CKPT || ck.write_traj != 0;
+  double *ck_r = nullptr, *ck_s = nullptr;
+  if (CKPT) {
+    ck_r = ck.ckpt + gcol;
+    ck_s = ck.ckpt + (size_t)klev * ck.ncol_pad + gcol;
+  }
   // flux rows at the model top (cloudsc2.F90:308-309, :732-733 -> -0.0)
-  stout(out.pfplsl + o.oh, 0.0);
-  stout(out.pfplsn + o.oh, 0.0);
-  stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
-  stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
+  if (wr) {
+    stout(out.pfplsl + o.oh, 0.0);
+    stout(out.pfplsn + o.oh, 0.0);
+    stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
+    stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
+  }
 
   int slot = 0, pslot = STAGES - 1;
   for (int jk = 0; jk < klev; ++jk) {
@@ -73,21 +91,27 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     const LevIn cur = csc2_read_level<NT>(ring + slot * (NL_NF * NT), jk, klev);
     const double pqs = HAS_PQS ? ring[(size_t)slot * (NL_NF * NT) + 15 * NT]
                                : satur_point(c, cur.pt, csc2_rcp(cur.pap));
+    if (CKPT) {
+      ck_r[(size_t)jk * ck.ncol_pad] = st.rfl;
+      ck_s[(size_t)jk * ck.ncol_pad] = st.sfl;
+    }
     LevOut y;
     nl_level<RV>(c, crh, jk, cur, pqs, st, y);
 
-    const size_t l = (size_t)jk * nproma;
-    stout(out.tent + o.oloc + l, y.tent);
-    stout(out.tenq + o.oloc + l, y.tenq);
-    stout(out.tenl + o.oloc + l, y.tenl);
-    stout(out.teni + o.oloc + l, y.teni);
-    if (out.loc_last) stout(out.loc_last + o.oloc + l, 0.0);
-    stout(out.pclc + o.o1 + l, y.pclc);
-    stout(out.pcovptot + o.o1 + l, 0.0);
-    stout(out.pfplsl + o.oh + l + nproma, y.rfln);
-    stout(out.pfplsn + o.oh + l + nproma, y.sfln);
-    stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);   // cloudsc2.F90:730-735
-    stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
+    if (wr) {
+      const size_t l = (size_t)jk * nproma;
+      stout(out.tent + o.oloc + l, y.tent);
+      stout(out.tenq + o.oloc + l, y.tenq);
+      stout(out.tenl + o.oloc + l, y.tenl);
+      stout(out.teni + o.oloc + l, y.teni);
+      if (out.loc_last) stout(out.loc_last + o.oloc + l, 0.0);
+      stout(out.pclc + o.o1 + l, y.pclc);
+      stout(out.pcovptot + o.o1 + l, 0.0);
+      stout(out.pfplsl + o.oh + l + nproma, y.rfln);
+      stout(out.pfplsn + o.oh + l + nproma, y.sfln);
+      stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);   // cloudsc2.F90:730-735
+      stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
+    }
     slot = (slot + 1 == STAGES) ? 0 : slot + 1;
     pslot = (pslot + 1 == STAGES) ? 0 : pslot + 1;
   }
@@ -150,20 +174,20 @@ cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cu
   return cudaGetLastError();
 }
 
-template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV>
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV, bool CKPT = false>
 static cudaError_t launch_nl_rv(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
-                                cudaStream_t s) {
+                                cudaStream_t s, NLCkpt ck = NLCkpt{nullptr, 0, 1}) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + NT - 1) / NT);
   const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV>;
+  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV, CKPT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, NT, smem, s>>>(c, g, in, out);
+  kern<<<grid, NT, smem, s>>>(c, g, in, out, ck);
   return cudaGetLastError();
 }
 template <bool HAS_PQS, int STAGES, int NT, int MAXREG>
@@ -198,6 +222,20 @@ cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, con
     case 7: return launch_nl_variant<false, 2, 64, 104>(c, g, in, out, s);    // 18 (19 by regs)
     default: return launch_nl_variant<false, 2, 128, 168>(c, g, in, out, s);  // 12
   }
+}
+
+// Forward (trajectory) sweep of the adjoint: the NL kernel + flux check-points.
+cudaError_t csc2_launch_nl_ckpt(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                double *ckpt, long long ncol_pad, int write_traj, cudaStream_t s) {
+  const NLCkpt ck{ckpt, ncol_pad, write_traj};
+  TrajOut o = out;
+  o.loc_last = nullptr;
+  if (c.rvtmp2 != 0.0) {
+    if (in.pqs) return launch_nl_rv<true, 2, 128, 168, true, true>(c, g, in, o, s, ck);
+    return launch_nl_rv<false, 2, 128, 168, true, true>(c, g, in, o, s, ck);
+  }
+  if (in.pqs) return launch_nl_rv<true, 2, 128, 168, false, true>(c, g, in, o, s, ck);
+  return launch_nl_rv<false, 2, 128, 168, false, true>(c, g, in, o, s, ck);
 }
 
 cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,
