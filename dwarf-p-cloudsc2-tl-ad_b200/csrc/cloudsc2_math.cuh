@@ -112,3 +112,11 @@ __device__ __forceinline__ void csc2_tanh_p1_sech2(double a, double &tanh_p1, do
   tanh_p1 = 2.0 * er;
   sech2 = 4.0 * er * r;
 }
+
+// Keep an expensive value unconditionally computed: without this the compiler turns
+// `cond ? f(x) : c` back into a (divergent) branch around f, which splits the level's basic block
+// and stops the scheduler from interleaving f with the surrounding chains.
+__device__ __forceinline__ double csc2_pin(double x) {
+  asm volatile("" : "+d"(x));
+  return x;
+}

@@ -100,7 +100,8 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
   // dqs/dT correction factor (:349-375)
   const bool cold = ztp1 < c.rtt;
   const double rw = csc2_rcp(ztp1 - c.r4les), ri = csc2_rcp(ztp1 - c.r4ies);
-  const double zfwat = cold ? 0.545 * csc2_tanh_p1(0.17 * (ztp1 - c.rlptrc)) : 1.0;
+  const double tanh_p1 = csc2_pin(csc2_tanh_p1(0.17 * (ztp1 - c.rlptrc)));   // unconditional
+  const double zfwat = cold ? 0.545 * tanh_p1 : 1.0;
   const double zfoeew = c.r2es * csc2_exp((cold ? c.r3ies * ri : c.r3les * rw) * (ztp1 - c.rtt));
   const double zfacw = c.r5les * (rw * rw), zfaci = c.r5ies * (ri * ri);
   const double zfac = zfwat * zfacw + (1.0 - zfwat) * zfaci;
@@ -184,7 +185,8 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
     L.zprr = cloudy ? zqlwc - zlnew : 0.0;
     zqlwc = zqlwc - L.zprr;
     // not cloudy: ice_fac = 0 and picld = ZQIWC make ZINEW = ZQIWC, i.e. ZPRS = 0 exactly
-    L.ice_fac = cloudy ? c.zckcodti * (1.0 - csc2_expn(-(rr * rr))) : 0.0;
+    const double zexp2 = csc2_pin(csc2_expn(-(rr * rr)));                        // unconditional
+    L.ice_fac = cloudy ? c.zckcodti * (1.0 - zexp2) : 0.0;
     L.picld = cloudy ? pclc * zcldi : zqiwc;
   }
   L.ztp1 = ztp1; L.zqp1 = zqp1; L.zl = zl; L.zi = zi;
