@@ -100,13 +100,13 @@ __device__ __forceinline__ double dmax_(double a, double b) { return a > b ? a :
 // both Tetens exponentials are always evaluated (their weights may be 0) so that the compiler
 // can interleave the two polynomial chains.
 __device__ __forceinline__ double satur_point(const KConst &c, double t, double pap_inv) {
-  const double x = (dmax_(c.rtice, dmin_(c.rtwat, t)) - c.rtice) * c.rtwat_rtice_r;
-  const double alfa = dmin_(1.0, x * x);
+  const double x = (csc2_max_pos(csc2_min_pos(t, c.rtwat), c.rtice) - c.rtice) * c.rtwat_rtice_r;
+  const double alfa = csc2_min_pos(x * x, 1.0);
   const double tm = t - c.rtt;
   const double el = csc2_exp(c.r3les * tm * csc2_rcp(t - c.r4les));
   const double ei = csc2_exp(c.r3ies * tm * csc2_rcp(t - c.r4ies));
   const double foeew = c.r2es * (alfa * el + (1.0 - alfa) * ei);
-  const double qs = dmin_(foeew * pap_inv, CSC2_ZQMAX);
+  const double qs = csc2_min_pos(foeew * pap_inv, CSC2_ZQMAX);
   return qs * csc2_rcp(1.0 - c.retv * qs);
 }
 

@@ -120,3 +120,19 @@ __device__ __forceinline__ double csc2_pin(double x) {
   asm volatile("" : "+d"(x));
   return x;
 }
+
+// Comparisons of a double with a POSITIVE constant on the integer pipe: for c > 0 and any
+// non-NaN x (negative, zero of either sign, positive) the IEEE order of x and c equals the order
+// of their bit patterns read as signed 64-bit integers.  Moves the compare off the FP64 pipe
+// (DSETP costs a 2-cycle FP64 slot), which is what bounds these kernels (tools/probes/fp64_probe).
+__device__ __forceinline__ bool csc2_lt_pos(double x, double c) {   // x <  c, c > 0
+  return __double_as_longlong(x) < __double_as_longlong(c);
+}
+__device__ __forceinline__ bool csc2_gt_pos(double x, double c) {   // x >  c, c > 0
+  return __double_as_longlong(x) > __double_as_longlong(c);
+}
+__device__ __forceinline__ bool csc2_ge_pos(double x, double c) {   // x >= c, c > 0
+  return __double_as_longlong(x) >= __double_as_longlong(c);
+}
+__device__ __forceinline__ double csc2_min_pos(double x, double c) { return csc2_lt_pos(x, c) ? x : c; }
+__device__ __forceinline__ double csc2_max_pos(double x, double c) { return csc2_gt_pos(x, c) ? x : c; }

@@ -31,7 +31,7 @@ struct Carry {
 // Two-iteration saturation adjustment (cuadjtqs.F90:118-130 phase select, :212-244).
 __device__ __forceinline__ void cuadjtqs_point(const KConst &c, double zqp /*1/p*/, double &t,
                                                double &q) {
-  const bool liq = t > c.rtt;
+  const bool liq = csc2_gt_pos(t, c.rtt);
   const double z3es = liq ? c.r3les : c.r3ies;
   const double z4es = liq ? c.r4les : c.r4ies;
   const double z5alcp = liq ? c.r5alvcp : c.r5alscp;
@@ -40,12 +40,12 @@ __device__ __forceinline__ void cuadjtqs_point(const KConst &c, double zqp /*1/p
   for (int it = 0; it < 2; ++it) {
     const double r = csc2_rcp(t - z4es);
     const double foeew = c.r2es * csc2_exp(z3es * (t - c.rtt) * r);
-    double qsat = dmin_(zqp * foeew, CSC2_ZQMAX);
-    const double cor = csc2_rcp(1.0 - c.retv * qsat);
-    qsat *= cor;
+    const double q0 = csc2_min_pos(zqp * foeew, CSC2_ZQMAX);      // ZQSAT before the correction
+    // ZCOR = 1/u, u = 1-RETV*q0 ; ZQSAT = q0/u ; ZCOND = (q-ZQSAT)/(1+ZQSAT*ZCOR*Z2S)  (:226-235)
+    // with ONE reciprocal:  ZCOND = (q*u - q0) * u / (u*u + q0*Z2S)
+    const double u = fma(-c.retv, q0, 1.0);
     const double z2s = z5alcp * (r * r);
-    const double den = csc2_rcp(1.0 + qsat * cor * z2s);
-    const double cond = (q - qsat) * den;
+    const double cond = (fma(q, u, -q0) * u) * csc2_rcp(fma(q0, z2s, u * u));
     t += zaldcp * cond;
     q -= cond;
   }
@@ -98,7 +98,7 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
   const double zdp_inv = csc2_rcp(zdp);
 
   // dqs/dT correction factor (:349-375)
-  const bool cold = ztp1 < c.rtt;
+  const bool cold = csc2_lt_pos(ztp1, c.rtt);
   const double rw = csc2_rcp(ztp1 - c.r4les), ri = csc2_rcp(ztp1 - c.r4ies);
   const double tanh_p1 = csc2_pin(csc2_tanh_p1(0.17 * (ztp1 - c.rlptrc)));   // unconditional
   const double zfwat = cold ? 0.545 * tanh_p1 : 1.0;
@@ -108,12 +108,12 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
   // ZCOR = 1/(1-RETV*ZESDP) with ZESDP = MIN(ZFOEEW/PAPP1, ZQMAX) shares the reciprocal of the
   // subsidence section: 1/(1-RETV*ZFOEEW/PAPP1) = PAPP1 * ZFAC2, ZFAC2 = 1/(PAPP1-RETV*ZFOEEW) (:451)
   const double zfac2 = csc2_rcp(x.pap - c.retv * zfoeew);
-  const double zcor = (zfoeew * pap_inv > CSC2_ZQMAX) ? c.zcor_cap : x.pap * zfac2;
+  const double zcor = csc2_gt_pos(zfoeew * pap_inv, CSC2_ZQMAX) ? c.zcor_cap : x.pap * zfac2;
   const double zdqsdtemp = zfac * zcor * pqs;
 
   // critical humidity, ice supersaturation (:384-408)
   const double zcrh2 = crit_rh(crh, CSC2_CETA(jk), CSC2_SQ1MCETA(jk));
-  const double zsupsat = (ztp1 < c.rtice) ? (1.8 - 3.e-03 * ztp1) : 1.0;
+  const double zsupsat = csc2_lt_pos(ztp1, c.rtice) ? (1.8 - 3.e-03 * ztp1) : 1.0;
   const double zqsat = pqs * zsupsat;
   const double zqcrit = zcrh2 * zqsat;
 
@@ -138,7 +138,7 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
   const double zgdp = c.rg * zdp_inv;
   const double zlude = x.plude * dt * zgdp;
   {
-    const bool llo1 = jk < c.klev - 1 && zlude >= c.rlmin && x.plu1 >= CSC2_ZEPS2;
+    const bool llo1 = jk < c.klev - 1 && csc2_ge_pos(zlude, c.rlmin) && csc2_ge_pos(x.plu1, CSC2_ZEPS2);
     const double e = csc2_expn(-zlude * csc2_rcp(llo1 ? x.plu1 : 1.0));
     pclc = llo1 ? pclc + (1.0 - pclc) * (1.0 - e) : pclc;
     zqc = llo1 ? zqc + zlude : zqc;
@@ -174,7 +174,7 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
 
   // autoconversion (:504-534): liquid completely, ice up to the factor that needs the post-melt T
   {
-    const bool cloudy = pclc > CSC2_ZEPS2;
+    const bool cloudy = csc2_gt_pos(pclc, CSC2_ZEPS2);
     const double pclc_inv = csc2_rcp(cloudy ? pclc : 1.0);
     const double zcldl = zqlwc * pclc_inv;
     const double rl = zcldl * c.rlcrit_inv;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void nl_tail(const KConst &c, const LevLocal &L, Carr
 
   // new precipitation, rain/snow split on the post-melt T (:538-552)
   const double zdr = L.zc2dp * (L.zprr + zprs);
-  const bool frz1 = ztp1 < c.rtt;
+  const bool frz1 = csc2_lt_pos(ztp1, c.rtt);
   double zrfreeze = frz1 ? L.zc2dp * L.zprr : 0.0;
   zsfln += frz1 ? zdr : 0.0;
   zrfln += frz1 ? 0.0 : zdr;
@@ -238,7 +238,7 @@ __device__ __forceinline__ void nl_tail(const KConst &c, const LevLocal &L, Carr
   {
     const double zdq = dmax_(0.0, zqold - zqp1);
     const double zdr2 = L.zc2dp * zdq;
-    const bool frz2 = ztp1 < c.rtt;
+    const bool frz2 = csc2_lt_pos(ztp1, c.rtt);
     zrfreeze += frz2 ? L.zfwat * zdr2 : 0.0;
     zcondi += frz2 ? zdq * c.zqtmst : 0.0;
     zcondl += frz2 ? 0.0 : zdq * c.zqtmst;
