@@ -48,7 +48,7 @@ __device__ __forceinline__ void adj_iter_fwd(const KConst &c, const AdjTraj &tr,
   it.r = csc2_rcp(t5 - tr.z4es);
   it.foeew = c.r2es * csc2_exp(tr.z3es * (t5 - c.rtt) * it.r);
   it.qs_raw = zqp5 * it.foeew;
-  it.cap = it.qs_raw > CSC2_ZQMAX;
+  it.cap = csc2_gt_pos(it.qs_raw, CSC2_ZQMAX);
   it.qs_raw = it.cap ? CSC2_ZQMAX : it.qs_raw;
   it.cor = csc2_rcp(1.0 - c.retv * it.qs_raw);
   it.qs = it.qs_raw * it.cor;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void adj_iter_fwd(const KConst &c, const AdjTraj &tr,
 // cuadjtqs_point, so the forward sweep and the recomputation agree bit for bit).
 __device__ __forceinline__ void cuadjtqs_traj(const KConst &c, double zqp5 /*1/p5*/, double &t5,
                                               double &q5, AdjTraj &tr) {
-  const bool liq = t5 > c.rtt;                              // cuadjtqsad.F90:150-162
+  const bool liq = csc2_gt_pos(t5, c.rtt);                              // cuadjtqsad.F90:150-162
   tr.z3es = liq ? c.r3les : c.r3ies;
   tr.z4es = liq ? c.r4les : c.r4ies;
   tr.z5alcp = liq ? c.r5alvcp : c.r5alscp;
@@ -123,21 +123,21 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double pap5_inv = csc2_rcp(x5.pap);
 
   const double rw = csc2_rcp(ztp25 - c.r4les), ri = csc2_rcp(ztp25 - c.r4ies);
-  const bool cold = ztp25 < c.rtt;
+  const bool cold = csc2_lt_pos(ztp25, c.rtt);
   const double targ = 0.17 * (ztp25 - c.rlptrc);
   double tanh_p1, sech2;
   csc2_tanh_p1_sech2(targ, tanh_p1, sech2);
   const double zfwat5 = cold ? 0.545 * tanh_p1 : 1.0;
   const double zfoeew5 = c.r2es * csc2_exp((cold ? c.r3ies * ri : c.r3les * rw) * (ztp25 - c.rtt));
   const double zesdp15 = zfoeew5 * pap5_inv;
-  const double zesdp5 = dmin_(zesdp15, CSC2_ZQMAX);
+  const double zesdp5 = csc2_min_pos(zesdp15, CSC2_ZQMAX);
   const double zfacw5 = c.r5les * (rw * rw), zfaci5 = c.r5ies * (ri * ri);
   const double zfac5 = zfwat5 * zfacw5 + (1.0 - zfwat5) * zfaci5;
   const double zcor5 = csc2_rcp(1.0 - c.retv * zesdp5);
   const double zdqsdtemp5 = zfac5 * zcor5 * pqs5;
 
   const double zcrh2 = crit_rh(crh, CSC2_CETA(jk), CSC2_SQ1MCETA(jk));
-  const bool vcold = ztp25 < c.rtice;
+  const bool vcold = csc2_lt_pos(ztp25, c.rtice);
   const double zsupsat5 = vcold ? (1.8 - 3.e-03 * ztp25) : 1.0;
   const double zqsat5 = pqs5 * zsupsat5;
   const double zqcrit5 = zcrh2 * zqsat5;
@@ -158,7 +158,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double zdp5_inv = csc2_rcp(zdp5);
   const double zgdp5 = c.rg * zdp5_inv;
   const double zlude5 = x5.plude * dt * zgdp5;
-  const bool llo1 = (jk < c.klev - 1) && zlude5 >= c.rlmin && x5.plu1 >= CSC2_ZEPS2;
+  const bool llo1 = (jk < c.klev - 1) && csc2_ge_pos(zlude5, c.rlmin) && csc2_ge_pos(x5.plu1, CSC2_ZEPS2);
   const double plu_inv = csc2_rcp(llo1 ? x5.plu1 : 1.0);
   const double econv = csc2_expn(-zlude5 * plu_inv);
   const double pclc5 = llo1 ? zclc5 + (1.0 - zclc5) * (1.0 - econv) : zclc5;
@@ -197,7 +197,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double ztp15 = ztp25 - zsnmlt5 * zcons5_inv;
 
   // autoconversion (:655-722)
-  const bool cloudy = pclc5 > CSC2_ZEPS2;
+  const bool cloudy = csc2_gt_pos(pclc5, CSC2_ZEPS2);
   const double pclc5_inv = csc2_rcp(cloudy ? pclc5 : 1.0);
   const double zcldl5 = zqlwc15 * pclc5_inv;
   const double zexp35 = csc2_expn(-SQA_(zcldl5 * c.rlcrit_inv));
@@ -210,7 +210,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double zprs5 = cloudy ? zqiwc15 - pclc5 * zcldi5 * zexpdi5 : 0.0;
   const double zc2dp5 = c.zcons2 * zdp5;
   const double zdr15 = zc2dp5 * (zprr5 + zprs5);
-  const bool frz1 = ztp15 < c.rtt;
+  const bool frz1 = csc2_lt_pos(ztp15, c.rtt);
   const double zrfreeze15 = frz1 ? zc2dp5 * zprr5 : 0.0;
   const double zfwatr15 = frz1 ? 0.0 : 1.0;
 
@@ -237,7 +237,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const bool exc = (zqold5 - q5adj) >= 0.0;
   const double zdq5 = exc ? (zqold5 - q5adj) : 0.0;
   const double zdr25 = zc2dp5 * zdq5;
-  const bool frz2 = t5adj < c.rtt;
+  const bool frz2 = csc2_lt_pos(t5adj, c.rtt);
   const double zfwatr25 = frz2 ? 0.0 : 1.0;
   const double zrfreeze35 = zrfreeze15 + (frz2 ? zfwat5 * zdr25 : 0.0);
   const double zcondl25 = zcondl15 + zfwatr25 * zdq5 * c.zqtmst;
@@ -423,7 +423,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     if (lreg) {                                            // :1554-1559
       const double zrat = (partial5 ? zqpd5 : 1.0) * csc2_rcp(partial5 ? zqcd5 : 1.0);
       const double b = 1.0 - zscalm * (1.0 - zrat);
-      const double zyyy = dmin_(0.3, 3.5 * csc2_sqrt(zrat * (b * b * b)) * csc2_rcp(1.0 - zscalm));
+      const double zyyy = csc2_min_pos(3.5 * csc2_sqrt(zrat * (b * b * b)) * csc2_rcp(1.0 - zscalm), 0.3);
       pc_ = zyyy * pc_;
     }
     const double h = (0.5 * csc2_rcp(zsqrt5)) * pc_ * den5_inv;
@@ -455,7 +455,7 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
     zfwat_ += (zfacw5 - zfaci5) * zfac;
     ztp1_ -= 2.0 * zfaci5 * ri * zfaci;                    // 2*R5IES*ZFACI/(T-R4IES)**3
     ztp1_ -= 2.0 * zfacw5 * rw * zfacw;
-    zesdp = (zesdp15 > CSC2_ZQMAX) ? 0.0 : zesdp;
+    zesdp = csc2_gt_pos(zesdp15, CSC2_ZQMAX) ? 0.0 : zesdp;
     zfoeew_ += zesdp * pap5_inv;
     pap_ -= zesdp * zfoeew5 * (pap5_inv * pap5_inv);
     const double rsel = cold ? ri : rw;
