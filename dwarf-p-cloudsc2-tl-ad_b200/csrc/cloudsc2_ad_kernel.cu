@@ -188,12 +188,8 @@ static cudaError_t launch_ad_k(const KConst &c, const Geom &g, const TrajIn &in,
                                cudaStream_t s) {
   const size_t smem = (size_t)AD_STAGES * AD_NF * NT * sizeof(double);
   auto kern = k_cloudsc2_ad<RV, DOT, LREG, MINB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static int smem_ok_on_device = -1;
+  if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   // forward (trajectory) sweep: its own launch at the NL kernel's occupancy (12 warps/SM instead of
   // the 8 the adjoint level allows), check-pointing the fluxes the reverse sweep restarts from
   cudaError_t e = csc2_launch_nl_ckpt(c, g, in, out, opt.ckpt, opt.ncol_pad, opt.write_traj, s);

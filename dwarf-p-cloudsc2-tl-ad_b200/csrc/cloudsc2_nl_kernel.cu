@@ -181,12 +181,8 @@ static cudaError_t launch_nl_rv(const KConst &c, const Geom &g, const TrajIn &in
   const int grid = (int)((ncol + NT - 1) / NT);
   const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double);
   auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV, CKPT>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static int smem_ok_on_device = -1;
+  if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   kern<<<grid, NT, smem, s>>>(c, g, in, out, ck);
   return cudaGetLastError();
 }

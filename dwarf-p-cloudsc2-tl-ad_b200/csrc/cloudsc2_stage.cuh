@@ -86,3 +86,17 @@ __device__ __forceinline__ LevIn csc2_read_level(const double *d, int jk, int kl
   x.gi = d[13 * NT]; x.psupsat = d[14 * NT];
   return x;
 }
+
+// Opt a kernel in to more than 48 kB of dynamic shared memory, once per (kernel, device): the
+// attribute is per device, and cloudsc2_gpu_init may move the library to another device.
+// `done_for_device` is a static of the calling launcher (one per kernel instantiation).
+template <typename K>
+static inline cudaError_t csc2_allow_smem(K kern, size_t smem, int &done_for_device) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev == done_for_device) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) done_for_device = dev;
+  return e;
+}

@@ -301,12 +301,8 @@ static cudaError_t launch_tl_k(const KConst &c, const Geom &g, const TrajIn &in,
                                cudaStream_t s) {
   const size_t smem = (size_t)STAGES * TL_NF * NT * sizeof(double);
   auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static int smem_ok_on_device = -1;
+  if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   kern<<<grid, CSC2_TL_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
 }
