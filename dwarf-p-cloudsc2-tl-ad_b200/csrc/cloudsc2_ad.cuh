@@ -209,7 +209,6 @@ __device__ __forceinline__ void ad_level(const KConst &c, const CritRH &crh, int
   const double zexpdi5 = csc2_exp(-(c.zckcodti * zexp15 * (1.0 - zexp25)));
   const double zprs5 = cloudy ? zqiwc15 - pclc5 * zcldi5 * zexpdi5 : 0.0;
   const double zc2dp5 = c.zcons2 * zdp5;
-  const double zdr15 = zc2dp5 * (zprr5 + zprs5);
   const bool frz1 = csc2_lt_pos(ztp15, c.rtt);
   const double zrfreeze15 = frz1 ? zc2dp5 * zprr5 : 0.0;
   const double zfwatr15 = frz1 ? 0.0 : 1.0;

@@ -49,9 +49,14 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const int jl = gcol - ibl * g.nproma;
   const int klev = g.klev, nproma = g.nproma;
   const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
-  double *ck_r = opt.ckpt + gcol;                                   // [klev][ncol_pad] rain
-  double *ck_s = opt.ckpt + (size_t)klev * opt.ncol_pad + gcol;     // [klev][ncol_pad] snow
-  const size_t cks = (size_t)opt.ncol_pad;
+  // Flux entering level JK (the only state the reverse sweep needs from the forward sweep):
+  // when the forward sweep wrote the trajectory outputs, it IS PFPLSL5(JK) / PFPLSN5(JK)
+  // (cloudsc2ad.F90:847-848), so no separate check-point array is written or read; otherwise
+  // it comes from the [2][klev][ncol_pad] check-point buffer.
+  const bool from_traj = opt.write_traj != 0;
+  const double *ck_r = from_traj ? out.pfplsl + o.oh : opt.ckpt + gcol;
+  const double *ck_s = from_traj ? out.pfplsn + o.oh : opt.ckpt + (size_t)klev * opt.ncol_pad + gcol;
+  const size_t cks = from_traj ? (size_t)nproma : (size_t)opt.ncol_pad;
   constexpr int SLOT = AD_NF * NT;
 
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));

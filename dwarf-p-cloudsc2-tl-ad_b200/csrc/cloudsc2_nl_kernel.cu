@@ -91,7 +91,7 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     const LevIn cur = csc2_read_level<NT>(ring + slot * (NL_NF * NT), jk, klev);
     const double pqs = HAS_PQS ? ring[(size_t)slot * (NL_NF * NT) + 15 * NT]
                                : satur_point(c, cur.pt, csc2_rcp(cur.pap));
-    if (CKPT) {
+    if (CKPT && !wr) {   // with the trajectory outputs written, PFPLSL/PFPLSN are the check-points
       ck_r[(size_t)jk * ck.ncol_pad] = st.rfl;
       ck_s[(size_t)jk * ck.ncol_pad] = st.sfl;
     }
