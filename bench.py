@@ -384,6 +384,17 @@ def main():
                "sample": f"{sample} columns, NPROMA={nproma}, best of 3, block loop only "
                          "(C restatement of the reference; Fortran not buildable in this image)",
                "readme_config_4threads_nproma32": cps4}
+        # TL / AD kernels of the CPU port on the same cores (CLOUDSC2TL / CLOUDSC2AD block loops,
+        # increments = 1 % of the inputs), for the "modes" lines: a small sample, they are slow
+        try:
+            st_c = pkg.ArrayState(src, nproma, 16384)
+            cpu["tl_columns_per_s"] = 16384 / min(ob.bench_tlad("tl", prm, src.ceta, st_c, numomp=threads)
+                                                  for _ in range(2))
+            cpu["ad_columns_per_s"] = 16384 / min(ob.bench_tlad("ad", prm, src.ceta, st_c, numomp=threads)
+                                                  for _ in range(2))
+            cpu["tl_ad_sample"] = "16384 columns, best of 2, block loop only"
+        except Exception as e:                      # never let the baseline leg kill the bench line
+            cpu["tl_ad_error"] = str(e)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
