@@ -20,7 +20,7 @@ G2O_OUT = {"tent": "ptent", "tenq": "ptenq", "tenl": "ptenl", "teni": "pteni", "
 
 
 @pytest.mark.parametrize("nproma,ngptot,lregcl", [(100, 100, True), (32, 100, True), (1, 40, False),
-                                                  (64, 200, False)])
+                                                  (64, 200, False), (128, 2048, True), (256, 1000, False)])
 def test_ad_fields_match_oracle(pkg, ob, src100, nproma, ngptot, lregcl):
     prm = pkg.default_params(lregcl=lregcl)
     st = pkg.ArrayState(src100, nproma, ngptot)

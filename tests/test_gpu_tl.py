@@ -27,7 +27,7 @@ def _tl_reference(ob, prm, src, st, scale=0.01):
 
 
 @pytest.mark.parametrize("nproma,ngptot,lregcl", [(100, 100, False), (32, 100, False), (1, 100, False),
-                                                  (64, 640, True), (128, 300, True)])
+                                                  (64, 640, True), (128, 300, True), (128, 4096, False), (256, 3000, True)])
 def test_tl_fields_match_oracle(pkg, ob, src100, nproma, ngptot, lregcl):
     prm = pkg.default_params(lregcl=lregcl)
     st = pkg.ArrayState(src100, nproma, ngptot)
