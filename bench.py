@@ -372,6 +372,26 @@ def main():
 
     total_launches = int(sum_over_ranks(float(launches)))
 
+    # ---- the path's only collective, on the real interconnect: block-sharded Taylor and adjoint
+    # self-tests (BASELINE configs 2/3 scaled to 6400 columns per rank), norms all-reduced (MAX)
+    # over the ranks with NCCL (cloudsc_driver_tl_mod.F90:125, cloudsc_driver_ad_mod.F90:107)
+    selftests = None
+    try:
+        t0 = time.perf_counter()
+        z, _ = pkg.sharded_taylor(gpu, src, nproma, 6400 * world, rank, world, device=dev)
+        pen, istart = pkg.taylor_verdict(z)
+        gpu_ad = pkg.Cloudsc2(pkg.default_params(lregcl=True), KLEV, src.ceta, device=local_rank)
+        zn, _ = pkg.sharded_adjoint(gpu_ad, src, nproma, 6400 * world, rank, world, device=dev)
+        gpu_ad.close()
+        gpu._bind()
+        selftests = {"ngptot_total": 6400 * world, "taylor_penalty": pen, "taylor_passed": 0 <= pen <= 5,
+                     "taylor_ratios": [float(v) for v in z], "adjoint_znormg_eps": zn,
+                     "adjoint_passed": bool(pkg.adjoint_verdict(zn)),
+                     "allreduce": "nccl max over %d rank(s)" % world if world > 1 else "single rank",
+                     "seconds": time.perf_counter() - t0}
+    except Exception as e:                          # evidence only: never lose the bench line over it
+        selftests = {"error": str(e)}
+
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -411,7 +431,10 @@ def main():
                              "algorithmic_bytes_per_launch": NL_BYTES_PER_COL * ngp,
                              "fp64_pipe_pct_ncu": NCU["nl"]["fp64_pipe_pct"]},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
-                "modes": results, "nproma_sweep_ngptot160000": sweep}
+                "modes": results, "nproma_sweep_ngptot160000": sweep, "selftests": selftests}
+        # the reference's own report lines (timer_mod.F90:114-174), on stderr
+        sys.stderr.write(pkg.report.performance_table(1, ngp * world, ds.nblocks * world, nproma,
+                                                      ms_nl * 1e-3, numproc=world) + "\n")
         print(json.dumps(line))
     ds.free()
     gpu.close()
