@@ -94,6 +94,8 @@ def _declare(lib):
         "cloudsc2_gpu_expand_shard_dev": (i, [vp, i, i, i, vp, i, i, C.c_longlong, vp]),
         "cloudsc2_gpu_host_register": (i, [vp, C.c_ulonglong]),
         "cloudsc2_gpu_host_unregister": (i, [vp]),
+        "cloudsc2_gpu_host_alloc": (i, [C.POINTER(vp), C.c_ulonglong]),
+        "cloudsc2_gpu_host_free": (i, [vp]),
         "cloudsc2_gpu_malloc": (i, [C.POINTER(vp), C.c_ulonglong]),
         "cloudsc2_gpu_free": (i, [vp]),
         "cloudsc2_gpu_memcpy_h2d": (i, [vp, vp, C.c_ulonglong]),

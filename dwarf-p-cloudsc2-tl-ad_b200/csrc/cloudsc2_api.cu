@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "cloudsc2_launch.h"
@@ -72,12 +73,14 @@ Ctx g;
 struct Options {
   int e2e_mode = 0;         // 0/1 staged copies, 2 zero-copy kernel on mapped host arrays
   int e2e_chunk_mb = 256;   // cap of the staging chunk size
+  int e2e_host_derive = 1;  // derive PCOVPTOT / CLD(:,:,NCLV) / PFHPSL / PFHPSN on the host instead of copying them
   bool loaded = false;
   void load() {
     if (loaded) return;
     loaded = true;
     if (const char *e = getenv("CSC2_E2E_MODE")) e2e_mode = atoi(e);
     if (const char *e = getenv("CSC2_E2E_CHUNK_MB")) if (atoi(e) > 0) e2e_chunk_mb = atoi(e);
+    if (const char *e = getenv("CSC2_E2E_HOST_DERIVE")) e2e_host_derive = atoi(e);
   }
 };
 Options opts;
@@ -214,6 +217,15 @@ int download_outputs(const cloudsc2_fields *h, const DevProblem &dp) {
 }
 
 inline long long pad_cols(long long n) { return (n + 127) / 128 * 128; }
+
+// Host threads for the derived-output fill: an explicit count, because launchers such as torchrun
+// export OMP_NUM_THREADS=1 to every rank; the cores are shared between the ranks of the box.
+int host_worker_threads() {
+  int ndev = 1;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(16u, (hw ? hw : 8u) / (unsigned)ndev));
+}
 
 // Device-side aliases of page-locked, mapped host arrays; false if any array is not mapped.
 bool map_host_fields(const cloudsc2_fields &h, cloudsc2_fields &d) {
@@ -353,6 +365,16 @@ int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes) {
   CK(cudaStreamSynchronize(g.stream));
   return 0;
 }
+int cloudsc2_gpu_host_alloc(void **ptr, unsigned long long bytes) {
+  if (int rc = require_init()) return rc;
+  if (!ptr) return fail(3, "cloudsc2_gpu_host_alloc: NULL argument");
+  CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+  return 0;
+}
+int cloudsc2_gpu_host_free(void *ptr) {
+  CK(cudaFreeHost(ptr));
+  return 0;
+}
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes) {
   if (int rc = require_init()) return rc;
   CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
@@ -404,6 +426,7 @@ int cloudsc2_gpu_set_option(const char *name, int value) {
   if (!name) return fail(3, "option name is NULL");
   if (!strcmp(name, "e2e_mode")) { opts.e2e_mode = value; return 0; }
   if (!strcmp(name, "e2e_chunk_mb") && value > 0) { opts.e2e_chunk_mb = value; return 0; }
+  if (!strcmp(name, "e2e_host_derive")) { opts.e2e_host_derive = value; return 0; }
   if (!strcmp(name, "nl_variant")) { csc2_set_nl_variant(value); return 0; }
   return fail(3, "unknown option '%s' (or bad value %d)", name, value);
 }
@@ -524,8 +547,18 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
   const size_t nchunks = plan.size();
   const KConst kc = make_kconst(ptsphy);
 
-  std::vector<cudaEvent_t> k0(nchunks), k1(nchunks);
-  for (size_t i = 0; i < nchunks; ++i) { CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i])); }
+  // Four of the eleven output arrays need not cross PCIe: PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV)
+  // are identically zero (cloudsc_driver_mod.F90:87-88; cloudsc2.F90 never raises PCOVPTOT with
+  // LEVAPLS2 off), PFHPSL = -PFPLSL*RLVTT and PFHPSN = -PFPLSN*RLSTT (:730-735) are one exact
+  // multiplication of arrays that are copied anyway.  The host fills them per chunk as soon as the
+  // chunk's D2H has landed, overlapped with the transfers of the later chunks; that leaves the
+  // H2D direction -- the bound of this call -- less disturbed by D2H traffic.
+  const bool derive = opts.e2e_host_derive != 0;
+  std::vector<cudaEvent_t> k0(nchunks), k1(nchunks), dn(nchunks);
+  for (size_t i = 0; i < nchunks; ++i) {
+    CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i]));
+    CK(cudaEventCreateWithFlags(&dn[i], cudaEventDisableTiming));
+  }
   CK(cudaEventRecord(g.ev[0], g.stream));
   for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(g.pipe[i], g.ev[0], 0));
 
@@ -579,10 +612,39 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
     // B_LOC slabs T (0), Q,QL,QI (2-4) and the zeroed CLD(:,:,NCLV) (7)
     CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0, 8 * n2 * D, d_loc + 5 * n2 * b0, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + n2, 5 * n2 * D, 3 * n2 * D, cb, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 7 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + 4 * n2, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
-    CK(d2h(h->pa, d_pa, n2)); CK(d2h(h->pcovptot, d_pcov, n2));
+    if (!derive)
+      CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 7 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + 4 * n2, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    CK(d2h(h->pa, d_pa, n2));
     CK(d2h(h->pfplsl, d_fl, n2h)); CK(d2h(h->pfplsn, d_fn, n2h));
-    CK(d2h(h->pfhpsl, d_hl, n2h)); CK(d2h(h->pfhpsn, d_hn, n2h));
+    if (!derive) {
+      CK(d2h(h->pcovptot, d_pcov, n2));
+      CK(d2h(h->pfhpsl, d_hl, n2h)); CK(d2h(h->pfhpsn, d_hn, n2h));
+    }
+    CK(cudaEventRecord(dn[ic], s));
+  }
+  if (derive) {
+    // host side of the derived outputs, chunk by chunk behind the D2H of PFPLSL / PFPLSN
+    const double rlvtt = g.prm.rlvtt, rlstt = g.prm.rlstt;
+    const int nthr = host_worker_threads();
+    size_t cb0 = 0;
+    for (size_t ic = 0; ic < nchunks; cb0 += plan[ic], ++ic) {
+      CK(cudaEventSynchronize(dn[ic]));
+      const long long blk_lo = (long long)cb0, blk_hi = (long long)(cb0 + plan[ic]);
+#pragma omp parallel for schedule(static) num_threads(nthr)
+      for (long long b = blk_lo; b < blk_hi; ++b) {
+        const int icend = (int)std::min<long long>(nproma, (long long)ngptot - b * nproma);
+        std::memset(h->pcovptot + n2 * b, 0, n2 * D);                  // whole block (driver_mod.F90:87)
+        std::memset(h->b_loc + 8 * n2 * b + 7 * n2, 0, n2 * D);        // %CLD(:,:,NCLV) (:88)
+        const double *fl = h->pfplsl + n2h * b, *fn = h->pfplsn + n2h * b;
+        double *hl = h->pfhpsl + n2h * b, *hn = h->pfhpsn + n2h * b;
+        for (int jk = 0; jk <= klev; ++jk)
+          for (int jl = 0; jl < icend; ++jl) {                         // columns beyond ICEND keep their values
+            const size_t i = (size_t)jk * nproma + jl;
+            hl[i] = -fl[i] * rlvtt;
+            hn[i] = -fn[i] * rlstt;
+          }
+      }
+    }
   }
   for (int i = 0; i < kStreams; ++i) {
     CK(cudaEventRecord(g.ev[2], g.pipe[i]));
@@ -598,6 +660,7 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
     kms += t;
     cudaEventDestroy(k0[i]);
     cudaEventDestroy(k1[i]);
+    cudaEventDestroy(dn[i]);
   }
   if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
   if (elapsed_kernel_s) *elapsed_kernel_s = kms * 1e-3;

@@ -338,6 +338,19 @@ class Cloudsc2:
                                                      y.ctypes.data_as(_abi.c_double_p), x.size))
         return y
 
+    def host_alloc_like(self, arr: np.ndarray) -> tuple[np.ndarray, int]:
+        """A page-locked (cudaHostAlloc) copy of `arr` -> (array view, pointer to free with host_free)."""
+        self._bind()
+        p = C.c_void_p()
+        self._check(self.lib.cloudsc2_gpu_host_alloc(C.byref(p), max(arr.nbytes, 8)))
+        buf = (C.c_double * arr.size).from_address(p.value)
+        out = np.frombuffer(buf, dtype=np.float64, count=arr.size).reshape(arr.shape)
+        out[...] = arr
+        return out, int(p.value)
+
+    def host_free(self, ptr: int):
+        self._check(self.lib.cloudsc2_gpu_host_free(ptr))
+
     def pin(self, arr: np.ndarray):
         self._bind()
         self._check(self.lib.cloudsc2_gpu_host_register(arr.ctypes.data, arr.nbytes))

@@ -197,6 +197,11 @@ int cloudsc2_gpu_sync(void);
  * ALLOCATE in expand_mod.F90:110,127,148).  Optional; pageable memory works, slower. */
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes);
 int cloudsc2_gpu_host_unregister(void *ptr);
+/* Allocate / free page-locked host memory directly (cudaHostAlloc): what a host uses INSTEAD of
+ * ALLOCATE + cloudsc2_gpu_host_register when it can (Fortran: C_F_POINTER on the result).  DMA from
+ * such memory runs at the full PCIe rate; registered pageable memory was measured ~15 % slower. */
+int cloudsc2_gpu_host_alloc(void **ptr, unsigned long long bytes);
+int cloudsc2_gpu_host_free(void *ptr);
 
 /* ---- tuning ------------------------------------------------------------------------------- */
 /* Integer tuning options (defaults come from the environment variables in parentheses):
@@ -204,6 +209,10 @@ int cloudsc2_gpu_host_unregister(void *ptr);
  *                                      2 = zero-copy: the kernel reads/writes page-locked, mapped
  *                                      host arrays directly (cloudsc2_gpu_host_register)
  *   "e2e_chunk_mb" (CSC2_E2E_CHUNK_MB) cap of the staging chunk size in MB (default 256)
+ *   "e2e_host_derive" (CSC2_E2E_HOST_DERIVE) 1 (default): the host-pointer NL entry does not copy
+ *                                      PCOVPTOT, TENDENCY_LOC%CLD(:,:,NCLV) (identically zero) and
+ *                                      PFHPSL/PFHPSN (= -PFPLSL*RLVTT, -PFPLSN*RLSTT) back over PCIe
+ *                                      but fills them on the host, bit-identically; 0: copy all
  *   "nl_variant"   (CSC2_NL_VARIANT)   launch shape of the NL kernel (csrc/cloudsc2_nl_kernel.cu)
  * Nothing like this exists in the reference (its only knobs are NUMOMP and NPROMA). */
 int cloudsc2_gpu_set_option(const char *name, int value);

@@ -222,3 +222,22 @@ def test_nl_staged_chunk_plan_covers_every_block(pkg, src100, gpu_nl):
                 assert np.array_equal(v, want[k]), (cap, k)
     finally:
         gpu_nl.set_option("e2e_chunk_mb", 256)
+
+
+@pytest.mark.parametrize("nproma,ngptot", [(32, 1000), (128, 5000), (7, 23)])
+def test_nl_host_derived_outputs_equal_copied_outputs(pkg, src100, gpu_nl, nproma, ngptot):
+    """Option e2e_host_derive (default on): PCOVPTOT, TENDENCY_LOC%CLD(:,:,NCLV), PFHPSL, PFHPSN are
+    filled on the host instead of being copied back; the result must be bit-identical to copying
+    everything, including the -0.0 enthalpy flux at the model top and untouched padding columns."""
+    a, b = pkg.ArrayState(src100, nproma, ngptot), pkg.ArrayState(src100, nproma, ngptot)
+    for s in (a, b):
+        s.reset_outputs(fill=4.75)
+    gpu_nl.nl(a)
+    gpu_nl.set_option("e2e_host_derive", 0)
+    try:
+        gpu_nl.nl(b)
+    finally:
+        gpu_nl.set_option("e2e_host_derive", 1)
+    for n in a.a:
+        assert np.array_equal(a.a[n], b.a[n]), n
+        assert np.array_equal(np.signbit(a.a[n]), np.signbit(b.a[n])), n
