@@ -2,10 +2,11 @@
 // NPROMA block in one launch.  Replaces the OpenMP block loop of CLOUDSC_DRIVER
 // (reference src/cloudsc2_nl/cloudsc_driver_mod.F90:82-111).
 //
-// Mapping: thread <-> column, CTA = 128 consecutive columns, the KLEV loop runs in registers with
-// the next level's 15 inputs prefetched while the current level is computed.  Loads/stores are
-// coalesced along NPROMA (JL); every input is read exactly once (plus the ~40-level tropopause
-// pre-pass over PT/PGTENT, which the main sweep re-reads out of L2), PQSAT never touches memory.
+// Mapping: thread <-> column, CTA = 128 consecutive columns, the KLEV loop keeps the column state
+// in registers while the next level's 15 inputs are copied by cp.async into a per-thread slot of a
+// shared-memory ring (cloudsc2_stage.cuh).  Loads/stores are coalesced along NPROMA (JL); every
+// input is read exactly once (plus the ~40-level tropopause pre-pass over PT/PGTENT), PQSAT never
+// touches memory.  The same kernel, with flux check-points, is the forward sweep of the adjoint.
 #include <cstdlib>
 
 #include "cloudsc2_nl.cuh"
@@ -19,7 +20,9 @@ __device__ __forceinline__ void stout(double *p, double v) { __stcs(p, v); }
 
 constexpr int NL_NF = CSC2_NTRAJ;   // staged fields per level: 15 inputs + optional PQS
 
-// STAGES = depth of the shared-memory ring (levels in flight + the one being computed)
+// Template parameters: HAS_PQS (PQS supplied by the caller instead of the fused SATUR), STAGES =
+// depth of the shared-memory ring (levels in flight + the one being computed), NT = threads per
+// CTA, MAXREG = register cap (-> CTAs per SM), RV = (RVTMP2 != 0).
 // CKPT: forward (trajectory) sweep of the adjoint -- additionally check-points the rain / snow flux
 // ENTERING every level ([2][klev][ncol_pad]) and writes the trajectory outputs only on request.
 struct NLCkpt {
