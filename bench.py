@@ -323,6 +323,23 @@ def main():
                                  "bytes_per_column": AD_BYTES_PER_COL,
                                  "note": "CLOUDSC2AD as written: traj in/out, adjoints RMW",
                                  **ncu_part("ad", ms_ad)}
+                # the adjoint behind an existing trajectory (every 4D-Var inner loop; the reference's own
+                # adjoint test runs CLOUDSC2TL on the same inputs first): no forward sweep, the flux
+                # check-points are the PFPLSL5/PFPLSN5 already in the state.  Bytes: as written minus the
+                # 1374 trajectory outputs not re-written plus the 2x137 fluxes read = 9464 values.
+                gpu.nl_dev(ds, src.ptsphy, stream=stream)
+                gpu.set_option("ad_have_trajectory", 1)
+                try:
+                    ms_ad2 = timed(lambda: gpu.ad_dev(ds, src.ptsphy, din, dout, stream=stream),
+                                   max(3, args.steps // 2), 3)
+                finally:
+                    gpu.set_option("ad_have_trajectory", 0)
+                gbs2 = 9464 * 8 * ngp / (ms_ad2 * 1e-3) / 1e9
+                results["ad_have_trajectory"] = {
+                    "columns_per_s": ngp * world / (ms_ad2 * 1e-3), "ms_per_step": ms_ad2, "gbs_per_gpu": gbs2,
+                    "frac_of_hbm": gbs2 / peak, "bytes_per_column": 9464 * 8,
+                    "note": "reverse sweep only (option ad_have_trajectory): trajectory fluxes taken from a "
+                            "preceding NL/TL call on the same inputs"}
             except pkg.Cloudsc2Error as e:
                 results["ad"] = {"error": str(e)}
         for p in list(din.values()) + list(dout.values()):

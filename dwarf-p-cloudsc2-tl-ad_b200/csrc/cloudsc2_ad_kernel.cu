@@ -53,7 +53,7 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   // when the forward sweep wrote the trajectory outputs, it IS PFPLSL5(JK) / PFPLSN5(JK)
   // (cloudsc2ad.F90:847-848), so no separate check-point array is written or read; otherwise
   // it comes from the [2][klev][ncol_pad] check-point buffer.
-  const bool from_traj = opt.write_traj != 0;
+  const bool from_traj = opt.write_traj != 0 || opt.have_traj != 0;
   const double *ck_r = from_traj ? out.pfplsl + o.oh : opt.ckpt + gcol;
   const double *ck_s = from_traj ? out.pfplsn + o.oh : opt.ckpt + (size_t)klev * opt.ncol_pad + gcol;
   const size_t cks = from_traj ? (size_t)nproma : (size_t)opt.ncol_pad;
@@ -202,8 +202,10 @@ static cudaError_t launch_ad_k(const KConst &c, const Geom &g, const TrajIn &in,
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   // forward (trajectory) sweep: its own launch at the NL kernel's occupancy (12 warps/SM instead of
   // the 8 the adjoint level allows), check-pointing the fluxes the reverse sweep restarts from
-  cudaError_t e = csc2_launch_nl_ckpt(c, g, in, out, opt.ckpt, opt.ncol_pad, opt.write_traj, s);
-  if (e != cudaSuccess) return e;
+  if (!opt.have_traj) {
+    cudaError_t e = csc2_launch_nl_ckpt(c, g, in, out, opt.ckpt, opt.ncol_pad, opt.write_traj, s);
+    if (e != cudaSuccess) return e;
+  }
   kern<<<grid, CSC2_AD_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
 }

@@ -73,6 +73,7 @@ Ctx g;
 struct Options {
   int e2e_mode = 0;         // 0/1 staged copies, 2 zero-copy kernel on mapped host arrays
   int e2e_chunk_mb = 256;   // cap of the staging chunk size
+  int ad_have_trajectory = 0;   // cloudsc2_gpu_ad_dev: skip the forward sweep (fluxes already in dev->pfplsl/pfplsn)
   int e2e_host_derive = 1;  // derive PCOVPTOT / CLD(:,:,NCLV) / PFHPSL / PFHPSN on the host instead of copying them
   bool loaded = false;
   void load() {
@@ -427,6 +428,7 @@ int cloudsc2_gpu_set_option(const char *name, int value) {
   if (!strcmp(name, "e2e_mode")) { opts.e2e_mode = value; return 0; }
   if (!strcmp(name, "e2e_chunk_mb") && value > 0) { opts.e2e_chunk_mb = value; return 0; }
   if (!strcmp(name, "e2e_host_derive")) { opts.e2e_host_derive = value; return 0; }
+  if (!strcmp(name, "ad_have_trajectory")) { opts.ad_have_trajectory = value != 0; return 0; }
   if (!strcmp(name, "nl_variant")) { csc2_set_nl_variant(value); return 0; }
   return fail(3, "unknown option '%s' (or bad value %d)", name, value);
 }
@@ -720,10 +722,12 @@ int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const c
   inc_views(din_, dout_, din, dout);
   const long long ncp = pad_cols((long long)geo.nblocks * nproma);
   if (int rc = g.work.reserve((size_t)2 * klev * ncp * sizeof(double))) return rc;
-  ADOpts opt{0.0, 0, nullptr, g.work.d(), ncp, 1};
+  opts.load();
+  // option "ad_have_trajectory": dev->pfplsl / pfplsn already hold the trajectory of these inputs
+  ADOpts opt{0.0, 0, nullptr, g.work.d(), ncp, 1, opts.ad_have_trajectory};
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
   CK(csc2_launch_ad(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
-  g.launches += 2;      // forward (NL + check-points) and reverse sweep
+  g.launches += opt.have_traj ? 1 : 2;      // forward (NL + check-points) and reverse sweep
   return 0;
 }
 
@@ -871,10 +875,12 @@ int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
   TLOpts topt{0.01, 1, nullptr, n1, ncp};
   CK(csc2_launch_tl(kc, geo, in, out, din, dout, topt, s));
   // AD applied to y with zero-initialised input adjoints; N2 = <0.01 x, M'^T y> (:198-256)
-  ADOpts aopt{0.01, 1, n2, ckpt, ncp, 1};
+  // the TL launch above has just written the trajectory outputs of these very inputs (cloudsc2tl.F90:
+  // 1079-1111), so the adjoint restarts from PFPLSL5 / PFPLSN5 and needs no forward sweep of its own
+  ADOpts aopt{0.01, 1, n2, ckpt, ncp, 1, 1};
   CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
   CK(csc2_launch_ad_finalize(geo, n1, n2, d_norms, d_z, s));
-  g.launches += 4;      // TL, AD forward, AD reverse, finalize
+  g.launches += 3;      // TL, AD reverse sweep, finalize
   double hz;
   CK(cudaMemcpyAsync(&hz, d_z, sizeof(double), cudaMemcpyDeviceToHost, s));
   if (norms_col)

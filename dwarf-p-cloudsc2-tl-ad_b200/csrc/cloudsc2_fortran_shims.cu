@@ -201,7 +201,7 @@ static void tlad(bool is_ad, const int *kidia, const int *kfdia, const int *klon
   dout.pcovptot = m.inout(pcovptot, n2);
   Geom g{*klon, *klev, *kfdia, 1};
   if (is_ad) {
-    ADOpts opt{0.0, 0, nullptr, m.next, (long long)ncp, 1};
+    ADOpts opt{0.0, 0, nullptr, m.next, (long long)ncp, 1, 0};
     CKA(csc2_launch_ad(kc, g, in, out, din, dout, opt, s));
     csc2_shim_count_launch();      // forward + reverse sweep = two launches
   } else {

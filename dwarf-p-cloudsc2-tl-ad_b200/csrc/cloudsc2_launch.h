@@ -51,6 +51,9 @@ struct ADOpts {
   double *ckpt;
   long long ncol_pad;
   int write_traj;          // write the trajectory outputs (PTENT5...) like the reference (:842-864)
+  int have_traj;           // the trajectory fluxes PFPLSL5/PFPLSN5 in `out` are already those of `in`
+                           // (a CLOUDSC2 / CLOUDSC2TL call on the same inputs ran before, as in the
+                           // adjoint test and in any 4D-Var inner loop): skip the forward sweep
 };
 cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            const IncIn &din, const IncOut &dout, const ADOpts &opt, cudaStream_t s);

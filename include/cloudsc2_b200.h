@@ -213,6 +213,11 @@ int cloudsc2_gpu_host_free(void *ptr);
  *                                      PCOVPTOT, TENDENCY_LOC%CLD(:,:,NCLV) (identically zero) and
  *                                      PFHPSL/PFHPSN (= -PFPLSL*RLVTT, -PFPLSN*RLSTT) back over PCIe
  *                                      but fills them on the host, bit-identically; 0: copy all
+ *   "ad_have_trajectory"               1: cloudsc2_gpu_ad_dev trusts that dev->pfplsl / dev->pfplsn
+ *                                      already hold the trajectory fluxes of the same inputs (a
+ *                                      cloudsc2_gpu_nl_dev / _tl_dev call ran before, as in every
+ *                                      4D-Var inner loop) and skips its forward sweep; 0 (default):
+ *                                      CLOUDSC2AD as written, trajectory recomputed (cloudsc2ad.F90:364-866)
  *   "nl_variant"   (CSC2_NL_VARIANT)   launch shape of the NL kernel (csrc/cloudsc2_nl_kernel.cu)
  * Nothing like this exists in the reference (its only knobs are NUMOMP and NPROMA). */
 int cloudsc2_gpu_set_option(const char *name, int value);

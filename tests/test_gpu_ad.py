@@ -124,3 +124,53 @@ def test_adjoint_test_other_blockings(pkg, src100, nproma, ngptot, lregcl):
     # cyclic expansion: column g behaves exactly like column g mod 100
     if ngptot > 100:
         assert np.array_equal(nc[100:200], nc[:100])
+
+
+def test_ad_with_precomputed_trajectory_equals_as_written(pkg, src100):
+    """Option ad_have_trajectory: when CLOUDSC2 (or CLOUDSC2TL) has already run on the same inputs,
+    cloudsc2_gpu_ad_dev restarts from the trajectory fluxes PFPLSL5 / PFPLSN5 it finds in the state
+    and skips its own forward sweep.  Input adjoints must be bit-identical to the as-written path
+    (trajectory recomputed inside the call, cloudsc2ad.F90:364-866)."""
+    prm = pkg.default_params(lregcl=True)
+    nproma, ngptot = 64, 500
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    nb = st.nblocks
+    rng = np.random.default_rng(3)
+    _, seed = pkg.driver.alloc_increments(nb, 137, nproma)
+    for k in seed:
+        seed[k][...] = rng.standard_normal(seed[k].shape) * 1e-4
+
+    def run(gpu, have_traj):
+        ds = pkg.DeviceState(gpu, st)
+        ds.zero()
+        adj, _ = pkg.driver.alloc_increments(nb, 137, nproma)
+        d_in = {k: gpu.malloc(v.nbytes) for k, v in adj.items()}
+        d_out = {k: gpu.malloc(v.nbytes) for k, v in seed.items()}
+        try:
+            for k, v in adj.items():
+                gpu.h2d(d_in[k], v)
+            for k, v in seed.items():
+                gpu.h2d(d_out[k], v)
+            if have_traj:
+                gpu.nl_dev(ds, st.ptsphy)                 # the trajectory run that precedes the adjoint
+                gpu.set_option("ad_have_trajectory", 1)
+            before = gpu.launch_count()
+            gpu.ad_dev(ds, st.ptsphy, d_in, d_out)
+            gpu.sync()
+            launches = gpu.launch_count() - before
+            for k, v in adj.items():
+                gpu.d2h(v, d_in[k])
+        finally:
+            gpu.set_option("ad_have_trajectory", 0)
+            for p in list(d_in.values()) + list(d_out.values()):
+                gpu.free(p)
+            ds.free()
+        return adj, launches
+
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        ref, n_ref = run(gpu, False)
+        got, n_got = run(gpu, True)
+    assert (n_ref, n_got) == (2, 1)                       # forward + reverse  vs  reverse only
+    for k in ref:
+        assert np.array_equal(ref[k], got[k]), k
+        assert np.abs(ref[k]).max() > 0 or k == "psupsat", k
