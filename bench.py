@@ -47,10 +47,11 @@ AD_BYTES_PER_COL = 10564 * 8                                                    
 TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
 # DRAM traffic per column measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch
 # over 163 840 columns, profiles/r1_{nl,tl,ad}_ncu.md) and FP64-pipe utilisation of the same capture
-NCU = {"nl": {"dram_bytes_per_column": 4.739e9 / 163840, "fp64_pipe_pct": 58.3, "profile": "profiles/r1_nl_ncu.md"},
-       "tl": {"dram_bytes_per_column": 9.237e9 / 163840, "fp64_pipe_pct": 56.9, "profile": "profiles/r1_tl_ncu.md"},
-       # AD = forward sweep (NL kernel + flux check-points, ~5.1 GB) + reverse sweep kernel (12.107 GB)
-       "ad": {"dram_bytes_per_column": (12.107e9 + 4.739e9 + 0.36e9) / 163840, "fp64_pipe_pct": 43.9,
+NCU = {"nl": {"dram_bytes_per_column": 4.741e9 / 163840, "fp64_pipe_pct": 58.2, "profile": "profiles/r1_nl_ncu.md"},
+       "tl": {"dram_bytes_per_column": 9.236e9 / 163840, "fp64_pipe_pct": 56.9, "profile": "profiles/r1_tl_ncu.md"},
+       # AD = forward sweep (the NL kernel, 4.74 GB; its flux outputs are the check-points) + reverse sweep
+       # kernel (12.108 GB)
+       "ad": {"dram_bytes_per_column": (12.108e9 + 4.741e9) / 163840, "fp64_pipe_pct": 43.3,
               "profile": "profiles/r1_ad_ncu.md"}}
 METRIC = "NL columns/s (KLEV=137)"
 UNIT = "columns/s"
