@@ -174,3 +174,41 @@ def test_ad_with_precomputed_trajectory_equals_as_written(pkg, src100):
     for k in ref:
         assert np.array_equal(ref[k], got[k]), k
         assert np.abs(ref[k]).max() > 0 or k == "psupsat", k
+
+
+def test_ad_kernel_is_the_transpose_of_the_reference_derivative(pkg, golden):
+    """<D, y> = <dx, M'^T y> with D = central finite differences of the REFERENCE'S Python NL kernel
+    along dx = 0.01 x (tests/golden/tl_fd_pyref.npz) and M'^T y from the CUDA adjoint, called like
+    CALL CLOUDSC2AD (per-block Fortran-ABI entry, PQS5 supplied): pins the GPU adjoint against
+    reference code, not only against our own TL."""
+    from pathlib import Path
+    import ctypes as C
+    fd = np.load(Path(__file__).resolve().parent / "golden" / "tl_fd_pyref.npz")
+    lib = pkg.load_library()
+    x5 = {k[3:]: np.ascontiguousarray(golden[k]) for k in golden.files if k.startswith("in_")}
+    x5["pqs"] = np.ascontiguousarray(golden["pqs"])
+    klev, klon = x5["ptm1"].shape
+    half = lambda n: klev + (1 if n == "paphp1" or n.startswith("pf") else 0)
+    out10 = ("ptent", "ptenq", "ptenl", "pteni", "pclc", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "pcovptot")
+    order26 = ("paphp1", "papp1", "pqm1", "pqs", "ptm1", "pl", "pi", "plude", "plu", "pmfu", "pmfd",
+               "ptent", "pgtent", "ptenq", "pgtenq", "ptenl", "pgtenl", "pteni", "pgteni", "psupsat",
+               "pclc", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "pcovptot")
+    rng = np.random.default_rng(17)
+    y = {n: np.ascontiguousarray(rng.uniform(0.5, 1.5, fd["d_" + n].shape) / max(np.abs(fd["d_" + n]).max(), 1e-30))
+         for n in out10}
+    lhs = sum(float((fd["d_" + n] * y[n]).sum()) for n in out10)
+    traj = {**x5, **{n: np.zeros((half(n), klon)) for n in out10}}
+    incr = {**{k: np.zeros_like(v) for k, v in x5.items()}, **{n: v.copy() for n, v in y.items()}}
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ref = lambda v: C.byref(C.c_int(v))
+    ptsphy = float(golden["ptsphy"])
+    with pkg.Cloudsc2(pkg.default_params(lregcl=False), klev, golden["ceta"]) as gpu:
+        gpu._bind()
+        lib.cloudsc2ad_(ref(1), ref(klon), ref(klon), ref(1), ref(klev), ref(0), C.byref(C.c_double(ptsphy)),
+                        *[dp(traj[n]) for n in order26], *[dp(incr[n]) for n in order26])
+    # PSUPSAT' is ASSIGNED PTSPHY*ZQP1' by the reference (cloudsc2ad.F90:1733): undo the extra PTSPHY
+    rhs = sum(float((0.01 * x5[k] * incr[k]).sum()) for k in x5 if k != "psupsat")
+    rhs += float((0.01 * x5["psupsat"] * incr["psupsat"]).sum()) / ptsphy
+    assert abs(lhs) > 1.0 and abs(lhs - rhs) <= 1e-6 * abs(lhs), (lhs, rhs)
+    for n in out10:
+        assert not incr[n].any(), n                      # output adjoints consumed and zeroed

@@ -129,3 +129,36 @@ def test_taylor_test_blocked(pkg, ob, src100, gpu_nl, nproma, ngptot):
     lam = 10.0 ** -np.arange(1, 11)
     tol = 1e-8 * np.maximum(1.0, np.abs(rbo)) + 1e-12 / lam * np.maximum(1.0, np.abs(rbo))
     assert (np.abs(rb - rbo) <= tol).all()
+
+
+def test_tl_kernel_matches_finite_differences_of_reference_python_kernel(pkg, golden):
+    """GPU CLOUDSC2TL (with PQS5 / PQS' supplied, CLOUDSC2TL-call semantics) against the central
+    finite differences of the reference's Python NL kernel (tests/golden/tl_fd_pyref.npz)."""
+    from pathlib import Path
+    import ctypes as C
+    fd = np.load(Path(__file__).resolve().parent / "golden" / "tl_fd_pyref.npz")
+    lib = pkg.load_library()
+    x5 = {k[3:]: np.ascontiguousarray(golden[k]) for k in golden.files if k.startswith("in_")}
+    x5["pqs"] = np.ascontiguousarray(golden["pqs"])
+    klev, klon = x5["ptm1"].shape
+    half = lambda n: klev + (1 if n == "paphp1" or n.startswith("pf") else 0)
+    out10 = ("ptent", "ptenq", "ptenl", "pteni", "pclc", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "pcovptot")
+    order26 = ("paphp1", "papp1", "pqm1", "pqs", "ptm1", "pl", "pi", "plude", "plu", "pmfu", "pmfd",
+               "ptent", "pgtent", "ptenq", "pgtenq", "ptenl", "pgtenl", "pteni", "pgteni", "psupsat",
+               "pclc", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "pcovptot")
+    traj = {**x5, **{n: np.zeros((half(n), klon)) for n in out10}}
+    incr = {**{k: 0.01 * v for k, v in x5.items()}, **{n: np.zeros((half(n), klon)) for n in out10}}
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ref = lambda v: C.byref(C.c_int(v))
+    src = pkg.synth_source(seed=0, klon=100, klev=klev)
+    with pkg.Cloudsc2(pkg.default_params(lregcl=False), klev, golden["ceta"]) as gpu:
+        gpu._bind()
+        # the per-block Fortran-ABI entry takes PQS5 and PQS' explicitly, like CALL CLOUDSC2TL
+        lib.cloudsc2tl_(ref(1), ref(klon), ref(klon), ref(1), ref(klev), ref(0),
+                        C.byref(C.c_double(float(golden["ptsphy"]))),
+                        *[dp(traj[n]) for n in order26], *[dp(incr[n]) for n in order26])
+    del src
+    for n in out10:
+        d = fd["d_" + n]
+        tol = (1e-6 if n == "pclc" else 1e-8) * max(np.abs(d).max(), 1e-300)
+        assert np.abs(incr[n] - d).max() <= tol, n
