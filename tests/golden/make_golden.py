@@ -40,9 +40,15 @@ def namespaces(prm, ceta):
 
 
 def main():
+    # usage: make_golden.py            -> nl_pyref.npz        (seed 0, inputs + outputs, 32 columns)
+    #        make_golden.py SEED       -> nl_pyref_seedN.npz  (outputs only, 48 columns; the inputs
+    #                                     are regenerated from the deterministic generator by the tests)
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     prm = pkg.default_params()
-    src100 = pkg.synth_source(seed=0, klon=100, klev=KLEV, params=prm)
+    src100 = pkg.synth_source(seed=seed, klon=100, klev=KLEV, params=prm)
     cols = sorted(set(list(range(0, 100, 3))[:NCOL - 2] + [98, 99]))[:NCOL]
+    if seed:
+        cols = list(range(1, 97, 2))
     src = src100.subset(cols)
     klon, klev = src.klon, src.klev
     yrmcst, yrethf, yrecldp, yrephli, yrecld = namespaces(prm, src.ceta)
@@ -76,12 +82,15 @@ def main():
         assert np.isfinite(v).all(), n
         print(f"  {n:9s} min {v.min(): .4e} max {v.max(): .4e} nonzero {np.count_nonzero(v)}")
     out = {"cols": np.asarray(cols), "ceta": src.ceta, "ptsphy": np.float64(src.ptsphy),
-           "pqs": pqs}
-    out.update({"in_" + k: v for k, v in x.items()})
+           "pqs": pqs, "seed": np.int64(seed)}
+    if seed == 0:
+        out.update({"in_" + k: v for k, v in x.items()})
+    else:
+        out["in_checksum"] = np.float64(sum(float(np.abs(v).sum()) for v in x.values()))
     out.update({"out_" + k: v for k, v in y.items()})
     out["params_names"] = np.asarray([n for n, _ in prm._fields_])
     out["params_values"] = np.asarray([float(getattr(prm, n)) for n, _ in prm._fields_])
-    dst = Path(__file__).with_name("nl_pyref.npz")
+    dst = Path(__file__).with_name("nl_pyref.npz" if seed == 0 else f"nl_pyref_seed{seed}.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, dst.stat().st_size, "bytes")
 

@@ -241,3 +241,21 @@ def test_nl_host_derived_outputs_equal_copied_outputs(pkg, src100, gpu_nl, nprom
     for n in a.a:
         assert np.array_equal(a.a[n], b.a[n]), n
         assert np.array_equal(np.signbit(a.a[n]), np.signbit(b.a[n])), n
+
+
+def test_nl_matches_reference_python_golden_second_atmosphere(pkg, gpu_nl):
+    """GPU (fused SATUR + CLOUDSC2) vs the reference's Python kernel on 48 columns of generator
+    seed 5 (tests/golden/nl_pyref_seed5.npz)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "nl_pyref_seed5.npz")
+    cols = list(g["cols"])
+    src = pkg.synth_source(seed=int(g["seed"]), klon=100, klev=137).subset(cols)
+    st = pkg.ArrayState(src, nproma=len(cols), ngptot=len(cols))
+    with pkg.Cloudsc2(pkg.default_params(lregcl=False), 137, src.ceta) as gpu:
+        gpu.nl(st)
+    o = st.outputs()
+    got = {"ptent": o["tend_loc_t"][0], "ptenq": o["tend_loc_q"][0], "ptenl": o["tend_loc_l"][0],
+           "pteni": o["tend_loc_i"][0], "pclc": o["pa"][0], "pfplsl": o["pfplsl"][0],
+           "pfplsn": o["pfplsn"][0], "pfhpsl": o["pfhpsl"][0], "pfhpsn": o["pfhpsn"][0],
+           "pcovptot": o["pcovptot"][0]}
+    _cmp(got, {n: g["out_" + n] for n in got})
