@@ -74,8 +74,8 @@ __device__ __forceinline__ LevIn scale_level(const LevIn &x, double f, bool zero
   return d;
 }
 
-template <bool ONFLY, int STAGES, bool RV, bool LREG>
-__global__ void __launch_bounds__(CSC2_TL_THREADS)
+template <bool ONFLY, int STAGES, bool RV, bool LREG, int MINB>
+__global__ void __launch_bounds__(CSC2_TL_THREADS, MINB)
 k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const TLOpts opt) {
   extern __shared__ double ring_all[];
@@ -295,12 +295,12 @@ k_taylor_finalize(const Geom g, const Lambdas lams, const double *__restrict__ t
 
 }  // namespace
 
-template <bool ONFLY, int STAGES, bool RV, bool LREG>
+template <bool ONFLY, int STAGES, bool RV, bool LREG, int MINB = 2>
 static cudaError_t launch_tl_k(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                                const IncIn &din, const IncOut &dout, const TLOpts &opt, int grid,
                                cudaStream_t s) {
   const size_t smem = (size_t)STAGES * TL_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG>;
+  auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG, MINB>;
   static int smem_ok_on_device = -1;
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   kern<<<grid, CSC2_TL_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
@@ -316,6 +316,11 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
     // RVTMP2 != 0 never happens in this dwarf: one shape only
     if (lreg) return launch_tl_k<ONFLY, 2, true, true>(c, g, in, out, din, dout, opt, grid, s);
     return launch_tl_k<ONFLY, 2, true, false>(c, g, in, out, din, dout, opt, grid, s);
+  }
+  static const int minb = [] { const char *e = getenv("CSC2_TL_MINB"); return e ? atoi(e) : 2; }();
+  if (minb == 3) {   // tuning knob: 3 CTAs/SM at 168 registers
+    if (lreg) return launch_tl_k<ONFLY, STAGES, false, true, 3>(c, g, in, out, din, dout, opt, grid, s);
+    return launch_tl_k<ONFLY, STAGES, false, false, 3>(c, g, in, out, din, dout, opt, grid, s);
   }
   if (lreg) return launch_tl_k<ONFLY, STAGES, false, true>(c, g, in, out, din, dout, opt, grid, s);
   return launch_tl_k<ONFLY, STAGES, false, false>(c, g, in, out, din, dout, opt, grid, s);
