@@ -105,7 +105,7 @@ __device__ __forceinline__ double satur_point(const KConst &c, double t, double 
   const double tm = t - c.rtt;
   const double el = csc2_exp(c.r3les * tm * csc2_rcp(t - c.r4les));
   const double ei = csc2_exp(c.r3ies * tm * csc2_rcp(t - c.r4ies));
-  const double foeew = c.r2es * (alfa * el + (1.0 - alfa) * ei);
+  const double foeew = c.r2es * fma(alfa, el - ei, ei);      // ALFA*EL+(1-ALFA)*EI
   const double qs = csc2_min_pos(foeew * pap_inv, CSC2_ZQMAX);
   return qs * csc2_rcp(1.0 - c.retv * qs);
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
   const double zfwat = cold ? 0.545 * tanh_p1 : 1.0;
   const double zfoeew = c.r2es * csc2_exp((cold ? c.r3ies * ri : c.r3les * rw) * (ztp1 - c.rtt));
   const double zfacw = c.r5les * (rw * rw), zfaci = c.r5ies * (ri * ri);
-  const double zfac = zfwat * zfacw + (1.0 - zfwat) * zfaci;
+  const double zfac = fma(zfwat, zfacw - zfaci, zfaci);     // ZFWAT*ZFACW+(1-ZFWAT)*ZFACI
   // ZCOR = 1/(1-RETV*ZESDP) with ZESDP = MIN(ZFOEEW/PAPP1, ZQMAX) shares the reciprocal of the
   // subsidence section: 1/(1-RETV*ZFOEEW/PAPP1) = PAPP1 * ZFAC2, ZFAC2 = 1/(PAPP1-RETV*ZFOEEW) (:451)
   const double zfac2 = csc2_rcp(x.pap - c.retv * zfoeew);
@@ -139,13 +139,13 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
   const double zlude = x.plude * dt * zgdp;
   {
     const bool llo1 = jk < c.klev - 1 && csc2_ge_pos(zlude, c.rlmin) && csc2_ge_pos(x.plu1, CSC2_ZEPS2);
-    const double e = csc2_expn(-zlude * csc2_rcp(llo1 ? x.plu1 : 1.0));
-    pclc = llo1 ? pclc + (1.0 - pclc) * (1.0 - e) : pclc;
+    const double e = csc2_pin(csc2_expn(-zlude * csc2_rcp(llo1 ? x.plu1 : 1.0)));   // unconditional
+    pclc = llo1 ? fma(pclc - 1.0, e, 1.0) : pclc;              // PCLC+(1-PCLC)*(1-EXP(..))
     zqc = llo1 ? zqc + zlude : zqc;
   }
 
   // compensating subsidence (:448-460)
-  const double zldcp = zfwat * zlvdcp + (1.0 - zfwat) * zlsdcp;
+  const double zldcp = fma(zfwat, zlvdcp - zlsdcp, zlsdcp);   // ZFWAT*ZLVDCP+(1-ZFWAT)*ZLSDCP
   {
     const double zfac1 = csc2_rcp(c.rd * ztp1);
     const double zrho = x.pap * zfac1;
@@ -160,7 +160,7 @@ __device__ __forceinline__ LevLocal nl_local(const KConst &c, const CritRH &crh,
 
   // new condensate and condensation rates (:464-469)
   double zqlwc = zqc * zfwat;
-  const double zqiwc = zqc * (1.0 - zfwat);
+  const double zqiwc = zqc - zqlwc;                            // ZQC*(1-ZFWAT)
   L.zcondl = (zqlwc - zl) * c.zqtmst;
   L.zcondi = (zqiwc - zi) * c.zqtmst;
 
