@@ -412,7 +412,15 @@ def main():
         zn, _ = pkg.sharded_adjoint(gpu_ad, src, nproma, 6400 * world, rank, world, device=dev)
         gpu_ad.close()
         gpu._bind()
+        # cost of the collective itself: MAX all-reduce of the ten Taylor norms, device tensor, 20 calls
+        torch.cuda.synchronize()
+        ta = time.perf_counter()
+        for _ in range(20):
+            pkg.allreduce_norms(z, "max", dev)
+        torch.cuda.synchronize()
+        allreduce_us = (time.perf_counter() - ta) / 20 * 1e6
         selftests = {"ngptot_total": 6400 * world, "taylor_penalty": pen, "taylor_passed": 0 <= pen <= 5,
+                     "allreduce_us_per_call": allreduce_us,
                      "taylor_ratios": [float(v) for v in z], "adjoint_znormg_eps": zn,
                      "adjoint_passed": bool(pkg.adjoint_verdict(zn)),
                      "allreduce": "nccl max over %d rank(s)" % world if world > 1 else "single rank",
