@@ -106,6 +106,8 @@ def _declare(lib):
         "cloudsc2_gpu_set_option": (i, [C.c_char_p, i]),
         "cloudsc2_gpu_satur": (i, [C.c_longlong, c_double_p, c_double_p, c_double_p]),
         "cloudsc2_gpu_validate_dev": (i, [vp, i, vp, i, i, i, i, C.c_longlong, c_double_p]),
+        "cloudsc2_gpu_validate_slabs_dev": (i, [vp, i, vp, i, i, i, C.c_longlong, i, C.c_longlong,
+                                                c_double_p]),
         # include/cloudsc2_host.h
         "cloudsc2_default_params": (None, [P]),
         "cloudsc2_source_synth": (i, [C.POINTER(Source), C.c_ulonglong, i, i, P]),
@@ -118,6 +120,10 @@ def _declare(lib):
                                                C.POINTER(i * 4), C.POINTER(i)]),
         "cloudsc2_h5_read_i4": (C.c_longlong, [C.c_char_p, C.c_char_p, C.POINTER(i),
                                                C.c_longlong]),
+        "cloudsc2_source_load_h5": (i, [C.POINTER(Source), P, C.c_char_p]),
+        "cloudsc2_reference_load_h5": (i, [vp, C.c_char_p]),
+        "cloudsc2_reference_free": (None, [vp]),
+        "cloudsc2_input_last_error": (C.c_char_p, []),
         "cloudsc2_validate_host": (None, [c_double_p, c_double_p, i, i, i, c_double_p]),
         "cloudsc2_error_rel": (d, [c_double_p, C.POINTER(i)]),
     }

@@ -405,21 +405,29 @@ int cloudsc2_gpu_satur(long long n, const double *pap, const double *pt, double 
   return 0;
 }
 
-int cloudsc2_gpu_validate_dev(const double *ref_src, int nlon, const double *field, int nproma,
-                              int nlev, int ndim, int ngptot, long long gcol0, double out[5]) {
+int cloudsc2_gpu_validate_slabs_dev(const double *ref_src, int nlon, const double *field, int nproma,
+                                    int nlev, int ndim, long long blk_stride, int ngptot,
+                                    long long gcol0, double out[5]) {
   if (int rc = require_init()) return rc;
   if (!ref_src || !field || !out) return fail(3, "NULL argument to cloudsc2_gpu_validate_dev");
-  if (nlon <= 0 || nproma <= 0 || nlev <= 0 || ndim <= 0 || ngptot <= 0 || gcol0 < 0)
+  if (nlon <= 0 || nproma <= 0 || nlev <= 0 || ndim <= 0 || ngptot <= 0 || gcol0 < 0 ||
+      blk_stride < (long long)nproma * nlev * ndim)
     return fail(3, "bad dimensions in cloudsc2_gpu_validate_dev");
   if (int rc = g.res.reserve(csc2_validate_scratch_bytes() + 8 * sizeof(double))) return rc;
   double *d_out = g.res.d();
   void *scratch = d_out + 8;
-  CK(csc2_launch_validate(ref_src, nlon, field, nproma, (long long)nlev * ndim, ngptot,
+  CK(csc2_launch_validate(ref_src, nlon, field, nproma, (long long)nlev * ndim, blk_stride, ngptot,
                           nblocks_of(ngptot, nproma), gcol0, scratch, d_out, g.stream));
   g.launches += 2;
   CK(cudaMemcpyAsync(out, d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   return 0;
+}
+
+int cloudsc2_gpu_validate_dev(const double *ref_src, int nlon, const double *field, int nproma,
+                              int nlev, int ndim, int ngptot, long long gcol0, double out[5]) {
+  return cloudsc2_gpu_validate_slabs_dev(ref_src, nlon, field, nproma, nlev, ndim,
+                                         (long long)nproma * nlev * ndim, ngptot, gcol0, out);
 }
 
 int cloudsc2_gpu_set_option(const char *name, int value) {

@@ -72,8 +72,8 @@ void csc2_set_nl_variant(int v);
 #define CSC2_VALIDATE_MAX_CTAS (148 * 8)
 size_t csc2_validate_scratch_bytes();
 cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *field, int nproma,
-                                 long long rows, int ngptot, int nblocks, long long gcol0,
-                                 void *scratch, double *out5, cudaStream_t s);
+                                 long long rows, long long blk_stride, int ngptot, int nblocks,
+                                 long long gcol0, void *scratch, double *out5, cudaStream_t s);
 
 // SATUR alone, elementwise over n points (device pointers).
 cudaError_t csc2_launch_satur(const KConst &c, const double *pap, const double *pt, double *pqsat,

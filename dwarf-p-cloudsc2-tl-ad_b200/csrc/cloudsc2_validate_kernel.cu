@@ -48,11 +48,13 @@ __device__ Stats block_fold(Stats s) {
   return s;
 }
 
-// field: (nproma, rows, nblocks) with rows = nlev*ndim ; ref_src: (nlon, rows)
+// field: (nproma, rows, nblocks) with rows = nlev*ndim, consecutive blocks blk_stride doubles apart
+// (= nproma*rows for a plain array; larger for a slab range of an AOSOA buffer such as
+// TENDENCY_LOC%T = B_LOC(:,:,1,:), cloudsc2_array_state_mod.F90:248-251); ref_src: (nlon, rows)
 __global__ void __launch_bounds__(256)
 k_validate_partial(const double *__restrict__ ref_src, int nlon, const double *__restrict__ field,
-                   int nproma, long long rows, int ngptot, long long gcol0, long long total,
-                   Stats *__restrict__ partial) {
+                   int nproma, long long rows, long long blk_stride, int ngptot, long long gcol0,
+                   long long total, Stats *__restrict__ partial) {
   Stats s = identity();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -61,7 +63,7 @@ k_validate_partial(const double *__restrict__ ref_src, int nlon, const double *_
     const long long r = t % rows;
     const long long b = t / rows;
     const long long col = b * nproma + jl;
-    const double v = __ldcs(field + idx);
+    const double v = __ldcs(field + b * blk_stride + r * nproma + jl);
     s.vmin = fmin(s.vmin, v);
     s.vmax = fmax(s.vmax, v);
     if (col < ngptot) {
@@ -91,13 +93,13 @@ k_validate_final(const Stats *__restrict__ partial, int n, double *__restrict__ 
 size_t csc2_validate_scratch_bytes() { return (size_t)CSC2_VALIDATE_MAX_CTAS * sizeof(Stats); }
 
 cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *field, int nproma,
-                                 long long rows, int ngptot, int nblocks, long long gcol0,
-                                 void *scratch, double *out5, cudaStream_t s) {
+                                 long long rows, long long blk_stride, int ngptot, int nblocks,
+                                 long long gcol0, void *scratch, double *out5, cudaStream_t s) {
   const long long total = (long long)nproma * rows * nblocks;
   long long ctas = (total + 255) / 256;
   if (ctas > CSC2_VALIDATE_MAX_CTAS) ctas = CSC2_VALIDATE_MAX_CTAS;
   if (ctas < 1) ctas = 1;
-  k_validate_partial<<<(int)ctas, 256, 0, s>>>(ref_src, nlon, field, nproma, rows, ngptot, gcol0,
+  k_validate_partial<<<(int)ctas, 256, 0, s>>>(ref_src, nlon, field, nproma, rows, blk_stride, ngptot, gcol0,
                                                total, static_cast<Stats *>(scratch));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -304,13 +304,17 @@ class Cloudsc2:
                                                            nproma, ngptot, gcol0, stream))
 
     def validate_dev(self, ref_src_ptr: int, nlon: int, field_ptr: int, nproma: int, nlev: int,
-                     ndim: int, ngptot: int, gcol0: int = 0) -> np.ndarray:
-        """validate_mod.F90:165-261 on the device -> [min, max, max|err|, sum|err|, sum|ref|]."""
+                     ndim: int, ngptot: int, gcol0: int = 0, blk_stride: int | None = None) -> np.ndarray:
+        """validate_mod.F90:165-261 on the device -> [min, max, max|err|, sum|err|, sum|ref|].
+        blk_stride (doubles between blocks) selects a slab range of an AOSOA buffer, e.g.
+        TENDENCY_LOC%T = B_LOC(:,:,1,:) with blk_stride = 8*NPROMA*KLEV."""
         self._bind()
         out = np.zeros(5)
-        self._check(self.lib.cloudsc2_gpu_validate_dev(ref_src_ptr, nlon, field_ptr, nproma, nlev,
-                                                       ndim, ngptot, gcol0,
-                                                       out.ctypes.data_as(_abi.c_double_p)))
+        if blk_stride is None:
+            blk_stride = nproma * nlev * ndim
+        self._check(self.lib.cloudsc2_gpu_validate_slabs_dev(ref_src_ptr, nlon, field_ptr, nproma, nlev,
+                                                             ndim, blk_stride, ngptot, gcol0,
+                                                             out.ctypes.data_as(_abi.c_double_p)))
         return out
 
     def satur(self, pap: np.ndarray, pt: np.ndarray) -> np.ndarray:

@@ -62,6 +62,33 @@ def synth_source(seed: int = 0, klon: int = 100, klev: int = 137,
     return out
 
 
+def _source_from_struct(s: "_abi.Source") -> SourceColumns:
+    klon, klev = int(s.klon), int(s.klev)
+
+    def arr(ptr, shape):
+        return np.ctypeslib.as_array(ptr, shape=shape).copy()
+    f = {n: arr(getattr(s, n), (klev, klon)) for n in SRC_2D}
+    f["paph"] = arr(s.paph, (klev + 1, klon))
+    f["pclv"] = arr(s.pclv, (_abi.NCLV, klev, klon))
+    f["tend_cml"] = arr(s.tend_cml, (_abi.NSTATE, klev, klon))
+    return SourceColumns(klon, klev, float(s.ptsphy), arr(s.ceta, (klev,)), f)
+
+
+def load_source_h5(path) -> tuple[SourceColumns, _abi.Params]:
+    """CLOUDSC2_ARRAY_STATE%LOAD's reads of input.h5 (cloudsc2_array_state_mod.F90:153-203):
+    the un-expanded columns, PTSPHY and the constants that reach the kernels.  Raises on a
+    missing dataset (the reference aborts)."""
+    lib = _abi.load_library()
+    s, p = _abi.Source(), _abi.Params()
+    rc = lib.cloudsc2_source_load_h5(C.byref(s), C.byref(p), str(path).encode())
+    if rc:
+        raise KeyError(f"{path}: {lib.cloudsc2_input_last_error().decode()} (rc={rc})")
+    try:
+        return _source_from_struct(s), p
+    finally:
+        lib.cloudsc2_source_free(C.byref(s))
+
+
 def nblocks(ngptot: int, nproma: int) -> int:
     return ngptot // nproma + min(ngptot % nproma, 1)
 

@@ -184,6 +184,13 @@ int cloudsc2_gpu_expand_shard_dev(const double *src, int nlon, int nlev, int ndi
  * CLOUDSC_MPI_REDUCE_MIN/MAX/SUM, :197-199). Synchronous. */
 int cloudsc2_gpu_validate_dev(const double *ref_src, int nlon, const double *field, int nproma,
                               int nlev, int ndim, int ngptot, long long gcol0, double out[5]);
+/* Same for a slab range of an AOSOA buffer: `field` points at the first wanted slab of block 0 and
+ * consecutive blocks are blk_stride doubles apart -- TENDENCY_LOC%T/%A/%Q/%CLD are
+ * B_LOC(:,:,1,:), (:,:,2,:), (:,:,3,:), (:,:,4:,:) with blk_stride = 8*NPROMA*KLEV
+ * (cloudsc2_array_state_mod.F90:248-251). */
+int cloudsc2_gpu_validate_slabs_dev(const double *ref_src, int nlon, const double *field, int nproma,
+                                    int nlev, int ndim, long long blk_stride, int ngptot,
+                                    long long gcol0, double out[5]);
 
 /* ---- device memory helpers for non-torch hosts ------------------------------------------ */
 int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes);

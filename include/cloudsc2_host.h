@@ -68,6 +68,24 @@ long long cloudsc2_h5_read_f8(const char *path, const char *dataset, double *out
 long long cloudsc2_h5_read_i4(const char *path, const char *dataset, int *out,
                               long long max_elems);
 
+/* CLOUDSC2_ARRAY_STATE%LOAD's reads of input.h5 (cloudsc2_array_state_mod.F90:153-203): KLON, KLEV,
+ * the 100-column fields, PTSPHY and the constants of YOMCST / YOETHF / YRECLDP / YREPHLI that reach
+ * the kernels, through the mini reader above.  A missing dataset is an error
+ * (the reference aborts).  Switches in *p are set as the NL program sets them; RVTMP2 = 0 because
+ * the reference never loads it (yoethf.F90:30 vs :79-99).  0 = ok. */
+int cloudsc2_source_load_h5(cloudsc2_source *s, cloudsc2_params *p, const char *path);
+/* The un-expanded columns of reference.h5 that VALIDATE compares with
+ * (cloudsc2_array_state_mod.F90:225-233); tend_loc is (KLON,KLEV,8): slabs T,A,Q,CLD(5). */
+typedef struct cloudsc2_reference {
+  int klon, klev;
+  double *plude, *pcovptot, *pfplsl, *pfplsn, *pfhpsl, *pfhpsn; /* fluxes: klev+1 */
+  double *tend_loc;
+} cloudsc2_reference;
+int cloudsc2_reference_load_h5(cloudsc2_reference *r, const char *path);
+void cloudsc2_reference_free(cloudsc2_reference *r);
+/* Text of the last error of the two loaders (thread-local). */
+const char *cloudsc2_input_last_error(void);
+
 /* Validation statistics of one field, common/module/validate_mod.F90:165-211,263-296
  * (L1 sense): out[0]=min(field) out[1]=max(field) out[2]=max|err| out[3]=sum|err|
  * out[4]=sum|ref| ; relative error % as the reference prints it = see cloudsc2_error_rel. */

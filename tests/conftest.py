@@ -25,6 +25,7 @@ def built():
     """Make sure the native artefacts exist (no-op when they are up to date)."""
     import __graft_entry__ as ge
     ge.build_product()
+    ge.build_programs()
     ge.build_oracle()
     return ge
 

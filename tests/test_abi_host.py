@@ -133,67 +133,7 @@ def test_verdicts(pkg):
 
 # ---- mini HDF5 reader -------------------------------------------------------------------------
 
-def _tiny_h5(path, datasets):
-    """Write a superblock-v0 HDF5 file with contiguous datasets in the root group, byte by byte
-    (same on-disk structures as config-files/reference.h5: TREE/HEAP/SNOD, v1 object headers)."""
-    names = sorted(datasets)
-    heap_data = b"\0" * 8
-    name_off = {}
-    for n in names:
-        name_off[n] = len(heap_data)
-        s = n.encode() + b"\0"
-        heap_data += s + b"\0" * (-len(s) % 8)
-    heap_data += b"\0" * 32
-    UNDEF = 0xFFFFFFFFFFFFFFFF
-    pos = 96                      # after superblock (56 bytes + 40-byte root entry)
-    root_ohdr = pos; pos += 16 + 24
-    btree = pos; pos += 24 + 8 * (2 * 16 + 1) + 8 * 2 * 16
-    heap = pos; pos += 32
-    heap_data_addr = pos; pos += len(heap_data)
-    snod = pos; pos += 8 + 40 * 32
-    ohdrs, raws = {}, {}
-    for n in names:
-        ohdrs[n] = pos; pos += 16 + 256
-    for n in names:
-        raws[n] = pos; pos += datasets[n].nbytes + (-datasets[n].nbytes % 8)
-    eof = pos
-    b = bytearray(eof)
-    b[0:8] = b"\x89HDF\r\n\x1a\n"
-    b[8:16] = bytes([0, 0, 0, 0, 0, 8, 8, 0])
-    b[16:24] = struct.pack("<HHI", 16, 16, 0)
-    b[24:56] = struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
-    b[56:96] = struct.pack("<QQII", 0, root_ohdr, 1, 0) + struct.pack("<QQ", btree, heap)
-    # root object header: one symbol-table message
-    b[root_ohdr:root_ohdr + 16] = struct.pack("<BBHII", 1, 0, 1, 1, 24) + b"\0" * 4
-    b[root_ohdr + 16:root_ohdr + 40] = struct.pack("<HHBBBB", 0x11, 16, 0, 0, 0, 0) + struct.pack("<QQ", btree, heap)
-    b[btree:btree + 24] = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF)
-    b[btree + 24:btree + 48] = struct.pack("<QQQ", 0, snod, name_off[names[-1]])
-    b[heap:heap + 32] = b"HEAP" + struct.pack("<BBBBQQQ", 0, 0, 0, 0, len(heap_data), len(heap_data) - 32, heap_data_addr)
-    b[heap_data_addr:heap_data_addr + len(heap_data)] = heap_data
-    b[snod:snod + 8] = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
-    for k, n in enumerate(names):
-        e = snod + 8 + 40 * k
-        b[e:e + 40] = struct.pack("<QQII", name_off[n], ohdrs[n], 0, 0) + b"\0" * 16
-    for n in names:
-        a = datasets[n]
-        msgs = b""
-        dims = b"".join(struct.pack("<Q", d) for d in a.shape)
-        body = struct.pack("<BBBB", 1, a.ndim, 0, 0) + b"\0" * 4 + dims
-        msgs += struct.pack("<HHBBBB", 1, len(body), 0, 0, 0, 0) + body
-        if a.dtype == np.float64:
-            body = struct.pack("<BBBBI", 0x11, 0x20, 0x3f, 0, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
-        else:
-            body = struct.pack("<BBBBI", 0x10, 0x08, 0, 0, 4) + struct.pack("<HH", 0, 32)
-        body += b"\0" * (-len(body) % 8)
-        msgs += struct.pack("<HHBBBB", 3, len(body), 1, 0, 0, 0) + body
-        body = struct.pack("<BB", 3, 1) + struct.pack("<QQ", raws[n], a.nbytes)
-        body += b"\0" * (-len(body) % 8)
-        msgs += struct.pack("<HHBBBB", 8, len(body), 0, 0, 0, 0) + body
-        o = ohdrs[n]
-        b[o:o + 16] = struct.pack("<BBHII", 1, 0, 3, 1, len(msgs)) + b"\0" * 4
-        b[o + 16:o + 16 + len(msgs)] = msgs
-        b[raws[n]:raws[n] + a.nbytes] = a.tobytes()
-    Path(path).write_bytes(bytes(b))
+from tests.h5writer import write_h5 as _tiny_h5  # noqa: E402
 
 
 def test_mini_hdf5_reader_roundtrip(pkg, tmp_path):

@@ -1,0 +1,210 @@
+"""The three dwarf programs (host/dwarf_cloudsc2.cc, the C++ mirror of PROGRAM DWARF_CLOUDSC) and the
+input.h5 / reference.h5 loaders behind them.
+
+CPU part: loaders against files written by tests/h5writer.py, command-line handling, loud failure
+without a GPU.  GPU part: BASELINE configs 1-3 run as the reference's own command lines
+(README.md:49-61: `dwarf-cloudsc2-nl 4 160000 32`, `dwarf-cloudsc2-tl 1 100 1`,
+`dwarf-cloudsc2-ad 1 100 100`) and checked through what the programs print.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests.h5writer import PARAM_DATASETS, input_h5_datasets, write_h5
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _run(built, prog, *args, env=None, cwd=None):
+    exe = ROOT / "dwarf-p-cloudsc2-tl-ad_b200" / "bin" / prog
+    assert exe.exists(), exe
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([str(exe), *map(str, args)], capture_output=True, text=True, env=e, cwd=cwd,
+                          timeout=600)
+
+
+# ---- CPU: loaders -------------------------------------------------------------------------------
+
+def test_input_h5_loader_roundtrip(pkg, tmp_path):
+    src = pkg.synth_source(seed=3, klon=7, klev=12)
+    prm = pkg.default_params()
+    prm.rclcrit, prm.rtice, prm.rlptrc = 3.0e-4, 250.16, 266.0      # not the defaults
+    path = tmp_path / "input.h5"
+    d = input_h5_datasets(src, prm)
+    assert len(d) > 32                                               # several symbol-table nodes
+    write_h5(path, d)
+    got, gp = pkg.load_source_h5(path)
+    assert (got.klon, got.klev, got.ptsphy) == (7, 12, src.ptsphy)
+    for n, a in src.f.items():
+        assert np.array_equal(got.f[n], a), n
+    assert np.array_equal(got.ceta, src.ceta)                        # dwarf_cloudsc.F90:100-102
+    for member in PARAM_DATASETS.values():
+        assert getattr(gp, member) == getattr(prm, member), member
+    assert gp.rvtmp2 == 0.0 and gp.lphylin == 1 and gp.levapls2 == 0
+    # a missing dataset is an error naming it (the reference aborts in LOAD_ARRAY)
+    del d["PMFD"]
+    write_h5(path, d)
+    with pytest.raises(KeyError, match="PMFD"):
+        pkg.load_source_h5(path)
+    # a mis-shaped one too
+    d["PMFD"] = np.zeros((3, 3))
+    write_h5(path, d)
+    with pytest.raises(KeyError, match="PMFD"):
+        pkg.load_source_h5(path)
+    with pytest.raises(KeyError):
+        pkg.load_source_h5(tmp_path / "absent.h5")
+
+
+class _Reference(C.Structure):
+    _fields_ = [("klon", C.c_int), ("klev", C.c_int)] + [
+        (n, C.POINTER(C.c_double)) for n in ("plude", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn",
+                                             "tend_loc")]
+
+
+def test_reference_h5_loader(pkg, tmp_path):
+    rng = np.random.default_rng(11)
+    klon, klev = 5, 9
+    d = {"KLON": np.array([klon], dtype=np.int32), "KLEV": np.array([klev], dtype=np.int32)}
+    for n in ("PLUDE", "PCOVPTOT", "TENDENCY_LOC_T", "TENDENCY_LOC_A", "TENDENCY_LOC_Q"):
+        d[n] = rng.standard_normal((klev, klon))
+    for n in ("PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN"):
+        d[n] = rng.standard_normal((klev + 1, klon))
+    d["TENDENCY_LOC_CLD"] = rng.standard_normal((5, klev, klon))
+    path = tmp_path / "reference.h5"
+    write_h5(path, d)
+    lib = pkg.load_library()
+    r = _Reference()
+    assert lib.cloudsc2_reference_load_h5(C.byref(r), str(path).encode()) == 0
+    try:
+        assert (r.klon, r.klev) == (klon, klev)
+        n = klon * klev
+        assert np.array_equal(np.ctypeslib.as_array(r.pfplsn, shape=(klev + 1, klon)), d["PFPLSN"])
+        tl = np.ctypeslib.as_array(r.tend_loc, shape=(8, klev, klon))
+        assert np.array_equal(tl[0], d["TENDENCY_LOC_T"]) and np.array_equal(tl[1], d["TENDENCY_LOC_A"])
+        assert np.array_equal(tl[2], d["TENDENCY_LOC_Q"]) and np.array_equal(tl[3:], d["TENDENCY_LOC_CLD"])
+        assert n > 0
+    finally:
+        lib.cloudsc2_reference_free(C.byref(r))
+    ref = Path("/root/reference/config-files/reference.h5")           # build container only
+    if ref.exists():
+        assert lib.cloudsc2_reference_load_h5(C.byref(r), str(ref).encode()) == 0
+        assert (r.klon, r.klev) == (100, 137)
+        lib.cloudsc2_reference_free(C.byref(r))
+
+
+# ---- CPU: command line ----------------------------------------------------------------------------
+
+def test_programs_command_line(built, pkg):
+    for prog in ("dwarf-cloudsc2-nl", "dwarf-cloudsc2-tl", "dwarf-cloudsc2-ad"):
+        r = _run(built, prog, "--help")
+        assert r.returncode == 0 and "NUMOMP" in r.stdout
+        r = _run(built, prog, "1", "abc")                             # READ(CLARG,*) would abort
+        assert r.returncode == 1 and "ABOR1" in r.stderr and "NGPTOT" in r.stderr
+    if not pkg.gpu_available():
+        r = _run(built, "dwarf-cloudsc2-nl", "4", "1600", "32")
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr   # never computes on the host
+
+
+# ---- GPU: the BASELINE command lines ----------------------------------------------------------------
+
+_ERR_LINE = re.compile(r"^ (\S+)\s+(\d)D(\d)((?:\s+-?[0-9.]+E[+-]\d+){5})(\s+!!!!)?\s*$")
+
+
+def _validation_lines(stdout):
+    out = {}
+    for line in stdout.splitlines():
+        m = _ERR_LINE.match(line)
+        if m:
+            out[m.group(1)] = ([float(x) for x in m.group(4).split()], m.group(5) is not None)
+    return out
+
+
+@pytest.mark.gpu
+def test_dwarf_nl_baseline_config(built, pkg):
+    """dwarf-cloudsc2-nl 4 160000 32 (BASELINE config 1 / README.md:49)."""
+    r = _run(built, "dwarf-cloudsc2-nl", 4, 160000, 32, env={"CLOUDSC2_REPEAT": "3"})
+    assert r.returncode == 0, r.stderr
+    assert "NUMPROC=1, NUMOMP=4, NGPTOTG=160000, NPROMA=32, NGPBLKS=5000" in r.stderr
+    tot = [l for l in r.stderr.splitlines() if l.rstrip().endswith(": TOTAL")]
+    assert len(tot) == 1
+    nums = tot[0].replace("x", " ").replace(":", " ").split()
+    assert nums[:6] == ["1", "4", "160000", "160000", "5000", "32"]
+    v = _validation_lines(r.stdout)
+    want = ["PLUDE", "PCOVPTOT", "PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN", "TENDENCY_LOC%A",
+            "TENDENCY_LOC%Q", "TENDENCY_LOC%T", "TENDENCY_LOC%CLD"]
+    assert list(v) == want                                            # the reference's order (:239-251)
+    for name, (nums5, warn) in v.items():
+        assert not warn and nums5[2] == 0.0 and nums5[4] == 0.0, (name, nums5)   # bit-identical to 1 block
+    assert v["PFPLSN"][0][1] > 0 and v["TENDENCY_LOC%T"][0][1] > 0    # and not trivially zero
+    m = re.search(r"GPU: ([0-9.]+) ms per driver call", r.stderr)
+    assert m and float(m.group(1)) < 50.0
+
+
+@pytest.mark.gpu
+def test_dwarf_tl_baseline_config(built, pkg, ob, src100):
+    """dwarf-cloudsc2-tl 1 100 1 (BASELINE config 2): same ratios as the oracle's driver, TEST PASSED."""
+    r = _run(built, "dwarf-cloudsc2-tl", 1, 100, 1)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "TEST PASSED, penalty" in r.stdout
+    rows = re.findall(r"^\s+(\d+)\s+([0-9.]+)\s*$", r.stdout, flags=re.M)
+    assert [int(a) for a, _ in rows] == list(range(1, 11))
+    z_gpu = np.array([float(b) for _, b in rows])
+    prm = pkg.default_params(lregcl=False)
+    st = pkg.ArrayState(src100, nproma=1, ngptot=100)
+    z_cpu, _, _ = ob.driver_tl(prm, src100.ceta, st)
+    # lambda = 10^-1 .. 10^-5: deterministic to many digits; beyond that cancellation-dominated
+    assert np.allclose(z_gpu[:5], np.asarray(z_cpu)[:5], rtol=1e-6, atol=0)
+    assert pkg.taylor_verdict(z_gpu)[0] == pkg.taylor_verdict(z_cpu)[0]
+
+
+@pytest.mark.gpu
+def test_dwarf_ad_baseline_config(built, pkg):
+    """dwarf-cloudsc2-ad 1 100 100 (BASELINE config 3)."""
+    r = _run(built, "dwarf-cloudsc2-ad", 1, 100, 100)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "=           TEST OK         =" in r.stdout
+    m = re.search(r"The maximum error is\s+([0-9.]+)\s+times the zero of the machine", r.stdout)
+    assert m and float(m.group(1)) < 10000.0
+
+
+@pytest.mark.gpu
+def test_dwarf_nl_from_input_h5_and_host_arrays(built, pkg, src100, tmp_path):
+    """An input.h5 holding the synthetic columns gives the same results as the built-in generator;
+    a reference.h5 made from the un-expanded GPU results validates to zero error; the host-array path
+    (what the unchanged Fortran host would call) prints the same validation table."""
+    prm = pkg.default_params(lregcl=False)
+    write_h5(tmp_path / "input.h5", input_h5_datasets(src100, prm))
+    st = pkg.ArrayState(src100, nproma=100, ngptot=100)
+    with pkg.Cloudsc2(prm, src100.klev, src100.ceta) as gpu:
+        gpu.nl(st)
+    o = st.outputs()
+    loc = st.a["b_loc"][0]                                            # (8, KLEV, 100)
+    ref = {"KLON": np.array([100], dtype=np.int32), "KLEV": np.array([137], dtype=np.int32),
+           "PLUDE": src100.f["plude"], "PCOVPTOT": o["pcovptot"][0], "PFPLSL": o["pfplsl"][0],
+           "PFPLSN": o["pfplsn"][0], "PFHPSL": o["pfhpsl"][0], "PFHPSN": o["pfhpsn"][0],
+           "TENDENCY_LOC_T": loc[0], "TENDENCY_LOC_A": loc[1], "TENDENCY_LOC_Q": loc[2],
+           "TENDENCY_LOC_CLD": loc[3:]}
+    write_h5(tmp_path / "reference.h5", {k: np.ascontiguousarray(v) for k, v in ref.items()})
+    outs = []
+    for env in ({}, {"CLOUDSC2_HOST_ARRAYS": "1"}):
+        r = _run(built, "dwarf-cloudsc2-nl", 2, 4000, 64, env=env, cwd=tmp_path)   # picks up ./input.h5, ./reference.h5
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "input: input.h5 (KLON=100, KLEV=137)" in r.stdout and "reference: reference.h5" in r.stdout
+        v = _validation_lines(r.stdout)
+        assert len(v) == 10
+        for name, (nums5, warn) in v.items():
+            assert not warn and nums5[2] == 0.0, (name, nums5)
+        outs.append(v)
+    assert outs[0] == outs[1]
+    # a perturbed reference is flagged with the reference's own "!!!!" marker
+    ref["PFPLSN"] = ref["PFPLSN"] * (1.0 + 1e-9)
+    write_h5(tmp_path / "reference.h5", {k: np.ascontiguousarray(v) for k, v in ref.items()})
+    r = _run(built, "dwarf-cloudsc2-nl", 1, 1000, 32, cwd=tmp_path)
+    v = _validation_lines(r.stdout)
+    assert v["PFPLSN"][1] and not v["PFPLSL"][1]
