@@ -144,6 +144,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ngptot-per-gpu", type=int, default=163840)
+    ap.add_argument("--ngptot-total", type=int, default=0,
+                    help="strong scaling: fixed total NGPTOT block-sharded over the ranks "
+                         "(BASELINE config 5: 1310720 .. 5242880); overrides --ngptot-per-gpu")
     ap.add_argument("--nproma", type=int, default=128)
     ap.add_argument("--modes", default="nl,tl,ad")
     ap.add_argument("--no-e2e", action="store_true")
@@ -162,13 +165,18 @@ def main():
     pkg = importlib.import_module("dwarf-p-cloudsc2-tl-ad_b200")
     prm = pkg.default_params(lregcl=False)
     src = pkg.synth_source(seed=0, klon=100, klev=KLEV)
-    nproma, ngp = args.nproma, args.ngptot_per_gpu
+    nproma = args.nproma
+    strong = args.ngptot_total > 0
+    ngp_total = args.ngptot_total if strong else args.ngptot_per_gpu * args.gpus
+    # this rank's shard: contiguous block range, same arithmetic as dwarf_cloudsc.F90:65-69
+    ngp = pkg.shard_blocks(ngp_total, nproma, rank if world == args.gpus else 0, args.gpus).ngptot
+    scaling = "strong" if strong else "weak"
     config = {"workload": f"CLOUDSC2 NL (SATUR+CLOUDSC2), KLEV={KLEV}, NPROMA={nproma}, "
-                          f"NGPTOT={ngp} per GPU x {args.gpus} GPU(s) = {ngp * args.gpus}, "
+                          f"NGPTOT={ngp} per GPU x {args.gpus} GPU(s) = {ngp_total}, "
                           "100 synthetic source columns (seed 0) expanded on device",
-              "klev": KLEV, "nproma": nproma, "ngptot_per_gpu": ngp, "ngptot_total": ngp * args.gpus,
+              "klev": KLEV, "nproma": nproma, "ngptot_per_gpu": ngp, "ngptot_total": ngp_total,
               "parallelism": f"block-sharded x{args.gpus}, no data-path collective",
-              "l2": "inputs (2.7 GB per GPU) larger than L2; no flush needed"}
+              "l2": f"inputs ({ngp * 16448 / 1e9:.1f} GB per GPU) larger than L2; no flush needed"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -188,7 +196,7 @@ def main():
         val = sample / (ms * 1e-3)
         line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": f"{sample} of the {ngp} columns per step (NPROMA={nproma}), "
@@ -230,7 +238,7 @@ def main():
         return float(t.item())
 
     gpu = pkg.Cloudsc2(prm, KLEV, src.ceta, device=local_rank)
-    sh = pkg.shard_blocks(ngp * world, nproma, rank, world)
+    sh = pkg.shard_blocks(ngp_total, nproma, rank, world)
     assert sh.ngptot == ngp
     # a non-default torch stream: the kernels are launched on it through the ABI's `stream`
     # argument, and torch.cuda.Event records on it (events only see torch's current stream)
@@ -268,7 +276,7 @@ def main():
     ms_nl = timed(lambda: gpu.nl_dev(ds, src.ptsphy, stream=stream), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     launches = gpu.launch_count() - l0 - args.warmup
-    value = ngp * world / (ms_nl * 1e-3)
+    value = ngp_total / (ms_nl * 1e-3)
     nl_gbs = NL_BYTES_PER_COL * ngp / (ms_nl * 1e-3) / 1e9
     def ncu_part(mode, ms):
         n = NCU[mode]
@@ -305,7 +313,7 @@ def main():
             ms_tl = timed(lambda: gpu.tl_dev(ds, src.ptsphy, din, dout, stream=stream),
                           max(3, args.steps // 2), 3)
             gbs = TL_BYTES_PER_COL * ngp / (ms_tl * 1e-3) / 1e9
-            results["tl"] = {"columns_per_s": ngp * world / (ms_tl * 1e-3), "ms_per_step": ms_tl,
+            results["tl"] = {"columns_per_s": ngp_total / (ms_tl * 1e-3), "ms_per_step": ms_tl,
                              "gbs_per_gpu": gbs, "frac_of_hbm": gbs / peak,
                              "bytes_per_column": TL_BYTES_PER_COL,
                              "note": "CLOUDSC2TL as written: 16+16 arrays in, 10+10 out",
@@ -319,7 +327,7 @@ def main():
                 ms_ad = timed(lambda: gpu.ad_dev(ds, src.ptsphy, din, dout, stream=stream),
                               max(3, args.steps // 2), 3)
                 gbs = AD_BYTES_PER_COL * ngp / (ms_ad * 1e-3) / 1e9
-                results["ad"] = {"columns_per_s": ngp * world / (ms_ad * 1e-3), "ms_per_step": ms_ad,
+                results["ad"] = {"columns_per_s": ngp_total / (ms_ad * 1e-3), "ms_per_step": ms_ad,
                                  "gbs_per_gpu": gbs, "frac_of_hbm": gbs / peak,
                                  "bytes_per_column": AD_BYTES_PER_COL,
                                  "note": "CLOUDSC2AD as written: traj in/out, adjoints RMW",
@@ -337,7 +345,7 @@ def main():
                     gpu.set_option("ad_have_trajectory", 0)
                 gbs2 = 9464 * 8 * ngp / (ms_ad2 * 1e-3) / 1e9
                 results["ad_have_trajectory"] = {
-                    "columns_per_s": ngp * world / (ms_ad2 * 1e-3), "ms_per_step": ms_ad2, "gbs_per_gpu": gbs2,
+                    "columns_per_s": ngp_total / (ms_ad2 * 1e-3), "ms_per_step": ms_ad2, "gbs_per_gpu": gbs2,
                     "frac_of_hbm": gbs2 / peak, "bytes_per_column": 9464 * 8,
                     "note": "reverse sweep only (option ad_have_trajectory): trajectory fluxes taken from a "
                             "preceding NL/TL call on the same inputs"}
@@ -387,7 +395,7 @@ def main():
         t_e2e = (time.perf_counter() - t0) / args.e2e_steps
         barrier()
         t_e2e = max_over_ranks(t_e2e)
-        e2e = {"value": ngp * world / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+        e2e = {"value": ngp_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e,
                "api": "cloudsc2_gpu_nl (host arrays in the reference layout, page-locked memory from "
                       "cloudsc2_gpu_host_alloc)",
@@ -455,7 +463,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_nl, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "impl": "b200",
                 "roofline": {"bound": "hbm", "achieved": nl_gbs, "peak": peak, "unit": "GB/s",
                              "frac": nl_gbs / peak,
@@ -469,7 +477,7 @@ def main():
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
                 "modes": results, "nproma_sweep_ngptot160000": sweep, "selftests": selftests}
         # the reference's own report lines (timer_mod.F90:114-174), on stderr
-        sys.stderr.write(pkg.report.performance_table(1, ngp * world, ds.nblocks * world, nproma,
+        sys.stderr.write(pkg.report.performance_table(1, ngp_total, pkg.nblocks(ngp_total, nproma), nproma,
                                                       ms_nl * 1e-3, numproc=world) + "\n")
         print(json.dumps(line))
     ds.free()

@@ -77,6 +77,7 @@ def _declare(lib):
         "cloudsc2_gpu_finalize": (i, []),
         "cloudsc2_gpu_last_error": (C.c_char_p, []),
         "cloudsc2_gpu_available": (i, []),
+        "cloudsc2_gpu_device_count": (i, []),
         "cloudsc2_gpu_launch_count": (C.c_longlong, []),
         "cloudsc2_gpu_nl": (i, [i, i, i, d, F, c_double_p, c_double_p]),
         "cloudsc2_gpu_nl_dev": (i, [i, i, i, d, F, vp, vp]),

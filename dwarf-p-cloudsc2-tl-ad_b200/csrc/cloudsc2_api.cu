@@ -277,6 +277,13 @@ int cloudsc2_gpu_available(void) {
   return n > 0 ? 1 : 0;
 }
 
+int cloudsc2_gpu_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 long long cloudsc2_gpu_launch_count(void) { return g.launches; }
 
 int cloudsc2_gpu_init(const cloudsc2_params *params, int klev, const double *ceta, int device) {

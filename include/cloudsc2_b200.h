@@ -87,6 +87,9 @@ int cloudsc2_gpu_finalize(void);
 const char *cloudsc2_gpu_last_error(void);
 /* 1 if a usable CUDA device is visible, else 0 (never falls back to CPU). */
 int cloudsc2_gpu_available(void);
+/* Number of visible CUDA devices (0 without a GPU): what a multi-rank host uses to map rank -> device,
+ * like the reference maps MPI ranks to cores (cloudsc_mpi_mod.F90). */
+int cloudsc2_gpu_device_count(void);
 /* number of kernels launched by this library since init (bench.py: gpu_launches). */
 long long cloudsc2_gpu_launch_count(void);
 

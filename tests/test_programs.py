@@ -147,6 +147,32 @@ def test_dwarf_nl_baseline_config(built, pkg):
 
 
 @pytest.mark.gpu
+def test_dwarf_ranks_do_not_change_results(built, pkg):
+    """CLOUDSC2_NUMPROC=3 (three processes, sharing the GPU when the box has fewer): rank r expands from
+    its global column offset, so the validation table, the Taylor ratios' verdict and the adjoint norm
+    are those of the single-process run; the timer table has one TOTAL line per rank."""
+    one = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64)
+    three = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NUMPROC": "3"})
+    assert one.returncode == 0 and three.returncode == 0, three.stderr
+    assert "NUMPROC=3, NUMOMP=1, NGPTOTG=10000, NPROMA=64, NGPBLKS=53" in three.stderr   # 3334 columns on rank 0
+    ranks = [l for l in three.stderr.splitlines() if "TOTAL @ rank#" in l]
+    assert len(ranks) == 3 and [int(l.split()[1]) for l in ranks] == [3334, 3334, 3332]
+    grand = [l for l in three.stderr.splitlines() if l.rstrip().endswith(": TOTAL")][0].replace("x", " ").split()
+    assert grand[:4] == ["3", "1", "10000", "10000"]
+    v1, v3 = _validation_lines(one.stdout), _validation_lines(three.stdout)
+    assert list(v1) == list(v3) and len(v3) == 10
+    for name in v1:
+        assert v1[name][0][:3] == v3[name][0][:3] and v3[name][0][2] == 0.0 and not v3[name][1], name
+    a1 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50)
+    a2 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50, env={"CLOUDSC2_NUMPROC": "2"})
+    pat = r"The maximum error is\s+([0-9.]+)"
+    assert a1.returncode == 0 and a2.returncode == 0
+    assert float(re.search(pat, a1.stdout).group(1)) == float(re.search(pat, a2.stdout).group(1))
+    t2 = _run(built, "dwarf-cloudsc2-tl", 1, 200, 1, env={"CLOUDSC2_NUMPROC": "2"})
+    assert t2.returncode == 0 and "TEST PASSED" in t2.stdout
+
+
+@pytest.mark.gpu
 def test_dwarf_tl_baseline_config(built, pkg, ob, src100):
     """dwarf-cloudsc2-tl 1 100 1 (BASELINE config 2): same ratios as the oracle's driver, TEST PASSED."""
     r = _run(built, "dwarf-cloudsc2-tl", 1, 100, 1)
