@@ -181,18 +181,48 @@ struct Lambdas {
 // x5 = x + lambda * (x * 0.01)   (cloudsc_driver_tl_mod.F90:156-171, 200-215)
 __device__ __forceinline__ double pert(double x, double lam) { return x + lam * (x * 0.01); }
 
-__global__ void __launch_bounds__(CSC2_NL_THREADS)
+// Ring fields of the Taylor kernel: the 15 (+1) trajectory inputs, then the nine baseline outputs
+// F5 the differences are formed against.
+constexpr int TY_NF = CSC2_NTRAJ + 9;
+__device__ __forceinline__ void stage_base(double *d, const TrajOut &b, const ColOffsets &o, int jk,
+                                           int nproma) {
+  const size_t l = (size_t)jk * nproma;
+  csc2_cp_async8(d + 16 * NT, b.tent + o.oloc + l);
+  csc2_cp_async8(d + 17 * NT, b.tenq + o.oloc + l);
+  csc2_cp_async8(d + 18 * NT, b.tenl + o.oloc + l);
+  csc2_cp_async8(d + 19 * NT, b.teni + o.oloc + l);
+  csc2_cp_async8(d + 20 * NT, b.pclc + o.o1 + l);
+  csc2_cp_async8(d + 21 * NT, b.pfplsl + o.oh + l + nproma);
+  csc2_cp_async8(d + 22 * NT, b.pfplsn + o.oh + l + nproma);
+  csc2_cp_async8(d + 23 * NT, b.pfhpsl + o.oh + l + nproma);
+  csc2_cp_async8(d + 24 * NT, b.pfhpsn + o.oh + l + nproma);
+}
+
+// CTA order: lambda is the FASTEST index (blockIdx.x = column_cta * 10 + ilam), so the ten sweeps over
+// the same 128 columns are resident together and nine of them find the inputs and the baseline
+// outputs in L2 -- DRAM sees them once, not ten times.  Levels are staged one ahead in the same
+// shared-memory ring as the NL kernel.
+template <bool HAS_PQS, bool RV>
+__global__ void __maxnreg__(168)
 k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut base,
-            const Lambdas lams, double *__restrict__ diffsum, const long long ncol_pad) {
+            const __grid_constant__ Lambdas lams, double *__restrict__ diffsum, const long long ncol_pad) {
+  extern __shared__ double ring_all[];
+  double *ring = ring_all + threadIdx.x;
   csc2_math_init();
-  const int gcol = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cta = blockIdx.x / 10;
+  const int ilam = blockIdx.x - cta * 10;
+  const int gcol = cta * NT + threadIdx.x;
   const int ibl = gcol / g.nproma;
   if (ibl >= g.nblocks || gcol >= g.ngptot) return;
   const int jl = gcol - ibl * g.nproma;
   const int klev = g.klev, nproma = g.nproma;
-  const int ilam = blockIdx.y;
   const double lam = lams.v[ilam];
   const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, base.bs_loc);
+  constexpr int SLOT = TY_NF * NT;
+
+  csc2_stage_traj<NT, false, HAS_PQS ? 1 : 0>(ring, in, o, 0, klev, nproma);
+  stage_base(ring, base, o, 0, nproma);
+  csc2_cp_async_commit();
 
   // tropopause level of the PERTURBED state (the perturbed run is a plain CLOUDSC2 call)
   double ztrpaus = 0.1;
@@ -215,11 +245,18 @@ k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, con
   st.paph0 = pert(ldin(in.paph + o.oh), lam);
   st.rfl = 0.0; st.sfl = 0.0;
   double d_t = 0, d_q = 0, d_l = 0, d_i = 0, d_c = 0, d_fl = 0, d_fn = 0, d_hl = 0, d_hn = 0;
+  int slot = 0;
   for (int jk = 0; jk < klev; ++jk) {
-    LevIn x = load_level(in, o, jk, klev, nproma);
+    if (jk + 1 < klev) {
+      csc2_stage_traj<NT, false, HAS_PQS ? 1 : 0>(ring + (slot ^ 1) * SLOT, in, o, jk + 1, klev, nproma);
+      stage_base(ring + (slot ^ 1) * SLOT, base, o, jk + 1, nproma);
+    }
+    csc2_cp_async_commit();
+    csc2_cp_async_wait<1>();
+    const double *r = ring + slot * SLOT;
+    LevIn x = csc2_read_level<NT>(r, jk, klev);
     // PQS5 = ZQSAT + lambda*(0.01*ZQSAT) with ZQSAT = SATUR of the UNPERTURBED state (:135,:204)
-    const double qs = in.pqs ? ldin(in.pqs + o.o1 + (size_t)jk * nproma)
-                             : satur_point(c, x.pt, 1.0 / x.pap);
+    const double qs = HAS_PQS ? r[15 * NT] : satur_point(c, x.pt, csc2_rcp(x.pap));
     const double pqs5 = pert(qs, lam);
     x.paph1 = pert(x.paph1, lam); x.pap = pert(x.pap, lam); x.pt = pert(x.pt, lam);
     x.pq = pert(x.pq, lam); x.pl = pert(x.pl, lam); x.pi = pert(x.pi, lam);
@@ -227,18 +264,17 @@ k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, con
     x.pmfd = pert(x.pmfd, lam); x.gt = pert(x.gt, lam); x.gq = pert(x.gq, lam);
     x.gl = pert(x.gl, lam); x.gi = pert(x.gi, lam); x.psupsat = pert(x.psupsat, lam);
     LevOut y;
-    if (c.rvtmp2 != 0.0) nl_level<true>(c, crh, jk, x, pqs5, st, y);
-    else nl_level<false>(c, crh, jk, x, pqs5, st, y);
-    const size_t l = (size_t)jk * nproma;
-    d_t += ldin(base.tent + o.oloc + l) - y.tent;
-    d_q += ldin(base.tenq + o.oloc + l) - y.tenq;
-    d_l += ldin(base.tenl + o.oloc + l) - y.tenl;
-    d_i += ldin(base.teni + o.oloc + l) - y.teni;
-    d_c += ldin(base.pclc + o.o1 + l) - y.pclc;
-    d_fl += ldin(base.pfplsl + o.oh + l + nproma) - y.rfln;
-    d_fn += ldin(base.pfplsn + o.oh + l + nproma) - y.sfln;
-    d_hl += ldin(base.pfhpsl + o.oh + l + nproma) - (-y.rfln * c.rlvtt);
-    d_hn += ldin(base.pfhpsn + o.oh + l + nproma) - (-y.sfln * c.rlstt);
+    nl_level<RV>(c, crh, jk, x, pqs5, st, y);
+    d_t += r[16 * NT] - y.tent;
+    d_q += r[17 * NT] - y.tenq;
+    d_l += r[18 * NT] - y.tenl;
+    d_i += r[19 * NT] - y.teni;
+    d_c += r[20 * NT] - y.pclc;
+    d_fl += r[21 * NT] - y.rfln;
+    d_fn += r[22 * NT] - y.sfln;
+    d_hl += r[23 * NT] - (-y.rfln * c.rlvtt);
+    d_hn += r[24 * NT] - (-y.sfln * c.rlstt);
+    slot ^= 1;
   }
   double *d = diffsum + (size_t)ilam * 10 * ncol_pad + gcol;
   const long long n = ncol_pad;
@@ -348,13 +384,27 @@ static Lambdas make_lambdas() {
   return l;
 }
 
+template <bool HAS_PQS, bool RV>
+static cudaError_t launch_taylor_nl_k(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &base,
+                                      double *diffsum, long long ncol_pad, cudaStream_t s) {
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  const unsigned ncta = (unsigned)((ncol + NT - 1) / NT);
+  const size_t smem = (size_t)2 * TY_NF * NT * sizeof(double);
+  auto kern = k_taylor_nl<HAS_PQS, RV>;
+  static int smem_ok_on_device = -1;
+  if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
+  kern<<<ncta * 10u, NT, smem, s>>>(c, g, in, base, make_lambdas(), diffsum, ncol_pad);
+  return cudaGetLastError();
+}
+
 cudaError_t csc2_launch_taylor_nl(const KConst &c, const Geom &g, const TrajIn &in,
                                   const TrajOut &base, double *diffsum, long long ncol_pad,
                                   cudaStream_t s) {
-  const long long ncol = (long long)g.nblocks * g.nproma;
-  dim3 grid((unsigned)((ncol + CSC2_NL_THREADS - 1) / CSC2_NL_THREADS), 10, 1);
-  k_taylor_nl<<<grid, CSC2_NL_THREADS, 0, s>>>(c, g, in, base, make_lambdas(), diffsum, ncol_pad);
-  return cudaGetLastError();
+  if (c.rvtmp2 != 0.0)
+    return in.pqs ? launch_taylor_nl_k<true, true>(c, g, in, base, diffsum, ncol_pad, s)
+                  : launch_taylor_nl_k<false, true>(c, g, in, base, diffsum, ncol_pad, s);
+  return in.pqs ? launch_taylor_nl_k<true, false>(c, g, in, base, diffsum, ncol_pad, s)
+                : launch_taylor_nl_k<false, false>(c, g, in, base, diffsum, ncol_pad, s);
 }
 
 cudaError_t csc2_launch_taylor_finalize(const Geom &g, const double *tlsum, const double *diffsum,
