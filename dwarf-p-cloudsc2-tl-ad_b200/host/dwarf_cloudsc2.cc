@@ -467,10 +467,12 @@ int main(int argc, char **argv) {
   std::string exe = argv[0];
   int first = 1;
   if (argc > 1 && std::strncmp(argv[1], "--mode=", 7) == 0) { exe = std::string("-") + (argv[1] + 7); first = 2; }
-  if (exe.size() >= 3 && exe.compare(exe.size() - 3, 3, "-tl") == 0) o.mode = TL;
-  else if (exe.size() >= 3 && exe.compare(exe.size() - 3, 3, "-ad") == 0) o.mode = AD;
-  else if (exe.size() >= 3 && exe.compare(exe.size() - 3, 3, "-nl") == 0) o.mode = NL;
-  else abor1("program name must end in -nl, -tl or -ad (or pass --mode=nl|tl|ad first)");
+  const size_t slash = exe.find_last_of('/');
+  const std::string base = slash == std::string::npos ? exe : exe.substr(slash + 1);
+  if (base.find("-tl") != std::string::npos) o.mode = TL;
+  else if (base.find("-ad") != std::string::npos) o.mode = AD;
+  else if (base.find("-nl") != std::string::npos) o.mode = NL;
+  else abor1("program name must contain -nl, -tl or -ad (or pass --mode=nl|tl|ad first)");
   if (argc > first && (!std::strcmp(argv[first], "-h") || !std::strcmp(argv[first], "--help"))) {
     std::printf("usage: dwarf-cloudsc2-{nl|tl|ad} [NUMOMP [NGPTOT [NPROMA]]]\n"
                 "  defaults 1 16384 32 (dwarf_cloudsc.F90:27-29); NUMOMP is accepted and ignored\n"
