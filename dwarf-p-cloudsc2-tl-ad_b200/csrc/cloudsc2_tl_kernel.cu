@@ -202,6 +202,7 @@ __device__ __forceinline__ void stage_base(double *d, const TrajOut &b, const Co
 // the same 128 columns are resident together and nine of them find the inputs and the baseline
 // outputs in L2 -- DRAM sees them once, not ten times.  Levels are staged one ahead in the same
 // shared-memory ring as the NL kernel.
+// (168 registers = 3 CTAs/SM: at 128 the kernel spills and the ten sweeps take 8.7 instead of 8.3 ms)
 template <bool HAS_PQS, bool RV>
 __global__ void __maxnreg__(168)
 k_taylor_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut base,
