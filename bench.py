@@ -47,7 +47,7 @@ AD_BYTES_PER_COL = 10564 * 8                                                    
 TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
 # DRAM traffic per column measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch
 # over 163 840 columns, profiles/r1_{nl,tl,ad}_ncu.md) and FP64-pipe utilisation of the same capture
-NCU = {"nl": {"dram_bytes_per_column": 4.741e9 / 163840, "fp64_pipe_pct": 58.2, "profile": "profiles/r1_nl_ncu.md"},
+NCU = {"nl": {"dram_bytes_per_column": 4.739e9 / 163840, "fp64_pipe_pct": 60.5, "profile": "profiles/r1c_nl_ncu.md"},
        "tl": {"dram_bytes_per_column": 9.236e9 / 163840, "fp64_pipe_pct": 56.9, "profile": "profiles/r1_tl_ncu.md"},
        # AD = forward sweep (the NL kernel, 4.74 GB; its flux outputs are the check-points) + reverse sweep
        # kernel (12.108 GB)
@@ -469,7 +469,7 @@ def main():
                              "frac": nl_gbs / peak,
                              "traffic": NCU["nl"]["dram_bytes_per_column"] * ngp,
                              "traffic_note": "bytes per launch; ncu dram__bytes_read+write of one launch at "
-                                             "163 840 columns scaled by NGPTOT (profiles/r1_nl_ncu.md)",
+                                             "163 840 columns scaled by NGPTOT (profiles/r1c_nl_ncu.md)",
                              "peak_source": peak_src, "kernel": "k_cloudsc2_nl",
                              "algorithmic_bytes_per_column": NL_BYTES_PER_COL,
                              "algorithmic_bytes_per_launch": NL_BYTES_PER_COL * ngp,

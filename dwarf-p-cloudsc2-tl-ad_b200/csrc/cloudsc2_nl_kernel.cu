@@ -238,6 +238,9 @@ cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, con
     case 5: return launch_nl_variant<false, 2, 96, 112>(c, g, in, out, s);    // 18
     case 6: return launch_nl_variant<false, 2, 64, 112>(c, g, in, out, s);    // 18
     case 7: return launch_nl_variant<false, 2, 64, 104>(c, g, in, out, s);    // 18 (19 by regs)
+    case 8: return launch_nl_variant<false, 3, 128, 128>(c, g, in, out, s);   // 16, deeper ring
+    case 9: return launch_nl_variant<false, 2, 256, 128>(c, g, in, out, s);   // 16, 2 CTAs of 8 warps
+    case 10: return launch_nl_variant<false, 2, 64, 128>(c, g, in, out, s);   // 16, 8 CTAs of 2 warps
     case 11: return launch_nl_rv<false, 2, 128, 128, false, false, 1>(c, g, in, out, s);   // probes
     case 12: return launch_nl_rv<false, 2, 128, 128, false, false, 2>(c, g, in, out, s);
     case 13: return launch_nl_rv<false, 2, 128, 128, false, false, 3>(c, g, in, out, s);
