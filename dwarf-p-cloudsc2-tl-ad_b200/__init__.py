@@ -8,7 +8,7 @@ the library or a CUDA device is missing.
 """
 from ._abi import load_library, Params, Fields, IncrIn, IncrOut, NCLV, NSTATE, LIB_PATH
 from .state import (ArrayState, SourceColumns, default_params, expand, nblocks, synth_source,
-                    read_h5_f8, read_h5_i4, validate, load_source_h5)
+                    read_h5_f8, read_h5_i4, validate, load_source_h5, write_source_h5)
 from . import driver, pyapi, report, sharding
 from .sharding import (Shard, allreduce_norms, allreduce_validation, shard_blocks, sharded_adjoint,
                        sharded_taylor)
@@ -18,7 +18,7 @@ from .driver import (Cloudsc2, Cloudsc2Error, DeviceState, adjoint_verdict, gpu_
 __all__ = [
     "load_library", "Params", "Fields", "IncrIn", "IncrOut", "NCLV", "NSTATE", "LIB_PATH",
     "ArrayState", "SourceColumns", "default_params", "expand", "nblocks", "synth_source",
-    "read_h5_f8", "read_h5_i4", "validate", "load_source_h5",
+    "read_h5_f8", "read_h5_i4", "validate", "load_source_h5", "write_source_h5",
     "Cloudsc2", "Cloudsc2Error", "DeviceState", "adjoint_verdict", "gpu_available",
     "taylor_verdict", "driver", "sharding", "Shard", "allreduce_norms", "shard_blocks",
     "sharded_adjoint", "sharded_taylor", "allreduce_validation", "pyapi", "report",

@@ -125,6 +125,9 @@ def _declare(lib):
         "cloudsc2_reference_load_h5": (i, [vp, C.c_char_p]),
         "cloudsc2_reference_free": (None, [vp]),
         "cloudsc2_input_last_error": (C.c_char_p, []),
+        "cloudsc2_h5_write": (i, [C.c_char_p, vp, i]),
+        "cloudsc2_source_write_h5": (i, [C.POINTER(Source), P, C.c_char_p]),
+        "cloudsc2_reference_write_h5": (i, [vp, C.c_char_p]),
         "cloudsc2_validate_host": (None, [c_double_p, c_double_p, i, i, i, c_double_p]),
         "cloudsc2_error_rel": (d, [c_double_p, C.POINTER(i)]),
     }

@@ -20,6 +20,11 @@
 //   CLOUDSC2_INPUT      path of input.h5 (default ./input.h5 if it exists; else synthetic columns)
 //   CLOUDSC2_REFERENCE  path of reference.h5 for the NL validation (default ./reference.h5 if it
 //                       exists; else the un-expanded columns computed as one block are the reference)
+//   CLOUDSC2_WRITE_INPUT  path: write the columns and constants in use as an input.h5 (all datasets the
+//                       reference's loaders read) before running -- to run the reference's binaries
+//                       on the synthetic columns elsewhere
+//   CLOUDSC2_WRITE_REFERENCE  1: after the NL run write ./reference.h5 from block 1, like the reference
+//                       (dwarf_cloudsc.F90:124-126; needs NPROMA = KLON, cloudsc2_array_state_mod.F90:265-268)
 //   CLOUDSC2_SYNTH_SEED / CLOUDSC2_SYNTH_KLON / CLOUDSC2_SYNTH_KLEV   synthetic input (0 / 100 / 137)
 //   CLOUDSC2_DEVICE     CUDA device ordinal of rank 0 (0); rank r uses device (CLOUDSC2_DEVICE + r) mod #devices
 //   CLOUDSC2_REPEAT     timed repetitions of the driver call, best one reported (1)
@@ -301,6 +306,8 @@ RankResult run_rank(const Options &o, int rank) {
                   src.klon, src.klev, seed);
   }
   if (src.klev > 200) abor1("Dimension of ZPRES/ZPRESF is too short.");   // :88-91
+  if (const char *wi = std::getenv("CLOUDSC2_WRITE_INPUT"))
+    if (*wi && rank == 0 && cloudsc2_source_write_h5(&src, &prm, wi)) abor1(std::string("cannot write ") + wi);
   // dwarf_cloudsc.F90:105-107 and its twins: LEVAPLS2=.false., LPHYLIN=.true.; LREGCL per program
   prm.levapls2 = 0;
   prm.lphylin = 1;
@@ -382,6 +389,25 @@ RankResult run_rank(const Options &o, int rank) {
     V(8, ref.tend_loc + 0 * n, dev.b_loc.p + 0 * slab, klev, 1, bstride);
     V(9, ref.tend_loc + 3 * n, dev.b_loc.p + 3 * slab, klev, CLOUDSC2_NCLV, bstride);
     cloudsc2_reference_free(&ref);
+    // ---- GLOBAL_STATE%WRITE_REFERENCE, cloudsc2_array_state_mod.F90:260-287 --------------------------
+    if (env_int("CLOUDSC2_WRITE_REFERENCE", 0) == 1 && rank == 0) {
+      if (nproma != klon) abor1("[CLOUDSC2] Writing reference requires exactly NPROMA=KLON");   // :265-268
+      cloudsc2_reference out;
+      std::memset(&out, 0, sizeof out);
+      out.klon = klon; out.klev = klev;
+      auto fetch = [&](const double *d, size_t count) {
+        double *h = static_cast<double *>(std::malloc(count * sizeof(double)));
+        if (!h) abor1("out of memory");
+        ck(cloudsc2_gpu_memcpy_d2h(h, d, count * sizeof(double)), "cloudsc2_gpu_memcpy_d2h");
+        return h;
+      };
+      out.plude = fetch(dev.plude.p, n); out.pcovptot = fetch(dev.pcovptot.p, n);     // block 1 = first KLON columns
+      out.pfplsl = fetch(dev.pfplsl.p, n + klon); out.pfplsn = fetch(dev.pfplsn.p, n + klon);
+      out.pfhpsl = fetch(dev.pfhpsl.p, n + klon); out.pfhpsn = fetch(dev.pfhpsn.p, n + klon);
+      out.tend_loc = fetch(dev.b_loc.p, n * CLOUDSC2_NSTATE);
+      if (cloudsc2_reference_write_h5(&out, "reference.h5")) abor1("cannot write reference.h5");
+      cloudsc2_reference_free(&out);
+    }
   }
   dev.release();
   host.release();

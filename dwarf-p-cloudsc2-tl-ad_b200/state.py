@@ -89,6 +89,24 @@ def load_source_h5(path) -> tuple[SourceColumns, _abi.Params]:
         lib.cloudsc2_source_free(C.byref(s))
 
 
+def write_source_h5(src: SourceColumns, params: _abi.Params, path) -> None:
+    """Write `src` + `params` as an input.h5 with every dataset the reference's loaders read
+    (cloudsc2_source_write_h5): lets the reference's own binaries run on the synthetic columns."""
+    lib = _abi.load_library()
+    s = _abi.Source()
+    s.klon, s.klev, s.ptsphy = src.klon, src.klev, src.ptsphy
+    keep = []
+    for n in list(SRC_2D) + ["paph", "pclv", "tend_cml"]:
+        a = np.ascontiguousarray(src.f[n], dtype=np.float64)
+        keep.append(a)
+        setattr(s, n, a.ctypes.data_as(_abi.c_double_p))
+    ceta = np.ascontiguousarray(src.ceta, dtype=np.float64)
+    s.ceta = ceta.ctypes.data_as(_abi.c_double_p)
+    rc = lib.cloudsc2_source_write_h5(C.byref(s), C.byref(params), str(path).encode())
+    if rc:
+        raise OSError(f"cloudsc2_source_write_h5({path}) failed rc={rc}")
+
+
 def nblocks(ngptot: int, nproma: int) -> int:
     return ngptot // nproma + min(ngptot % nproma, 1)
 

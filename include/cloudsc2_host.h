@@ -68,6 +68,17 @@ long long cloudsc2_h5_read_f8(const char *path, const char *dataset, double *out
 long long cloudsc2_h5_read_i4(const char *path, const char *dataset, int *out,
                               long long max_elems);
 
+/* Minimal HDF5 writer, the counterpart of the reader: the same on-disk structures (superblock v0, root
+ * group, contiguous little-endian datasets); is_int 0 = f8, 1 = i4; dims in C order.  Replaces the
+ * host's writes through libhdf5 (hdf5_file_mod.F90 hdf5_file_write_*).  0 = ok. */
+typedef struct cloudsc2_h5_dataset {
+  const char *name;
+  int is_int, rank;
+  long long dims[4];
+  const void *data;
+} cloudsc2_h5_dataset;
+int cloudsc2_h5_write(const char *path, const cloudsc2_h5_dataset *ds, int n);
+
 /* CLOUDSC2_ARRAY_STATE%LOAD's reads of input.h5 (cloudsc2_array_state_mod.F90:153-203): KLON, KLEV,
  * the 100-column fields, PTSPHY and the constants of YOMCST / YOETHF / YRECLDP / YREPHLI that reach
  * the kernels, through the mini reader above.  A missing dataset is an error
@@ -83,6 +94,13 @@ typedef struct cloudsc2_reference {
 } cloudsc2_reference;
 int cloudsc2_reference_load_h5(cloudsc2_reference *r, const char *path);
 void cloudsc2_reference_free(cloudsc2_reference *r);
+/* Write an input.h5 holding `s` and `p`: every dataset CLOUDSC2_ARRAY_STATE%LOAD reads -- the fields and
+ * constants that reach the kernels with their values, all the other scalars the reference's loaders
+ * insist on (yoecldp.F90:244-369 etc.; unused by CLOUDSC2) as zeros -- so that the reference's own
+ * binaries can be run on the synthetic columns on a machine that has them.  And WRITE_REFERENCE
+ * (cloudsc2_array_state_mod.F90:260-287): the ten validated fields of the un-expanded columns. */
+int cloudsc2_source_write_h5(const cloudsc2_source *s, const cloudsc2_params *p, const char *path);
+int cloudsc2_reference_write_h5(const cloudsc2_reference *r, const char *path);
 /* Text of the last error of the two loaders (thread-local). */
 const char *cloudsc2_input_last_error(void);
 

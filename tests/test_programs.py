@@ -61,6 +61,29 @@ def test_input_h5_loader_roundtrip(pkg, tmp_path):
         pkg.load_source_h5(tmp_path / "absent.h5")
 
 
+def test_input_h5_writer_roundtrip(pkg, tmp_path):
+    """The library's own HDF5 writer (cloudsc2_source_write_h5): everything the reference's loaders read
+    is in the file, and what reaches the kernels reads back bit-identically."""
+    src = pkg.synth_source(seed=1, klon=9, klev=11)
+    prm = pkg.default_params()
+    path = tmp_path / "input.h5"
+    pkg.write_source_h5(src, prm, path)
+    got, gp = pkg.load_source_h5(path)
+    for n, a in src.f.items():
+        assert np.array_equal(got.f[n], a), n
+    for member in PARAM_DATASETS.values():
+        assert getattr(gp, member) == getattr(prm, member), member
+    assert got.ptsphy == src.ptsphy
+    # datasets CLOUDSC2 never uses but LOAD aborts without (yoecldp.F90:244-369, yoephli.F90:81-96, ...)
+    for name in ("YRECLDP_RAMID", "YRECLDP_RCL_FZRBB", "YREPHLI_RLPP00", "RKOOP2", "RV", "RALFDCP"):
+        assert pkg.read_h5_f8(path, name).size == 1, name
+    for name in ("YRECLDP_NBETA", "YREPHLI_LPHYLIN", "LDSLPHY", "LDMAINCALL", "YRECLDP_LAERICEAUTO"):
+        assert pkg.read_h5_i4(path, name).size == 1, name
+    assert pkg.read_h5_f8(path, "YRECLDP_RBETA").shape == (101,)
+    assert pkg.read_h5_i4(path, "YREPHLI_LPHYLIN")[0] == 1
+    assert np.isclose(pkg.read_h5_f8(path, "RV")[0], 461.5249933083879)
+
+
 class _Reference(C.Structure):
     _fields_ = [("klon", C.c_int), ("klev", C.c_int)] + [
         (n, C.POINTER(C.c_double)) for n in ("plude", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn",
@@ -89,6 +112,11 @@ def test_reference_h5_loader(pkg, tmp_path):
         assert np.array_equal(tl[0], d["TENDENCY_LOC_T"]) and np.array_equal(tl[1], d["TENDENCY_LOC_A"])
         assert np.array_equal(tl[2], d["TENDENCY_LOC_Q"]) and np.array_equal(tl[3:], d["TENDENCY_LOC_CLD"])
         assert n > 0
+        # and the writer (WRITE_REFERENCE) reproduces the file's content
+        assert lib.cloudsc2_reference_write_h5(C.byref(r), str(tmp_path / "again.h5").encode()) == 0
+        for n in d:
+            rd = pkg.read_h5_i4 if d[n].dtype == np.int32 else pkg.read_h5_f8
+            assert np.array_equal(rd(tmp_path / "again.h5", n), d[n]), n
     finally:
         lib.cloudsc2_reference_free(C.byref(r))
     ref = Path("/root/reference/config-files/reference.h5")           # build container only
@@ -234,3 +262,23 @@ def test_dwarf_nl_from_input_h5_and_host_arrays(built, pkg, src100, tmp_path):
     r = _run(built, "dwarf-cloudsc2-nl", 1, 1000, 32, cwd=tmp_path)
     v = _validation_lines(r.stdout)
     assert v["PFPLSN"][1] and not v["PFPLSL"][1]
+
+
+@pytest.mark.gpu
+def test_dwarf_write_input_and_reference(built, pkg, tmp_path):
+    """CLOUDSC2_WRITE_REFERENCE=1 (dwarf_cloudsc.F90:124-126: NPROMA must be KLON) and CLOUDSC2_WRITE_INPUT:
+    the files the program writes are the files it reads -- a later run at another NPROMA validates
+    against them with zero error."""
+    r = _run(built, "dwarf-cloudsc2-nl", 1, 100, 100, cwd=tmp_path,
+             env={"CLOUDSC2_WRITE_INPUT": "input.h5", "CLOUDSC2_WRITE_REFERENCE": "1"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "input.h5").exists() and (tmp_path / "reference.h5").exists()
+    assert pkg.read_h5_f8(tmp_path / "reference.h5", "PFPLSN").shape == (138, 100)
+    r = _run(built, "dwarf-cloudsc2-nl", 1, 100, 32, cwd=tmp_path, env={"CLOUDSC2_WRITE_REFERENCE": "1"})
+    assert r.returncode == 1 and "NPROMA=KLON" in r.stderr            # the reference's own refusal
+    r = _run(built, "dwarf-cloudsc2-nl", 2, 5000, 32, cwd=tmp_path)   # picks both files up
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "input: input.h5 (KLON=100, KLEV=137)" in r.stdout and "reference: reference.h5" in r.stdout
+    v = _validation_lines(r.stdout)
+    assert len(v) == 10 and all(nums5[2] == 0.0 and not warn for nums5, warn in v.values())
+    assert v["PFPLSL"][0][1] > 0
