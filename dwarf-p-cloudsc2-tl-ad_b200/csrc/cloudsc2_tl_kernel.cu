@@ -22,6 +22,7 @@ constexpr int NT = CSC2_TL_THREADS;
 constexpr int TL_NF = 32;
 
 // increments from arrays (all plain (NPROMA,KLEV[+1],NBLOCKS)) -> fields 16..31
+template <int NT>
 __device__ __forceinline__ void stage_incr(double *d, const IncIn &di, const ColOffsets &o, int jk,
                                            int klev, int nproma) {
   const size_t l = (size_t)jk * nproma;
@@ -74,8 +75,11 @@ __device__ __forceinline__ LevIn scale_level(const LevIn &x, double f, bool zero
   return d;
 }
 
-template <bool ONFLY, int STAGES, bool RV, bool LREG, int MINB>
-__global__ void __launch_bounds__(CSC2_TL_THREADS, MINB)
+// NT threads per CTA, MINB CTAs per SM -> register cap 65536 / (MINB * NT): 128 x 2 = 8 warps/SM at 255
+// registers is the default; 64 x 5 = 10 warps at 200 registers and 64 x 6 = 12 warps at 168 are tuning
+// variants.
+template <bool ONFLY, int STAGES, bool RV, bool LREG, int MINB, int NT>
+__global__ void __launch_bounds__(NT) __maxnreg__((65536 / (MINB * NT)) > 255 ? 255 : (65536 / (MINB * NT)) / 8 * 8)
 k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
               const IncIn din, const IncOut dout, const TLOpts opt) {
   extern __shared__ double ring_all[];
@@ -95,7 +99,7 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < klev) {
       csc2_stage_traj<NT, false>(ring + s * SLOT, in, o, s, klev, nproma);
-      if (!ONFLY) stage_incr(ring + s * SLOT, din, o, s, klev, nproma);
+      if (!ONFLY) stage_incr<NT>(ring + s * SLOT, din, o, s, klev, nproma);
     }
     csc2_cp_async_commit();
   }
@@ -122,7 +126,7 @@ k_cloudsc2_tl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     const int pf = jk + STAGES - 1;
     if (pf < klev) {
       csc2_stage_traj<NT, false>(ring + pslot * SLOT, in, o, pf, klev, nproma);
-      if (!ONFLY) stage_incr(ring + pslot * SLOT, din, o, pf, klev, nproma);
+      if (!ONFLY) stage_incr<NT>(ring + pslot * SLOT, din, o, pf, klev, nproma);
     }
     csc2_cp_async_commit();
     csc2_cp_async_wait<STAGES - 1>();
@@ -332,15 +336,17 @@ k_taylor_finalize(const Geom g, const Lambdas lams, const double *__restrict__ t
 
 }  // namespace
 
-template <bool ONFLY, int STAGES, bool RV, bool LREG, int MINB = 2>
+template <bool ONFLY, int STAGES, bool RV, bool LREG, int MINB = 2, int TNT = CSC2_TL_THREADS>
 static cudaError_t launch_tl_k(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
-                               const IncIn &din, const IncOut &dout, const TLOpts &opt, int grid,
+                               const IncIn &din, const IncOut &dout, const TLOpts &opt, int /*grid*/,
                                cudaStream_t s) {
-  const size_t smem = (size_t)STAGES * TL_NF * NT * sizeof(double);
-  auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG, MINB>;
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  const int grid = (int)((ncol + TNT - 1) / TNT);
+  const size_t smem = (size_t)STAGES * TL_NF * TNT * sizeof(double);
+  auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG, MINB, TNT>;
   static int smem_ok_on_device = -1;
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
-  kern<<<grid, CSC2_TL_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);
+  kern<<<grid, TNT, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
 }
 // dispatch on the two run-time switches that are compile-time in the kernel
@@ -355,6 +361,14 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
     return launch_tl_k<ONFLY, 2, true, false>(c, g, in, out, din, dout, opt, grid, s);
   }
   static const int minb = [] { const char *e = getenv("CSC2_TL_MINB"); return e ? atoi(e) : 2; }();
+  if (minb == 5 || minb == 6 || minb == 4) {   // tuning knobs: 64-thread CTAs, 4/5/6 per SM = 8/10/12 warps
+    if (minb == 4) return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 4, 64>(c, g, in, out, din, dout, opt, grid, s)
+                               : launch_tl_k<ONFLY, STAGES, false, false, 4, 64>(c, g, in, out, din, dout, opt, grid, s);
+    if (minb == 5) return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 5, 64>(c, g, in, out, din, dout, opt, grid, s)
+                               : launch_tl_k<ONFLY, STAGES, false, false, 5, 64>(c, g, in, out, din, dout, opt, grid, s);
+    return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 6, 64>(c, g, in, out, din, dout, opt, grid, s)
+                : launch_tl_k<ONFLY, STAGES, false, false, 6, 64>(c, g, in, out, din, dout, opt, grid, s);
+  }
   if (minb == 3) {   // tuning knob: 3 CTAs/SM at 168 registers
     if (lreg) return launch_tl_k<ONFLY, STAGES, false, true, 3>(c, g, in, out, din, dout, opt, grid, s);
     return launch_tl_k<ONFLY, STAGES, false, false, 3>(c, g, in, out, din, dout, opt, grid, s);
