@@ -571,7 +571,13 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
   // chunk's D2H has landed, overlapped with the transfers of the later chunks; that leaves the
   // H2D direction -- the bound of this call -- less disturbed by D2H traffic.
   const bool derive = opts.e2e_host_derive != 0;
-  std::vector<cudaEvent_t> k0(nchunks), k1(nchunks), dn(nchunks);
+  // per-chunk events; destroyed on every exit path (an error return must not leak them)
+  struct Events {
+    std::vector<cudaEvent_t> v;
+    explicit Events(size_t n) : v(n, nullptr) {}
+    ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    cudaEvent_t &operator[](size_t i) { return v[i]; }
+  } k0(nchunks), k1(nchunks), dn(nchunks);
   for (size_t i = 0; i < nchunks; ++i) {
     CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i]));
     CK(cudaEventCreateWithFlags(&dn[i], cudaEventDisableTiming));
@@ -675,9 +681,6 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, k0[i], k1[i]));
     kms += t;
-    cudaEventDestroy(k0[i]);
-    cudaEventDestroy(k1[i]);
-    cudaEventDestroy(dn[i]);
   }
   if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
   if (elapsed_kernel_s) *elapsed_kernel_s = kms * 1e-3;

@@ -241,6 +241,7 @@ cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, con
     case 8: return launch_nl_variant<false, 3, 128, 128>(c, g, in, out, s);   // 16, deeper ring
     case 9: return launch_nl_variant<false, 2, 256, 128>(c, g, in, out, s);   // 16, 2 CTAs of 8 warps
     case 10: return launch_nl_variant<false, 2, 64, 128>(c, g, in, out, s);   // 16, 8 CTAs of 2 warps
+    case 14: return launch_nl_variant<false, 2, 32, 128>(c, g, in, out, s);   // 16, 16 CTAs of 1 warp
     case 11: return launch_nl_rv<false, 2, 128, 128, false, false, 1>(c, g, in, out, s);   // probes
     case 12: return launch_nl_rv<false, 2, 128, 128, false, false, 2>(c, g, in, out, s);
     case 13: return launch_nl_rv<false, 2, 128, 128, false, false, 3>(c, g, in, out, s);

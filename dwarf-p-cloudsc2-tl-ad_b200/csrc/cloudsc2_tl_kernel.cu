@@ -361,6 +361,9 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
     return launch_tl_k<ONFLY, 2, true, false>(c, g, in, out, din, dout, opt, grid, s);
   }
   static const int minb = [] { const char *e = getenv("CSC2_TL_MINB"); return e ? atoi(e) : 2; }();
+  if (minb == 8)   // 32-thread CTAs, 8 per SM = 8 warps at 255 registers (finer tail)
+    return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 8, 32>(c, g, in, out, din, dout, opt, grid, s)
+                : launch_tl_k<ONFLY, STAGES, false, false, 8, 32>(c, g, in, out, din, dout, opt, grid, s);
   if (minb == 5 || minb == 6 || minb == 4) {   // tuning knobs: 64-thread CTAs, 4/5/6 per SM = 8/10/12 warps
     if (minb == 4) return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 4, 64>(c, g, in, out, din, dout, opt, grid, s)
                                : launch_tl_k<ONFLY, STAGES, false, false, 4, 64>(c, g, in, out, din, dout, opt, grid, s);

@@ -259,3 +259,35 @@ def test_nl_matches_reference_python_golden_second_atmosphere(pkg, gpu_nl):
            "pfplsn": o["pfplsn"][0], "pfhpsl": o["pfhpsl"][0], "pfhpsn": o["pfhpsn"][0],
            "pcovptot": o["pcovptot"][0]}
     _cmp(got, {n: g["out_" + n] for n in got})
+
+
+def test_nl_matches_reference_python_golden_edge_columns(pkg):
+    """GPU (fused SATUR + CLOUDSC2, KLEV = 60) vs the reference's Python kernel on the edge-case columns
+    of tests/golden/nl_pyref_edge.npz: temperatures exactly on RTT / RTICE / RLPTRC / RTT+2, dry and
+    supersaturated columns, PLU == ZEPS2, ... -- every branch decided on its boundary must fall on the
+    reference's side (the kernel's integer-pipe compares and shared reciprocals included)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "nl_pyref_edge.npz")
+    klev, klon = g["in_ptm1"].shape
+    src = pkg.synth_source(seed=int(g["seed"]), klon=klon, klev=klev)
+    f = src.f
+    f["pt"], f["pq"], f["pap"], f["paph"] = g["in_ptm1"], g["in_pqm1"], g["in_papp1"], g["in_paphp1"]
+    f["plu"], f["plude"], f["pmfu"], f["pmfd"] = g["in_plu"], g["in_plude"], g["in_pmfu"], g["in_pmfd"]
+    f["psupsat"] = g["in_psupsat"]
+    f["pclv"][0], f["pclv"][1] = g["in_pl"], g["in_pi"]
+    f["tend_cml"][0], f["tend_cml"][2] = g["in_pgtent"], g["in_pgtenq"]
+    f["tend_cml"][3], f["tend_cml"][4] = g["in_pgtenl"], g["in_pgteni"]
+    assert np.array_equal(src.ceta, g["ceta"])
+    for nproma in (klon, 7):
+        st = pkg.ArrayState(src, nproma=nproma, ngptot=klon)
+        with pkg.Cloudsc2(pkg.default_params(lregcl=False), klev, src.ceta) as gpu:
+            gpu.nl(st)
+        o = st.outputs()
+
+        def cols(a):      # (NB, KLEV[+1], NPROMA) -> (KLEV[+1], klon)
+            return np.concatenate([a[b] for b in range(a.shape[0])], axis=1)[:, :klon]
+        got = {"ptent": cols(o["tend_loc_t"]), "ptenq": cols(o["tend_loc_q"]), "ptenl": cols(o["tend_loc_l"]),
+               "pteni": cols(o["tend_loc_i"]), "pclc": cols(o["pa"]), "pfplsl": cols(o["pfplsl"]),
+               "pfplsn": cols(o["pfplsn"]), "pfhpsl": cols(o["pfhpsl"]), "pfhpsn": cols(o["pfhpsn"]),
+               "pcovptot": cols(o["pcovptot"])}
+        _cmp(got, {n: g["out_" + n] for n in got})

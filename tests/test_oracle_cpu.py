@@ -183,3 +183,26 @@ def test_cloudsc2_matches_reference_python_on_a_second_atmosphere(pkg, ob):
     for n in ob.OUT10:
         r = g["out_" + n]
         assert np.abs(y[n] - r).max() <= RTOL_PY * max(np.abs(r).max(), 1e-300), n
+
+
+def test_oracle_matches_reference_python_on_edge_columns(pkg, ob):
+    """tests/golden/nl_pyref_edge.npz (make_golden_edge.py): KLEV = 60, columns with the first-guess
+    temperature exactly ON the thresholds the scheme branches on (RTT, RTICE, RLPTRC, RTT+2), dry /
+    supersaturated / no-condensate / heavy-condensate columns, PLU == ZEPS2, no mass flux, PSUPSAT > 0,
+    very cold / very warm -- SATUR and CLOUDSC2 of the oracle against the reference's Python kernel."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "nl_pyref_edge.npz")
+    x = _inputs(g)
+    prm = pkg.default_params()
+    pqs = ob.satur(prm, x["papp1"], x["ptm1"])
+    assert np.abs(pqs / g["pqs"] - 1.0).max() < 1e-15 * 8
+    x["pqs"] = np.ascontiguousarray(g["pqs"])
+    y = ob.cloudsc2_block(prm, g["ceta"], float(g["ptsphy"]), x)
+    for n in ob.OUT10:
+        r = g["out_" + n]
+        scale = max(np.abs(r).max(), 1e-300)
+        assert np.abs(y[n] - r).max() <= RTOL_PY * scale, n
+    # the forced temperatures really sit on the thresholds
+    t1 = x["ptm1"] + float(g["ptsphy"]) * x["pgtent"]
+    assert (t1[:, 0] == prm.rtt).sum() >= 10 and (t1[:, 1] == prm.rtice).sum() >= 10
+    assert (t1[:, 3] == prm.rtt + 2.0).sum() >= 10 and (x["plu"][:, 9] == 1.0e-10).all()
