@@ -418,8 +418,26 @@ def main():
         pen, istart = pkg.taylor_verdict(z)
         gpu_ad = pkg.Cloudsc2(pkg.default_params(lregcl=True), KLEV, src.ceta, device=local_rank)
         zn, _ = pkg.sharded_adjoint(gpu_ad, src, nproma, 6400 * world, rank, world, device=dev)
+        # the reference's TL / AD PROGRAMS time their whole test loop (per block 1 NL + 1 TL + 10 perturbed
+        # NL, resp. 1 TL + 1 AD; cloudsc_driver_tl_mod.F90:126-254, cloudsc_driver_ad_mod.F90:108-271):
+        # the same loops as one library call each on this rank's device-resident columns
+        def host_timed(fn, n=3):
+            fn()
+            barrier()
+            t = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return max_over_ranks((time.perf_counter() - t) / n)
+        t_ad_drv = host_timed(lambda: gpu_ad.ad_test(ds, src.ptsphy))
         gpu_ad.close()
         gpu._bind()
+        t_tl_drv = host_timed(lambda: gpu.tl_taylor(ds, src.ptsphy))
+        results["tl_taylor_driver"] = {"columns_per_s": ngp_total / t_tl_drv, "ms_per_step": 1e3 * t_tl_drv,
+                                       "note": "dwarf-cloudsc2-tl's timed loop as one call: 1 NL + 1 TL + 10 perturbed "
+                                               "NL sweeps + ERROR_NORM, max over blocks"}
+        results["ad_test_driver"] = {"columns_per_s": ngp_total / t_ad_drv, "ms_per_step": 1e3 * t_ad_drv,
+                                     "note": "dwarf-cloudsc2-ad's timed loop as one call: 1 TL + 1 AD + dot products"}
         # cost of the collective itself: MAX all-reduce of the ten Taylor norms, device tensor, 20 calls
         torch.cuda.synchronize()
         ta = time.perf_counter()
@@ -457,6 +475,12 @@ def main():
             cpu["ad_columns_per_s"] = 16384 / min(ob.bench_tlad("ad", prm, src.ceta, st_c, numomp=threads)
                                                   for _ in range(2))
             cpu["tl_ad_sample"] = "16384 columns, best of 2, block loop only"
+            # the reference's TL / AD programs' own timed loops (Taylor test, adjoint test) on the CPU port
+            st_d = pkg.ArrayState(src, nproma, 4096)
+            cpu["tl_taylor_driver_columns_per_s"] = 4096 / ob.driver_tl(prm, src.ceta, st_d, numomp=threads)[2]
+            prm_ad = pkg.default_params(lregcl=True)
+            cpu["ad_test_driver_columns_per_s"] = 4096 / ob.driver_ad(prm_ad, src.ceta, st_d, numomp=threads)[2]
+            cpu["driver_sample"] = "4096 columns, one pass of CLOUDSC_DRIVER_TL / CLOUDSC_DRIVER_AD"
         except Exception as e:                      # never let the baseline leg kill the bench line
             cpu["tl_ad_error"] = str(e)
 
