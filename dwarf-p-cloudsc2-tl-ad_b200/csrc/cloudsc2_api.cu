@@ -167,9 +167,18 @@ int check_fields(const cloudsc2_fields *f) {
 struct DevProblem {
   cloudsc2_fields f;
   size_t n2b, n2hb;   // doubles per plain array / per half-level array
+  size_t n2, n2h;     // doubles per block of a plain / half-level array
+  int nblocks;
 };
-int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int nblocks, DevProblem &dp) {
+// Inputs always go up.  Outputs are written completely by the kernels except (a) the padding columns of
+// a ragged last block and (b) the B_LOC slabs nobody writes (A, QR, QS: never downloaded), so only the
+// last block's outputs are uploaded when NGPTOT is not a multiple of NPROMA -- or everything when the
+// caller asks for it (all_outputs: the device arrays must start from the host's values, e.g. the
+// trajectory fluxes of option ad_have_trajectory).
+int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, int nblocks, DevProblem &dp,
+                   bool all_outputs = false) {
   const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
+  dp.n2 = n2; dp.n2h = n2h; dp.nblocks = nblocks;
   dp.n2b = n2 * nblocks;
   dp.n2hb = n2h * nblocks;
   const size_t in_d = 8 * dp.n2b + dp.n2hb + CLOUDSC2_NCLV * dp.n2b + CLOUDSC2_NSTATE * dp.n2b;
@@ -195,18 +204,30 @@ int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int nblocks, 
   dp.f.pcovptot = q; q += dp.n2b;
   dp.f.pfplsl = q; q += dp.n2hb; dp.f.pfplsn = q; q += dp.n2hb;
   dp.f.pfhpsl = q; q += dp.n2hb; dp.f.pfhpsn = q; q += dp.n2hb;
-  // outputs start from the caller's values (tail columns and untouched slabs keep them)
-  CK(cudaMemcpyAsync(dp.f.b_loc, h->b_loc, CLOUDSC2_NSTATE * dp.n2b * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(dp.f.pa, h->pa, dp.n2b * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(dp.f.pcovptot, h->pcovptot, dp.n2b * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(dp.f.pfplsl, h->pfplsl, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(dp.f.pfplsn, h->pfplsn, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(dp.f.pfhpsl, h->pfhpsl, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(dp.f.pfhpsn, h->pfhpsn, dp.n2hb * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  const bool ragged = ngptot % nproma != 0;
+  if (all_outputs || ragged) {
+    // blocks [b0, nblocks) of every output array start from the caller's values
+    const size_t b0 = all_outputs ? 0 : (size_t)nblocks - 1, nb = (size_t)nblocks - b0;
+    const size_t D = sizeof(double);
+    CK(cudaMemcpyAsync(dp.f.b_loc + CLOUDSC2_NSTATE * n2 * b0, h->b_loc + CLOUDSC2_NSTATE * n2 * b0, CLOUDSC2_NSTATE * n2 * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.pa + n2 * b0, h->pa + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.pcovptot + n2 * b0, h->pcovptot + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.pfplsl + n2h * b0, h->pfplsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.pfplsn + n2h * b0, h->pfplsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.pfhpsl + n2h * b0, h->pfhpsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.pfhpsn + n2h * b0, h->pfhpsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
+  }
   return 0;
 }
-int download_outputs(const cloudsc2_fields *h, const DevProblem &dp) {
-  CK(cudaMemcpyAsync(h->b_loc, dp.f.b_loc, CLOUDSC2_NSTATE * dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+// B_LOC: only the slabs the kernels write come back -- T (0) and Q, QL, QI (2-4); CLD(:,:,NCLV) (7) when
+// the driver-level zeroing ran (loc_last).  A, QR, QS keep the host's values ("never written by
+// anyone").
+int download_outputs(const cloudsc2_fields *h, const DevProblem &dp, bool loc_last) {
+  const size_t D = sizeof(double), n2 = dp.n2, pitch = CLOUDSC2_NSTATE * dp.n2 * D;
+  CK(cudaMemcpy2DAsync(h->b_loc, pitch, dp.f.b_loc, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpy2DAsync(h->b_loc + 2 * n2, pitch, dp.f.b_loc + 2 * n2, pitch, 3 * n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, g.stream));
+  if (loc_last)
+    CK(cudaMemcpy2DAsync(h->b_loc + 7 * n2, pitch, dp.f.b_loc + 7 * n2, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaMemcpyAsync(h->pa, dp.f.pa, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaMemcpyAsync(h->pcovptot, dp.f.pcovptot, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaMemcpyAsync(h->pfplsl, dp.f.pfplsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
@@ -758,7 +779,8 @@ static int tlad_host(bool is_ad, int nproma, int klev, int ngptot, double ptsphy
   if (int rc = check_incr(a, b)) return rc;
   const int nblocks = nblocks_of(ngptot, nproma);
   DevProblem dp;
-  if (int rc = upload_problem(h, nproma, klev, nblocks, dp)) return rc;
+  opts.load();
+  if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks, dp, is_ad && opts.ad_have_trajectory)) return rc;
   const size_t tot = 15 * dp.n2b + dp.n2hb + 6 * dp.n2b + 4 * dp.n2hb;
   if (int rc = g.work2.reserve(tot * sizeof(double))) return rc;
   double *p = g.work2.d();
@@ -785,7 +807,7 @@ static int tlad_host(bool is_ad, int nproma, int klev, int ngptot, double ptsphy
   if (rc) return rc;
   for (auto &it : items)
     CK(cudaMemcpyAsync(it.host, *it.dev, it.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  return download_outputs(h, dp);
+  return download_outputs(h, dp, false);
 }
 int cloudsc2_gpu_tl(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
                     const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
@@ -849,9 +871,9 @@ int cloudsc2_gpu_tl_taylor(int nproma, int klev, int ngptot, double ptsphy, cons
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   DevProblem dp;
-  if (int rc = upload_problem(h, nproma, klev, nblocks_of(ngptot, nproma), dp)) return rc;
+  if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks_of(ngptot, nproma), dp)) return rc;
   int rc = cloudsc2_gpu_tl_taylor_dev(nproma, klev, ngptot, ptsphy, &dp.f, znormg, ratios_blk);
-  int rc2 = download_outputs(h, dp);
+  int rc2 = download_outputs(h, dp, true);
   return rc ? rc : rc2;
 }
 
@@ -914,9 +936,9 @@ int cloudsc2_gpu_ad_test(int nproma, int klev, int ngptot, double ptsphy, const 
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   DevProblem dp;
-  if (int rc = upload_problem(h, nproma, klev, nblocks_of(ngptot, nproma), dp)) return rc;
+  if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks_of(ngptot, nproma), dp)) return rc;
   int rc = cloudsc2_gpu_ad_test_dev(nproma, klev, ngptot, ptsphy, &dp.f, znormg, norms_col);
-  int rc2 = download_outputs(h, dp);
+  int rc2 = download_outputs(h, dp, true);
   return rc ? rc : rc2;
 }
 
