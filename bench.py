@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -274,7 +274,6 @@ def main():
     if sampler:
         sampler.start()
     ms_nl = timed(lambda: gpu.nl_dev(ds, src.ptsphy, stream=stream), args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
     launches = gpu.launch_count() - l0 - args.warmup
     value = ngp_total / (ms_nl * 1e-3)
     nl_gbs = NL_BYTES_PER_COL * ngp / (ms_nl * 1e-3) / 1e9
@@ -353,6 +352,9 @@ def main():
                 results["ad"] = {"error": str(e)}
         for p in list(din.values()) + list(dout.values()):
             gpu.free(p)
+
+    # clocks / throttle reasons sampled over all the kernel timing loops above (NL, TL, AD)
+    clocks = sampler.stop() if sampler else None
 
     # ---- NPROMA sweep (BASELINE config 4: NGPTOT = 160 000, NPROMA 32..256), NL kernel only ---
     sweep = None
