@@ -59,3 +59,33 @@ def gpu_nl(pkg, src100):
     g = pkg.Cloudsc2(pkg.default_params(lregcl=False), src100.klev, src100.ceta)
     yield g
     g.close()
+
+
+class _GoldenView:
+    """npz-like view of a golden set whose inputs are either stored (seed 0) or regenerated from the
+    deterministic generator (other seeds store outputs only)."""
+
+    def __init__(self, g, extra):
+        self._g, self._x = g, extra
+        self.files = [k for k in g.files if k != "in_checksum"] + list(extra)
+
+    def __getitem__(self, k):
+        return self._x[k] if k in self._x else self._g[k]
+
+
+@pytest.fixture(scope="session", params=["seed0", "seed5"])
+def golden_fd(request, pkg):
+    """(golden set of the reference's Python NL kernel, central finite differences of that kernel along
+    dx = 0.01 x) -- the anchors of the TL / AD parity tests; two atmospheres."""
+    gdir = ROOT / "tests" / "golden"
+    if request.param == "seed0":
+        return np.load(gdir / "nl_pyref.npz"), np.load(gdir / "tl_fd_pyref.npz")
+    g = np.load(gdir / "nl_pyref_seed5.npz")
+    f = pkg.synth_source(seed=int(g["seed"]), klon=100, klev=137).subset(list(g["cols"])).f
+    x = {"in_paphp1": f["paph"], "in_papp1": f["pap"], "in_pqm1": f["pq"], "in_ptm1": f["pt"],
+         "in_pl": f["pclv"][0], "in_pi": f["pclv"][1], "in_plude": f["plude"], "in_plu": f["plu"],
+         "in_pmfu": f["pmfu"], "in_pmfd": f["pmfd"], "in_pgtent": f["tend_cml"][0],
+         "in_pgtenq": f["tend_cml"][2], "in_pgtenl": f["tend_cml"][3], "in_pgteni": f["tend_cml"][4],
+         "in_psupsat": f["psupsat"]}
+    x = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in x.items()}
+    return _GoldenView(g, x), np.load(gdir / "tl_fd_pyref_seed5.npz")

@@ -46,10 +46,25 @@ def run(x, ptsphy, ns, klev, klon):
     return y
 
 
+def inputs_of(g):
+    """The 15 inputs of a golden set: stored (seed 0) or regenerated from the deterministic generator."""
+    if "in_ptm1" in g.files:
+        return {k[3:]: np.ascontiguousarray(g[k]) for k in g.files if k.startswith("in_")}
+    f = pkg.synth_source(seed=int(g["seed"]), klon=100, klev=137).subset(list(g["cols"])).f
+    x = {"paphp1": f["paph"], "papp1": f["pap"], "pqm1": f["pq"], "ptm1": f["pt"], "pl": f["pclv"][0],
+         "pi": f["pclv"][1], "plude": f["plude"], "plu": f["plu"], "pmfu": f["pmfu"], "pmfd": f["pmfd"],
+         "pgtent": f["tend_cml"][0], "pgtenq": f["tend_cml"][2], "pgtenl": f["tend_cml"][3],
+         "pgteni": f["tend_cml"][4], "psupsat": f["psupsat"]}
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in x.items()}
+
+
 def main():
-    g = np.load(Path(__file__).with_name("nl_pyref.npz"))
+    # usage: make_golden_tl.py          -> tl_fd_pyref.npz        (the 32 columns of nl_pyref.npz)
+    #        make_golden_tl.py seed5    -> tl_fd_pyref_seed5.npz  (the 48 columns of nl_pyref_seed5.npz)
+    tag = sys.argv[1] if len(sys.argv) > 1 else ""
+    g = np.load(Path(__file__).with_name(f"nl_pyref_{tag}.npz" if tag else "nl_pyref.npz"))
     prm = pkg.default_params()
-    x0 = {k[3:]: np.ascontiguousarray(g[k]) for k in g.files if k.startswith("in_")}
+    x0 = inputs_of(g)
     x0["pqs"] = np.ascontiguousarray(g["pqs"])
     klev, klon = x0["ptm1"].shape
     ns = namespaces(prm, g["ceta"])
@@ -68,7 +83,7 @@ def main():
         out["d_" + n] = d
         out["curv_" + n] = curv
         print(f"  {n:9s} max|D| {np.abs(d).max():.4e}   max second difference {curv.max():.3e}")
-    dst = Path(__file__).with_name("tl_fd_pyref.npz")
+    dst = Path(__file__).with_name(f"tl_fd_pyref_{tag}.npz" if tag else "tl_fd_pyref.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, dst.stat().st_size, "bytes")
 

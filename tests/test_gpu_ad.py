@@ -176,14 +176,13 @@ def test_ad_with_precomputed_trajectory_equals_as_written(pkg, src100):
         assert np.abs(ref[k]).max() > 0 or k == "psupsat", k
 
 
-def test_ad_kernel_is_the_transpose_of_the_reference_derivative(pkg, golden):
+def test_ad_kernel_is_the_transpose_of_the_reference_derivative(pkg, golden_fd):
     """<D, y> = <dx, M'^T y> with D = central finite differences of the REFERENCE'S Python NL kernel
     along dx = 0.01 x (tests/golden/tl_fd_pyref.npz) and M'^T y from the CUDA adjoint, called like
     CALL CLOUDSC2AD (per-block Fortran-ABI entry, PQS5 supplied): pins the GPU adjoint against
     reference code, not only against our own TL."""
-    from pathlib import Path
     import ctypes as C
-    fd = np.load(Path(__file__).resolve().parent / "golden" / "tl_fd_pyref.npz")
+    golden, fd = golden_fd
     lib = pkg.load_library()
     x5 = {k[3:]: np.ascontiguousarray(golden[k]) for k in golden.files if k.startswith("in_")}
     x5["pqs"] = np.ascontiguousarray(golden["pqs"])
