@@ -286,28 +286,36 @@ def main():
                      "frac_of_hbm": nl_gbs / peak, "bytes_per_column": NL_BYTES_PER_COL,
                      **ncu_part("nl", ms_nl)}
 
+    # torch views on library memory via __cuda_array_interface__
+    class _Wrap:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                             "version": 2}
+
+    def make_increments(state):
+        """The 16 + 10 increment arrays of CLOUDSC2TL / CLOUDSC2AD for a device state: dx = 0.01 x built on
+        the device by scaling copies of the inputs (cloudsc_driver_tl_mod.F90:156-171), 1e-7 elsewhere."""
+        m2 = state.nproma * KLEV * state.nblocks
+        m2h = state.nproma * (KLEV + 1) * state.nblocks
+        a = {n: gpu.malloc(8 * (m2h if n == "paph" else m2)) for n in pkg._abi.INCR_IN}
+        b = {n: gpu.malloc(8 * (m2h if n.startswith("pf") else m2)) for n in pkg._abi.INCR_OUT}
+        for n in ("paph", "pap", "pq", "pt", "plude", "plu", "pmfu", "pmfd", "psupsat"):
+            cnt = m2h if n == "paph" else m2
+            torch.as_tensor(_Wrap(a[n], cnt), device=dev).copy_(
+                torch.as_tensor(_Wrap(state.ptr[n], cnt), device=dev) * 0.01)
+        for n in ("pqs", "pl", "pi", "gtent", "gtenq", "gtenl", "gteni"):
+            torch.as_tensor(_Wrap(a[n], m2), device=dev).fill_(1e-7)
+        torch.cuda.synchronize()
+        return a, b, m2, m2h
+
+    def fill_output_adjoints(b, m2, m2h):
+        for n in pkg._abi.INCR_OUT:
+            torch.as_tensor(_Wrap(b[n], m2h if n.startswith("pf") else m2), device=dev).fill_(1e-6)
+        torch.cuda.synchronize()
+
     # ---- TL / AD ------------------------------------------------------------------------------
     if "tl" in modes or "ad" in modes:
-        n2 = nproma * KLEV * ds.nblocks
-        n2h = nproma * (KLEV + 1) * ds.nblocks
-        din = {n: gpu.malloc(8 * (n2h if n == "paph" else n2)) for n in pkg._abi.INCR_IN}
-        dout = {n: gpu.malloc(8 * (n2h if n.startswith("pf") else n2)) for n in pkg._abi.INCR_OUT}
-        # increments dx = 0.01 x built on the device by scaling copies of the inputs
-        scale_pairs = {"paph": ("paph", 0), "pap": ("pap", 0), "pq": ("pq", 0), "pt": ("pt", 0),
-                       "plude": ("plude", 0), "plu": ("plu", 0), "pmfu": ("pmfu", 0), "pmfd": ("pmfd", 0),
-                       "psupsat": ("psupsat", 0)}
-        # torch views on library memory via __cuda_array_interface__
-        class _Wrap:
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
-                                                 "version": 2}
-        for n, (srcname, _) in scale_pairs.items():
-            cnt = n2h if n == "paph" else n2
-            torch.as_tensor(_Wrap(din[n], cnt), device=dev).copy_(
-                torch.as_tensor(_Wrap(ds.ptr[srcname], cnt), device=dev) * 0.01)
-        for n in ("pqs", "pl", "pi", "gtent", "gtenq", "gtenl", "gteni"):
-            torch.as_tensor(_Wrap(din[n], n2), device=dev).fill_(1e-7)
-        torch.cuda.synchronize()
+        din, dout, n2, n2h = make_increments(ds)
         if "tl" in modes:
             ms_tl = timed(lambda: gpu.tl_dev(ds, src.ptsphy, din, dout, stream=stream),
                           max(3, args.steps // 2), 3)
@@ -319,10 +327,7 @@ def main():
                              **ncu_part("tl", ms_tl)}
         if "ad" in modes:
             try:
-                for n in pkg._abi.INCR_OUT:
-                    cnt = n2h if n.startswith("pf") else n2
-                    torch.as_tensor(_Wrap(dout[n], cnt), device=dev).fill_(1e-6)
-                torch.cuda.synchronize()
+                fill_output_adjoints(dout, n2, n2h)
                 ms_ad = timed(lambda: gpu.ad_dev(ds, src.ptsphy, din, dout, stream=stream),
                               max(3, args.steps // 2), 3)
                 gbs = AD_BYTES_PER_COL * ngp / (ms_ad * 1e-3) / 1e9
@@ -356,7 +361,7 @@ def main():
     # clocks / throttle reasons sampled over all the kernel timing loops above (NL, TL, AD)
     clocks = sampler.stop() if sampler else None
 
-    # ---- NPROMA sweep (BASELINE config 4: NGPTOT = 160 000, NPROMA 32..256), NL kernel only ---
+    # ---- NPROMA sweep (BASELINE config 4: NGPTOT = 160 000, NPROMA 32..256): NL, TL and AD kernels ---
     sweep = None
     if not args.no_sweep and world == 1:
         sweep = {}
@@ -366,6 +371,19 @@ def main():
             ms = timed(lambda: gpu.nl_dev(d2, src.ptsphy, stream=stream), 5, 3)
             sweep[str(npr)] = {"columns_per_s": 160000 / (ms * 1e-3), "ms_per_step": ms,
                                "frac_of_hbm": NL_BYTES_PER_COL * 160000 / (ms * 1e-3) / 1e9 / peak}
+            if "tl" in modes or "ad" in modes:
+                a2, b2, m2, m2h = make_increments(d2)
+                if "tl" in modes:
+                    ms = timed(lambda: gpu.tl_dev(d2, src.ptsphy, a2, b2, stream=stream), 3, 3)
+                    sweep[str(npr)]["tl"] = {"columns_per_s": 160000 / (ms * 1e-3), "ms_per_step": ms,
+                                             "frac_of_hbm": TL_BYTES_PER_COL * 160000 / (ms * 1e-3) / 1e9 / peak}
+                if "ad" in modes:
+                    fill_output_adjoints(b2, m2, m2h)
+                    ms = timed(lambda: gpu.ad_dev(d2, src.ptsphy, a2, b2, stream=stream), 3, 3)
+                    sweep[str(npr)]["ad"] = {"columns_per_s": 160000 / (ms * 1e-3), "ms_per_step": ms,
+                                             "frac_of_hbm": AD_BYTES_PER_COL * 160000 / (ms * 1e-3) / 1e9 / peak}
+                for q in list(a2.values()) + list(b2.values()):
+                    gpu.free(q)
             d2.free()
 
     # ---- e2e through the host-pointer C ABI call ----------------------------------------------
