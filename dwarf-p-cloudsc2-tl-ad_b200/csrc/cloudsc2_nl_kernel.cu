@@ -7,6 +7,7 @@
 // shared-memory ring (cloudsc2_stage.cuh).  Loads/stores are coalesced along NPROMA (JL); every
 // input is read exactly once (plus the ~40-level tropopause pre-pass over PT/PGTENT), PQSAT never
 // touches memory.  The same kernel, with flux check-points, is the forward sweep of the adjoint.
+#include <cstdint>
 #include <cstdlib>
 
 #include "cloudsc2_nl.cuh"
@@ -139,6 +140,142 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     stout(out.pcovptot + o.o1, 1.0);   // never true: keeps the dummy chains observable
 }
 
+// ---- experimental variant (CSC2_NL_VARIANT=20): level slabs fetched by ONE DMA warp with TMA bulk copies --
+// CTA = 16 compute warps (512 consecutive columns, one thread per column as above) + 1 DMA warp.  Per
+// level the DMA warp's lanes each issue one `cp.async.bulk` of a contiguous segment (min(NPROMA,512)
+// columns of one field) into the shared-memory ring and the bytes arrive on an mbarrier; the compute
+// warps wait on that barrier, read their own column's 15 values and release the stage through a second
+// mbarrier.  The compute warps then carry no load instructions, no address arithmetic and no array base
+// pointers for the inputs (~60 of the 876 warp instructions per level of the cp.async kernel).
+// Needs: no padding columns (NGPTOT = NBLOCKS*NPROMA), NPROMA a divisor or a multiple of 512 and >= 32,
+// 16-byte aligned arrays, fused SATUR; anything else runs the cp.async kernel.
+constexpr int TMA_NF = 15;
+struct TmaTable {
+  const double *base[TMA_NF];
+  long long blk_stride[TMA_NF];   // doubles between consecutive blocks of the field
+  int lvl_off[TMA_NF];            // 1 for PAPHP1(JK+1) and PLU(JK+1)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "CSC2_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra CSC2_DONE;\n\t"
+      "bra CSC2_WAIT;\n\t"
+      "CSC2_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// TMA_CW compute warps per CTA (+ 1 DMA warp), TMA_ST ring stages (levels in flight + the one being read)
+template <bool RV, int TMA_CW, int TMA_ST>
+__global__ void __launch_bounds__((TMA_CW + 1) * 32, 16 / TMA_CW)
+k_cloudsc2_nl_tma(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
+                  const __grid_constant__ TmaTable tab) {
+  constexpr int TMA_COLS = TMA_CW * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *ring = reinterpret_cast<double *>(smem_raw);                               // [TMA_ST][15][TMA_COLS]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + TMA_ST * TMA_NF * TMA_COLS);
+  __shared__ TmaTable stab;   // a shared copy: the DMA lanes index it with a run-time field number
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TMA_ST);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int klev = g.klev, nproma = g.nproma;
+  const long long ncol = (long long)g.nblocks * nproma;     // == NGPTOT (launch condition)
+  const long long col0 = (long long)blockIdx.x * TMA_COLS;
+  const int valid = (int)(ncol - col0 < TMA_COLS ? ncol - col0 : TMA_COLS);   // a multiple of 32
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int f = 0; f < TMA_NF; ++f) {
+      stab.base[f] = tab.base[f]; stab.blk_stride[f] = tab.blk_stride[f]; stab.lvl_off[f] = tab.lvl_off[f];
+    }
+#pragma unroll
+    for (int st = 0; st < TMA_ST; ++st) { mbar_init(full0 + 8 * st, 1); mbar_init(empty0 + 8 * st, valid >> 5); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  csc2_math_init();   // __syncthreads inside: table, barriers and the exp table are visible to everyone
+
+  if (warp == TMA_CW) {
+    // ---------------- DMA warp ----------------
+    const int seg = nproma < TMA_COLS ? nproma : TMA_COLS;   // contiguous columns of one field
+    const int nseg = valid / seg;
+    const int ncopy = TMA_NF * nseg;
+    int s = 0, round = 0;                     // stage of level jk, number of times the ring has wrapped
+    for (int jk = 0; jk < klev; ++jk) {
+      if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);     // every compute warp has read the stage
+      const bool last = jk == klev - 1;                              // PLU(JK+1) does not exist there (:434-438)
+      if (lane == 0) mbar_expect_tx(full0 + 8 * s, (uint32_t)((TMA_NF - (last ? 1 : 0)) * valid * 8));
+      __syncwarp();
+      for (int idx = lane; idx < ncopy; idx += 32) {
+        const int f = idx / nseg, sg = idx - f * nseg;
+        if (last && f == 7) continue;
+        const long long gc = col0 + (long long)sg * seg;
+        const long long ibl = gc / nproma;
+        const int jl0 = (int)(gc - ibl * nproma);
+        const double *src = stab.base[f] + ibl * stab.blk_stride[f] +
+                            (long long)(jk + stab.lvl_off[f]) * nproma + jl0;
+        tma_load_1d(smem_u32(ring + ((size_t)s * TMA_NF + f) * TMA_COLS + sg * seg), src,
+                    (uint32_t)seg * 8u, full0 + 8 * s);
+      }
+      if (++s == TMA_ST) { s = 0; ++round; }
+    }
+    return;
+  }
+
+  // ---------------- compute warps ----------------
+  const int tcol = warp * 32 + lane;
+  if (tcol >= valid) return;                 // whole warps only (valid is a multiple of 32)
+  const long long gcol = col0 + tcol;
+  const int ibl = (int)(gcol / nproma);
+  const int jl = (int)(gcol - (long long)ibl * nproma);
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
+  const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
+  Carry st;
+  st.paph0 = ldin(in.paph + o.oh);
+  st.rfl = 0.0;
+  st.sfl = 0.0;
+  stout(out.pfplsl + o.oh, 0.0);
+  stout(out.pfplsn + o.oh, 0.0);
+  stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
+  stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
+  const double *mine = ring + tcol;
+  int s = 0, round = 0;
+  for (int jk = 0; jk < klev; ++jk) {
+    mbar_wait(full0 + 8 * s, round & 1);
+    const LevIn cur = csc2_read_level<TMA_COLS>(mine + (size_t)s * TMA_NF * TMA_COLS, jk, klev);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    const double pqs = satur_point(c, cur.pt, csc2_rcp(cur.pap));
+    LevOut y;
+    nl_level<RV>(c, crh, jk, cur, pqs, st, y);
+    const size_t l = (size_t)jk * nproma;
+    stout(out.tent + o.oloc + l, y.tent);
+    stout(out.tenq + o.oloc + l, y.tenq);
+    stout(out.tenl + o.oloc + l, y.tenl);
+    stout(out.teni + o.oloc + l, y.teni);
+    if (out.loc_last) stout(out.loc_last + o.oloc + l, 0.0);
+    stout(out.pclc + o.o1 + l, y.pclc);
+    stout(out.pcovptot + o.o1 + l, 0.0);
+    stout(out.pfplsl + o.oh + l + nproma, y.rfln);
+    stout(out.pfplsn + o.oh + l + nproma, y.sfln);
+    stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);
+    stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
+    if (++s == TMA_ST) { s = 0; ++round; }
+  }
+}
+
 // expand_mod.F90:270-302 on the device: dst(nproma, rows, nblocks) <- src(nlon, rows), local
 // column j <- source column (gcol0 + j) mod nlon, zero beyond ngptot.
 __global__ void k_expand(const double *__restrict__ src, int nlon, long long rows,
@@ -227,8 +364,50 @@ static int nl_variant() {
 }
 void csc2_set_nl_variant(int v) { g_nl_variant = v < 0 ? 0 : v; }
 
+// The TMA variant when the geometry allows it (see k_cloudsc2_nl_tma), else cudaErrorNotSupported.
+template <int TMA_CW, int TMA_ST>
+static cudaError_t launch_nl_tma(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                 cudaStream_t s) {
+  constexpr int TMA_COLS = TMA_CW * 32;
+  const long long n2 = (long long)g.nproma * g.klev;
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  const bool shape_ok = g.nproma >= 32 && g.nproma % 2 == 0 &&
+                        ((g.nproma <= TMA_COLS && TMA_COLS % g.nproma == 0) || g.nproma % TMA_COLS == 0);
+  if (in.pqs || !shape_ok || ncol != g.ngptot) return cudaErrorNotSupported;
+  TmaTable t;
+  const double *base[TMA_NF] = {in.paph, in.pap, in.pt, in.pq, in.pl, in.pi, in.plude, in.plu, in.pmfu, in.pmfd,
+                                in.gt, in.gq, in.gl, in.gi, in.psupsat};
+  const long long bs[TMA_NF] = {n2 + g.nproma, n2, n2, n2, in.bs_cld, in.bs_cld, n2, n2, n2, n2,
+                                in.bs_cml, in.bs_cml, in.bs_cml, in.bs_cml, n2};
+  for (int f = 0; f < TMA_NF; ++f) {
+    if (reinterpret_cast<uintptr_t>(base[f]) % 16 != 0) return cudaErrorNotSupported;
+    t.base[f] = base[f]; t.blk_stride[f] = bs[f]; t.lvl_off[f] = (f == 0 || f == 7) ? 1 : 0;
+  }
+  const int grid = (int)((ncol + TMA_COLS - 1) / TMA_COLS);
+  const size_t smem = (size_t)TMA_ST * TMA_NF * TMA_COLS * sizeof(double) + 64;
+  const bool rv = c.rvtmp2 != 0.0;
+  auto k0 = k_cloudsc2_nl_tma<false, TMA_CW, TMA_ST>;
+  auto k1 = k_cloudsc2_nl_tma<true, TMA_CW, TMA_ST>;
+  static int ok0 = -1, ok1 = -1;
+  if (cudaError_t e = rv ? csc2_allow_smem(k1, smem, ok1) : csc2_allow_smem(k0, smem, ok0)) return e;
+  if (rv) k1<<<grid, (TMA_CW + 1) * 32, smem, s>>>(c, g, in, out, t);
+  else k0<<<grid, (TMA_CW + 1) * 32, smem, s>>>(c, g, in, out, t);
+  return cudaGetLastError();
+}
+
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {
+  if (nl_variant() >= 20 && nl_variant() <= 24) {   // experimental TMA variants: (compute warps, stages)
+    cudaError_t e;
+    switch (nl_variant()) {
+      case 20: e = launch_nl_tma<16, 3>(c, g, in, out, s); break;
+      case 21: e = launch_nl_tma<8, 3>(c, g, in, out, s); break;
+      case 22: e = launch_nl_tma<4, 3>(c, g, in, out, s); break;
+      case 23: e = launch_nl_tma<4, 2>(c, g, in, out, s); break;
+      default: e = launch_nl_tma<8, 2>(c, g, in, out, s); break;
+    }
+    if (e != cudaErrorNotSupported) return e;
+  }
   if (in.pqs) return launch_nl_variant<true, 2, 128, 128>(c, g, in, out, s);
   switch (nl_variant()) {   //                     stages, threads/CTA, registers -> warps per SM
     case 1: return launch_nl_variant<false, 3, 128, 168>(c, g, in, out, s);   // 12
