@@ -276,6 +276,91 @@ k_cloudsc2_nl_tma(const __grid_constant__ KConst c, const Geom g, const TrajIn i
   }
 }
 
+// ---- experimental variant (CSC2_NL_VARIANT=25): warp-private TMA staging --------------------------------
+// No DMA warp and no CTA-wide coupling: every warp fetches ITS OWN 32 columns.  Lane f < 15 owns field f
+// and issues, per level, ONE cp.async.bulk of the warp's 256 contiguous bytes of that field into the
+// warp's ring slots; the bytes arrive on a per-warp, per-stage mbarrier.  One warp instruction replaces the
+// 15 LDGSTS + 30 address adds + 15 base-pointer loads of the cp.async kernel; the source address of a lane
+// advances by NPROMA doubles per level.  Needs NPROMA % 32 == 0 and no padding columns (else cp.async kernel).
+template <bool RV>
+__global__ void __maxnreg__(128)
+k_cloudsc2_nl_wtma(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
+                   const __grid_constant__ TmaTable tab) {
+  constexpr int NT = 128, NW = NT / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *ring = reinterpret_cast<double *>(smem_raw);                               // [2][15][128]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + 2 * TMA_NF * NT);   // [NW][2]
+  __shared__ TmaTable stab;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int klev = g.klev, nproma = g.nproma;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int f = 0; f < TMA_NF; ++f) {
+      stab.base[f] = tab.base[f]; stab.blk_stride[f] = tab.blk_stride[f]; stab.lvl_off[f] = tab.lvl_off[f];
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * NW; ++i) mbar_init(smem_u32(bars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  csc2_math_init();   // __syncthreads inside
+  const long long ncol = (long long)g.nblocks * nproma;          // == NGPTOT (launch condition)
+  const long long wcol0 = (long long)blockIdx.x * NT + warp * 32; // first column of this warp
+  if (wcol0 >= ncol) return;                                      // whole warps only
+  const long long gcol = wcol0 + lane;
+  const int ibl = (int)(gcol / nproma);
+  const int jl = (int)(gcol - (long long)ibl * nproma);
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
+
+  // this lane's field: source of level 0 (lanes >= 15 own nothing) and destination slots of the warp
+  const int f = lane < TMA_NF ? lane : 0;
+  const int wbl = (int)(wcol0 / nproma);
+  const double *src0 = stab.base[f] + (long long)wbl * stab.blk_stride[f] +
+                       (long long)stab.lvl_off[f] * nproma + (wcol0 - (long long)wbl * nproma);
+  const uint32_t dst0 = smem_u32(ring + (size_t)f * NT + warp * 32);
+  const uint32_t bar0 = smem_u32(bars + 2 * warp);
+  auto issue = [&](int lev, int s) {
+    const bool last = lev == klev - 1;                            // PLU(JK+1) does not exist at the last level
+    if (lane == 0) mbar_expect_tx(bar0 + 8 * s, (uint32_t)((TMA_NF - (last ? 1 : 0)) * 256));
+    __syncwarp();
+    if (lane < TMA_NF && !(last && lane == 7))
+      tma_load_1d(dst0 + (uint32_t)(s * TMA_NF * NT * 8), src0 + (size_t)lev * nproma, 256u, bar0 + 8 * s);
+  };
+  issue(0, 0);
+
+  const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
+  Carry st;
+  st.paph0 = ldin(in.paph + o.oh);
+  st.rfl = 0.0;
+  st.sfl = 0.0;
+  stout(out.pfplsl + o.oh, 0.0);
+  stout(out.pfplsn + o.oh, 0.0);
+  stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
+  stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
+  const double *mine = ring + threadIdx.x;
+  for (int jk = 0; jk < klev; ++jk) {
+    const int s = jk & 1;
+    // the other stage was read during the previous iteration and its values have been consumed
+    if (jk + 1 < klev) issue(jk + 1, s ^ 1);
+    mbar_wait(bar0 + 8 * s, (jk >> 1) & 1);
+    const LevIn cur = csc2_read_level<NT>(mine + (size_t)s * TMA_NF * NT, jk, klev);
+    const double pqs = satur_point(c, cur.pt, csc2_rcp(cur.pap));
+    LevOut y;
+    nl_level<RV>(c, crh, jk, cur, pqs, st, y);
+    const size_t l = (size_t)jk * nproma;
+    stout(out.tent + o.oloc + l, y.tent);
+    stout(out.tenq + o.oloc + l, y.tenq);
+    stout(out.tenl + o.oloc + l, y.tenl);
+    stout(out.teni + o.oloc + l, y.teni);
+    if (out.loc_last) stout(out.loc_last + o.oloc + l, 0.0);
+    stout(out.pclc + o.o1 + l, y.pclc);
+    stout(out.pcovptot + o.o1 + l, 0.0);
+    stout(out.pfplsl + o.oh + l + nproma, y.rfln);
+    stout(out.pfplsn + o.oh + l + nproma, y.sfln);
+    stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);
+    stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
+  }
+}
+
 // expand_mod.F90:270-302 on the device: dst(nproma, rows, nblocks) <- src(nlon, rows), local
 // column j <- source column (gcol0 + j) mod nlon, zero beyond ngptot.
 __global__ void k_expand(const double *__restrict__ src, int nlon, long long rows,
@@ -395,8 +480,33 @@ static cudaError_t launch_nl_tma(const KConst &c, const Geom &g, const TrajIn &i
   return cudaGetLastError();
 }
 
+static cudaError_t launch_nl_wtma(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                  cudaStream_t s) {
+  const long long n2 = (long long)g.nproma * g.klev;
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  if (in.pqs || g.nproma % 32 != 0 || ncol != g.ngptot) return cudaErrorNotSupported;
+  TmaTable t;
+  const double *base[TMA_NF] = {in.paph, in.pap, in.pt, in.pq, in.pl, in.pi, in.plude, in.plu, in.pmfu, in.pmfd,
+                                in.gt, in.gq, in.gl, in.gi, in.psupsat};
+  const long long bs[TMA_NF] = {n2 + g.nproma, n2, n2, n2, in.bs_cld, in.bs_cld, n2, n2, n2, n2,
+                                in.bs_cml, in.bs_cml, in.bs_cml, in.bs_cml, n2};
+  for (int f = 0; f < TMA_NF; ++f) {
+    if (reinterpret_cast<uintptr_t>(base[f]) % 16 != 0) return cudaErrorNotSupported;
+    t.base[f] = base[f]; t.blk_stride[f] = bs[f]; t.lvl_off[f] = (f == 0 || f == 7) ? 1 : 0;
+  }
+  const int grid = (int)((ncol + 127) / 128);
+  const size_t smem = (size_t)2 * TMA_NF * 128 * sizeof(double) + 64;
+  if (c.rvtmp2 != 0.0) k_cloudsc2_nl_wtma<true><<<grid, 128, smem, s>>>(c, g, in, out, t);
+  else k_cloudsc2_nl_wtma<false><<<grid, 128, smem, s>>>(c, g, in, out, t);
+  return cudaGetLastError();
+}
+
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {
+  if (nl_variant() == 25) {
+    const cudaError_t e = launch_nl_wtma(c, g, in, out, s);
+    if (e != cudaErrorNotSupported) return e;
+  }
   if (nl_variant() >= 20 && nl_variant() <= 24) {   // experimental TMA variants: (compute warps, stages)
     cudaError_t e;
     switch (nl_variant()) {

@@ -291,3 +291,20 @@ def test_nl_matches_reference_python_golden_edge_columns(pkg):
                "pfplsn": cols(o["pfplsn"]), "pfhpsl": cols(o["pfhpsl"]), "pfhpsn": cols(o["pfhpsn"]),
                "pcovptot": cols(o["pcovptot"])}
         _cmp(got, {n: g["out_" + n] for n in got})
+
+
+@pytest.mark.parametrize("variant", [2, 22, 23, 25])
+def test_nl_launch_variants_agree(pkg, src100, gpu_nl, variant):
+    """The tuning variants of the NL kernel (CSC2_NL_VARIANT / option nl_variant: 12 warps per SM, a DMA warp
+    with TMA bulk copies into an mbarrier ring, warp-private TMA staging) compute the same fields as the
+    default cp.async kernel; geometries the TMA variants do not take (ragged, NPROMA % 32 != 0) fall back."""
+    for nproma, ngptot in ((128, 4096), (32, 640), (64, 1000), (100, 100)):
+        a, b = pkg.ArrayState(src100, nproma, ngptot), pkg.ArrayState(src100, nproma, ngptot)
+        gpu_nl.set_option("nl_variant", 0)
+        gpu_nl.nl(a)
+        gpu_nl.set_option("nl_variant", variant)
+        try:
+            gpu_nl.nl(b)
+        finally:
+            gpu_nl.set_option("nl_variant", 0)
+        _cmp(b.outputs(), a.outputs(), rtol=1e-13)
