@@ -282,3 +282,19 @@ def test_dwarf_write_input_and_reference(built, pkg, tmp_path):
     v = _validation_lines(r.stdout)
     assert len(v) == 10 and all(nums5[2] == 0.0 and not warn for nums5, warn in v.values())
     assert v["PFPLSL"][0][1] > 0
+
+
+@pytest.mark.gpu
+def test_dwarf_other_vertical_resolution_and_seed(built, pkg):
+    """KLEV and the synthetic atmosphere are run-time data for the programs too
+    (CLOUDSC2_SYNTH_KLEV / CLOUDSC2_SYNTH_SEED): KLEV = 91, seed 3."""
+    env = {"CLOUDSC2_SYNTH_KLEV": "91", "CLOUDSC2_SYNTH_SEED": "3"}
+    r = _run(built, "dwarf-cloudsc2-nl", 1, 3000, 48, env=env)         # ragged: 3000 = 62*48 + 24
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "100 synthetic columns x 91 levels, seed 3" in r.stdout
+    v = _validation_lines(r.stdout)
+    assert len(v) == 10 and all(nums5[2] == 0.0 and not warn for nums5, warn in v.values())
+    r = _run(built, "dwarf-cloudsc2-tl", 1, 100, 1, env=env)
+    assert r.returncode == 0 and "TEST PASSED" in r.stdout, r.stdout
+    r = _run(built, "dwarf-cloudsc2-ad", 1, 100, 100, env=env)
+    assert r.returncode == 0 and "TEST OK" in r.stdout, r.stdout
