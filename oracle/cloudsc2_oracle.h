@@ -6,9 +6,11 @@
  *
  * Parity status: the NL restatement is pinned against the reference's own importable Python
  * kernel (src/cloudsc2_nl_gt4py/cloudsc2_py.py) through the golden vectors in tests/golden/
- * (made by tests/golden/make_golden.py).  TL and AD are pinned against central finite differences
- * of that same reference kernel (tests/golden/tl_fd_pyref.npz, made by make_golden_tl.py: TL to
- * 1e-8, AD through <D,y> = <dx, AD y> to 1e-6) and by the reference's own known-answer properties
+ * (made by make_golden.py on two synthetic atmospheres and by make_golden_edge.py on edge-case
+ * columns sitting on the scheme's branch thresholds, KLEV = 60).  TL and AD are pinned against central
+ * finite differences of that same reference kernel (tests/golden/tl_fd_pyref*.npz, made by
+ * make_golden_tl.py on two atmospheres: TL to 1e-7, AD through <D,y> = <dx, AD y> to 1e-6) and by the
+ * reference's own known-answer properties
  * (Taylor test, adjoint dot-product test).  Against the reference
  * FORTRAN BINARIES on the real input.h5: PARITY UNPINNED (no Fortran compiler, no HDF5, and
  * config-files/input.h5 is absent in this environment).
