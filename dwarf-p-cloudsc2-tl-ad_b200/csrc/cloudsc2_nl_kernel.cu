@@ -361,6 +361,112 @@ k_cloudsc2_nl_wtma(const __grid_constant__ KConst c, const Geom g, const TrajIn 
   }
 }
 
+// ---- experimental variant (CSC2_NL_VARIANT=30): two adjacent columns per thread --------------------------
+// A thread owns columns 2t and 2t+1 of the CTA: every staged copy, ring read and output store is 16 bytes
+// wide, so the per-level overhead that does not depend on the column (array base pointers, address adds,
+// constant loads, loop control: ~150 of the 876 warp instructions) is paid once for two columns, and the two
+// independent level evaluations sit in one basic block.  255 registers, 8 warps per SM (= 16 column-warps).
+// Needs even NPROMA, 16-byte aligned arrays and no padding columns (else the cp.async kernel).
+__device__ __forceinline__ void csc2_cp_async16(double2 *smem_dst, const double *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void stout2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+
+template <bool RV>
+__global__ void __maxnreg__(255)
+k_cloudsc2_nl_x2(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out) {
+  constexpr int NT = 128;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw) + threadIdx.x;    // [2][15][NT] double2
+  csc2_math_init();
+  const int klev = g.klev, nproma = g.nproma;
+  const long long ncol = (long long)g.nblocks * nproma;                  // == NGPTOT (launch condition)
+  const long long gcol = ((long long)blockIdx.x * NT + threadIdx.x) * 2;
+  if (gcol >= ncol) return;
+  const int ibl = (int)(gcol / nproma);
+  const int jl = (int)(gcol - (long long)ibl * nproma);                  // even; jl + 1 is in the same block
+  const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
+
+  auto stage = [&](double2 *d, int jk) {
+    const size_t l = (size_t)jk * nproma;
+    csc2_cp_async16(d + 0 * NT, in.paph + o.oh + l + nproma);
+    csc2_cp_async16(d + 1 * NT, in.pap + o.o1 + l);
+    csc2_cp_async16(d + 2 * NT, in.pt + o.o1 + l);
+    csc2_cp_async16(d + 3 * NT, in.pq + o.o1 + l);
+    csc2_cp_async16(d + 4 * NT, in.pl + o.ocld + l);
+    csc2_cp_async16(d + 5 * NT, in.pi + o.ocld + l);
+    csc2_cp_async16(d + 6 * NT, in.plude + o.o1 + l);
+    if (jk < klev - 1) csc2_cp_async16(d + 7 * NT, in.plu + o.o1 + l + nproma);
+    csc2_cp_async16(d + 8 * NT, in.pmfu + o.o1 + l);
+    csc2_cp_async16(d + 9 * NT, in.pmfd + o.o1 + l);
+    csc2_cp_async16(d + 10 * NT, in.gt + o.ocml + l);
+    csc2_cp_async16(d + 11 * NT, in.gq + o.ocml + l);
+    csc2_cp_async16(d + 12 * NT, in.gl + o.ocml + l);
+    csc2_cp_async16(d + 13 * NT, in.gi + o.ocml + l);
+    csc2_cp_async16(d + 14 * NT, in.psupsat + o.o1 + l);
+  };
+  stage(ring, 0);
+  csc2_cp_async_commit();
+
+  const CritRH crh0 = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
+  const CritRH crh1 = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1 + 1, o.ocml + 1, nproma));
+  Carry st0, st1;
+  {
+    const double2 p0 = *reinterpret_cast<const double2 *>(in.paph + o.oh);
+    st0.paph0 = p0.x; st1.paph0 = p0.y;
+  }
+  st0.rfl = st0.sfl = st1.rfl = st1.sfl = 0.0;
+  stout2(out.pfplsl + o.oh, 0.0, 0.0);
+  stout2(out.pfplsn + o.oh, 0.0, 0.0);
+  stout2(out.pfhpsl + o.oh, -0.0 * c.rlvtt, -0.0 * c.rlvtt);
+  stout2(out.pfhpsn + o.oh, -0.0 * c.rlstt, -0.0 * c.rlstt);
+
+  for (int jk = 0; jk < klev; ++jk) {
+    const int s = jk & 1;
+    if (jk + 1 < klev) stage(ring + (s ^ 1) * (TMA_NF * NT), jk + 1);
+    csc2_cp_async_commit();
+    csc2_cp_async_wait<1>();
+    const double2 *d = ring + s * (TMA_NF * NT);
+    LevIn a, b;
+    {
+      double2 v;
+      v = d[0 * NT]; a.paph1 = v.x; b.paph1 = v.y;
+      v = d[1 * NT]; a.pap = v.x; b.pap = v.y;
+      v = d[2 * NT]; a.pt = v.x; b.pt = v.y;
+      v = d[3 * NT]; a.pq = v.x; b.pq = v.y;
+      v = d[4 * NT]; a.pl = v.x; b.pl = v.y;
+      v = d[5 * NT]; a.pi = v.x; b.pi = v.y;
+      v = d[6 * NT]; a.plude = v.x; b.plude = v.y;
+      v = (jk < klev - 1) ? d[7 * NT] : make_double2(0.0, 0.0); a.plu1 = v.x; b.plu1 = v.y;
+      v = d[8 * NT]; a.pmfu = v.x; b.pmfu = v.y;
+      v = d[9 * NT]; a.pmfd = v.x; b.pmfd = v.y;
+      v = d[10 * NT]; a.gt = v.x; b.gt = v.y;
+      v = d[11 * NT]; a.gq = v.x; b.gq = v.y;
+      v = d[12 * NT]; a.gl = v.x; b.gl = v.y;
+      v = d[13 * NT]; a.gi = v.x; b.gi = v.y;
+      v = d[14 * NT]; a.psupsat = v.x; b.psupsat = v.y;
+    }
+    const double pqs0 = satur_point(c, a.pt, csc2_rcp(a.pap));
+    const double pqs1 = satur_point(c, b.pt, csc2_rcp(b.pap));
+    LevOut y0, y1;
+    nl_level<RV>(c, crh0, jk, a, pqs0, st0, y0);
+    nl_level<RV>(c, crh1, jk, b, pqs1, st1, y1);
+    const size_t l = (size_t)jk * nproma;
+    stout2(out.tent + o.oloc + l, y0.tent, y1.tent);
+    stout2(out.tenq + o.oloc + l, y0.tenq, y1.tenq);
+    stout2(out.tenl + o.oloc + l, y0.tenl, y1.tenl);
+    stout2(out.teni + o.oloc + l, y0.teni, y1.teni);
+    if (out.loc_last) stout2(out.loc_last + o.oloc + l, 0.0, 0.0);
+    stout2(out.pclc + o.o1 + l, y0.pclc, y1.pclc);
+    stout2(out.pcovptot + o.o1 + l, 0.0, 0.0);
+    stout2(out.pfplsl + o.oh + l + nproma, y0.rfln, y1.rfln);
+    stout2(out.pfplsn + o.oh + l + nproma, y0.sfln, y1.sfln);
+    stout2(out.pfhpsl + o.oh + l + nproma, -y0.rfln * c.rlvtt, -y1.rfln * c.rlvtt);
+    stout2(out.pfhpsn + o.oh + l + nproma, -y0.sfln * c.rlstt, -y1.sfln * c.rlstt);
+  }
+}
+
 // expand_mod.F90:270-302 on the device: dst(nproma, rows, nblocks) <- src(nlon, rows), local
 // column j <- source column (gcol0 + j) mod nlon, zero beyond ngptot.
 __global__ void k_expand(const double *__restrict__ src, int nlon, long long rows,
@@ -501,8 +607,34 @@ static cudaError_t launch_nl_wtma(const KConst &c, const Geom &g, const TrajIn &
   return cudaGetLastError();
 }
 
+static cudaError_t launch_nl_x2(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                cudaStream_t s) {
+  const long long ncol = (long long)g.nblocks * g.nproma;
+  if (in.pqs || g.nproma % 2 != 0 || ncol != g.ngptot) return cudaErrorNotSupported;
+  const void *ptrs[] = {in.paph, in.pap, in.pt, in.pq, in.pl, in.pi, in.plude, in.plu, in.pmfu, in.pmfd, in.gt,
+                        in.gq, in.gl, in.gi, in.psupsat, out.tent, out.tenq, out.tenl, out.teni, out.pclc,
+                        out.pcovptot, out.pfplsl, out.pfplsn, out.pfhpsl, out.pfhpsn, out.loc_last};
+  for (const void *p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) % 16 != 0) return cudaErrorNotSupported;
+  if ((in.bs_cld % 2) || (in.bs_cml % 2) || (out.bs_loc % 2)) return cudaErrorNotSupported;
+  const int grid = (int)((ncol / 2 + 127) / 128);
+  const size_t smem = (size_t)2 * TMA_NF * 128 * sizeof(double2);
+  auto k0 = k_cloudsc2_nl_x2<false>;
+  auto k1 = k_cloudsc2_nl_x2<true>;
+  static int ok0 = -1, ok1 = -1;
+  const bool rv = c.rvtmp2 != 0.0;
+  if (cudaError_t e = rv ? csc2_allow_smem(k1, smem, ok1) : csc2_allow_smem(k0, smem, ok0)) return e;
+  if (rv) k1<<<grid, 128, smem, s>>>(c, g, in, out);
+  else k0<<<grid, 128, smem, s>>>(c, g, in, out);
+  return cudaGetLastError();
+}
+
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {
+  if (nl_variant() == 30) {
+    const cudaError_t e = launch_nl_x2(c, g, in, out, s);
+    if (e != cudaErrorNotSupported) return e;
+  }
   if (nl_variant() == 25) {
     const cudaError_t e = launch_nl_wtma(c, g, in, out, s);
     if (e != cudaErrorNotSupported) return e;

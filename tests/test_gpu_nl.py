@@ -293,7 +293,7 @@ def test_nl_matches_reference_python_golden_edge_columns(pkg):
         _cmp(got, {n: g["out_" + n] for n in got})
 
 
-@pytest.mark.parametrize("variant", [2, 22, 23, 25])
+@pytest.mark.parametrize("variant", [2, 22, 23, 25, 30])
 def test_nl_launch_variants_agree(pkg, src100, gpu_nl, variant):
     """The tuning variants of the NL kernel (CSC2_NL_VARIANT / option nl_variant: 12 warps per SM, a DMA warp
     with TMA bulk copies into an mbarrier ring, warp-private TMA staging) compute the same fields as the
