@@ -373,8 +373,8 @@ __device__ __forceinline__ void csc2_cp_async16(double2 *smem_dst, const double 
 }
 __device__ __forceinline__ void stout2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
 
-template <bool RV>
-__global__ void __maxnreg__(255)
+template <bool RV, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 k_cloudsc2_nl_x2(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out) {
   constexpr int NT = 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -607,6 +607,7 @@ static cudaError_t launch_nl_wtma(const KConst &c, const Geom &g, const TrajIn &
   return cudaGetLastError();
 }
 
+template <int MAXREG>
 static cudaError_t launch_nl_x2(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                                 cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
@@ -619,8 +620,8 @@ static cudaError_t launch_nl_x2(const KConst &c, const Geom &g, const TrajIn &in
   if ((in.bs_cld % 2) || (in.bs_cml % 2) || (out.bs_loc % 2)) return cudaErrorNotSupported;
   const int grid = (int)((ncol / 2 + 127) / 128);
   const size_t smem = (size_t)2 * TMA_NF * 128 * sizeof(double2);
-  auto k0 = k_cloudsc2_nl_x2<false>;
-  auto k1 = k_cloudsc2_nl_x2<true>;
+  auto k0 = k_cloudsc2_nl_x2<false, MAXREG>;
+  auto k1 = k_cloudsc2_nl_x2<true, MAXREG>;
   static int ok0 = -1, ok1 = -1;
   const bool rv = c.rvtmp2 != 0.0;
   if (cudaError_t e = rv ? csc2_allow_smem(k1, smem, ok1) : csc2_allow_smem(k0, smem, ok0)) return e;
@@ -631,8 +632,10 @@ static cudaError_t launch_nl_x2(const KConst &c, const Geom &g, const TrajIn &in
 
 cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            cudaStream_t s) {
-  if (nl_variant() == 30) {
-    const cudaError_t e = launch_nl_x2(c, g, in, out, s);
+  if (nl_variant() >= 30 && nl_variant() <= 32) {   // two columns per thread at 255 / 168 / 128 registers
+    const cudaError_t e = nl_variant() == 30   ? launch_nl_x2<255>(c, g, in, out, s)
+                          : nl_variant() == 31 ? launch_nl_x2<168>(c, g, in, out, s)
+                                               : launch_nl_x2<128>(c, g, in, out, s);
     if (e != cudaErrorNotSupported) return e;
   }
   if (nl_variant() == 25) {
