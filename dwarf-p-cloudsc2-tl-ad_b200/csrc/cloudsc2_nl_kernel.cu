@@ -529,7 +529,10 @@ static cudaError_t launch_nl_rv(const KConst &c, const Geom &g, const TrajIn &in
                                 cudaStream_t s, NLCkpt ck = NLCkpt{nullptr, 0, 1}) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + NT - 1) / NT);
-  const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double);
+  // CSC2_NL_EXTRA_SMEM_KB (probe): unused extra dynamic shared memory per CTA, to measure how the size of the
+  // shared-memory carve-out (= what is left for L1) affects the kernel at unchanged occupancy
+  static const size_t extra = [] { const char *e = getenv("CSC2_NL_EXTRA_SMEM_KB"); return e ? (size_t)atoi(e) * 1024 : 0; }();
+  const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double) + extra;
   auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV, CKPT, PROBE>;
   static int smem_ok_on_device = -1;
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
