@@ -42,6 +42,23 @@ def ob(built):
 
 
 @pytest.fixture(scope="session")
+def obref(built):
+    """The same binding on oracle/_ref/libcloudsc2_ref.so: the reference's own Fortran kernels,
+    transliterated to C by oracle/f90toc.py (built in the container that has /root/reference; the
+    prebuilt .so travels to the GPU box)."""
+    import importlib.util
+    path = built.build_oracle_ref()
+    if path is None:
+        pytest.skip("oracle/_ref is not built and the reference sources are not here to build it")
+    spec = importlib.util.spec_from_file_location("oracle_binding_ref", ROOT / "tests" / "oracle_binding.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.ORACLE_LIB = path
+    assert b"f90toc" in mod.flavour()
+    return mod
+
+
+@pytest.fixture(scope="session")
 def src100(pkg):
     return pkg.synth_source(seed=0, klon=100, klev=137)
 

@@ -72,8 +72,16 @@ def lib():
     L.orc_adjoint_verdict.restype = i
     L.orc_adjoint_verdict.argtypes = [d]
     L.orc_max_threads.restype = i
+    if hasattr(L, "orc_flavour"):
+        L.orc_flavour.restype = C.c_char_p
     _lib = L
     return L
+
+
+def flavour() -> bytes:
+    """b"" for the hand-written restatement, a description for oracle/_ref (f90toc transliteration)."""
+    L = lib()
+    return L.orc_flavour() if hasattr(L, "orc_flavour") else b""
 
 
 def _p(a: np.ndarray):
