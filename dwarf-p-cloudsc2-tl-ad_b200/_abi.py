@@ -59,6 +59,18 @@ class Source(C.Structure):
                                   "psupsat", "pclv", "tend_cml", "ceta")]
 
 
+class Reference(C.Structure):
+    """struct cloudsc2_reference (include/cloudsc2_host.h): un-expanded reference columns."""
+    _fields_ = [("klon", C.c_int), ("klev", C.c_int)] + [
+        (n, c_double_p) for n in ("plude", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn",
+                                  "tend_loc")]
+
+
+NVALIDATED = 10
+VALIDATED_NAMES = ("PLUDE", "PCOVPTOT", "PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN",
+                   "TENDENCY_LOC%A", "TENDENCY_LOC%Q", "TENDENCY_LOC%T", "TENDENCY_LOC%CLD")
+
+
 class State(C.Structure):
     """struct cloudsc2_state (include/cloudsc2_host.h)."""
     _fields_ = [("nproma", C.c_int), ("klev", C.c_int), ("ngptot", C.c_int),
@@ -74,7 +86,15 @@ def _declare(lib):
     sig = {
         # include/cloudsc2_b200.h
         "cloudsc2_gpu_init": (i, [P, i, c_double_p, i]),
+        "cloudsc2_gpu_init_multi": (i, [P, i, c_double_p, i]),
+        "cloudsc2_gpu_init_devices": (i, [P, i, c_double_p, i, C.POINTER(i)]),
         "cloudsc2_gpu_finalize": (i, []),
+        "cloudsc2_gpu_num_devices": (i, []),
+        "cloudsc2_gpu_select_device": (i, [i]),
+        "cloudsc2_gpu_comm_unique_id": (i, [vp, i]),
+        "cloudsc2_gpu_comm_init_rank": (i, [i, i, vp, i]),
+        "cloudsc2_gpu_comm_info": (i, [C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+        "cloudsc2_gpu_allreduce_dev": (i, [vp, i, i]),
         "cloudsc2_gpu_last_error": (C.c_char_p, []),
         "cloudsc2_gpu_available": (i, []),
         "cloudsc2_gpu_device_count": (i, []),
@@ -109,6 +129,18 @@ def _declare(lib):
         "cloudsc2_gpu_validate_dev": (i, [vp, i, vp, i, i, i, i, C.c_longlong, c_double_p]),
         "cloudsc2_gpu_validate_slabs_dev": (i, [vp, i, vp, i, i, i, C.c_longlong, i, C.c_longlong,
                                                 c_double_p]),
+        "cloudsc2_gpu_state_load": (i, [C.POINTER(Source), i, i]),
+        "cloudsc2_gpu_state_free": (i, []),
+        "cloudsc2_gpu_state_info": (i, [i, C.POINTER(i), C.POINTER(i), C.POINTER(i),
+                                        C.POINTER(C.c_longlong)]),
+        "cloudsc2_gpu_state_fields": (i, [F]),
+        "cloudsc2_gpu_state_nl": (i, [c_double_p, c_double_p]),
+        "cloudsc2_gpu_state_tl_taylor": (i, [c_double_p, c_double_p, c_double_p]),
+        "cloudsc2_gpu_state_ad_test": (i, [c_double_p, c_double_p, c_double_p]),
+        "cloudsc2_gpu_state_validate": (i, [C.POINTER(Reference), c_double_p]),
+        "cloudsc2_gpu_state_get": (i, [C.c_char_p, c_double_p]),
+        "cloudsc2_gpu_nl_source": (i, [C.POINTER(Source), C.POINTER(Reference), i, i, c_double_p,
+                                       c_double_p, c_double_p]),
         # include/cloudsc2_host.h
         "cloudsc2_default_params": (None, [P]),
         "cloudsc2_source_synth": (i, [C.POINTER(Source), C.c_ulonglong, i, i, P]),
@@ -122,12 +154,12 @@ def _declare(lib):
         "cloudsc2_h5_read_i4": (C.c_longlong, [C.c_char_p, C.c_char_p, C.POINTER(i),
                                                C.c_longlong]),
         "cloudsc2_source_load_h5": (i, [C.POINTER(Source), P, C.c_char_p]),
-        "cloudsc2_reference_load_h5": (i, [vp, C.c_char_p]),
-        "cloudsc2_reference_free": (None, [vp]),
+        "cloudsc2_reference_load_h5": (i, [C.POINTER(Reference), C.c_char_p]),
+        "cloudsc2_reference_free": (None, [C.POINTER(Reference)]),
         "cloudsc2_input_last_error": (C.c_char_p, []),
         "cloudsc2_h5_write": (i, [C.c_char_p, vp, i]),
         "cloudsc2_source_write_h5": (i, [C.POINTER(Source), P, C.c_char_p]),
-        "cloudsc2_reference_write_h5": (i, [vp, C.c_char_p]),
+        "cloudsc2_reference_write_h5": (i, [C.POINTER(Reference), C.c_char_p]),
         "cloudsc2_validate_host": (None, [c_double_p, c_double_p, i, i, i, c_double_p]),
         "cloudsc2_error_rel": (d, [c_double_p, C.POINTER(i)]),
     }

@@ -198,7 +198,7 @@ static cudaError_t launch_ad_k(const KConst &c, const Geom &g, const TrajIn &in,
                                cudaStream_t s) {
   const size_t smem = (size_t)AD_STAGES * AD_NF * NT * sizeof(double);
   auto kern = k_cloudsc2_ad<RV, DOT, LREG, MINB>;
-  static int smem_ok_on_device = -1;
+  static CSC2_SMEM_FLAGS smem_ok_on_device{0};
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   // forward (trajectory) sweep: its own launch at the NL kernel's occupancy (12 warps/SM instead of
   // the 8 the adjoint level allows), check-pointing the fluxes the reverse sweep restarts from
@@ -213,13 +213,15 @@ template <bool RV, bool DOT>
 static cudaError_t launch_ad_variant(const KConst &c, const Geom &g, const TrajIn &in,
                                      const TrajOut &out, const IncIn &din, const IncOut &dout,
                                      const ADOpts &opt, int grid, cudaStream_t s) {
+#ifdef CSC2_EXPERIMENTS   // 3 CTAs/SM at 168 registers (CSC2_AD_MINB=3): slower, DESIGN.md 3.3
   static const int minb = [] { const char *e = getenv("CSC2_AD_MINB"); return e ? atoi(e) : 2; }();
-  if (minb == 2) {
-    if (c.lregcl) return launch_ad_k<RV, DOT, true, 2>(c, g, in, out, din, dout, opt, grid, s);
-    return launch_ad_k<RV, DOT, false, 2>(c, g, in, out, din, dout, opt, grid, s);
+  if (minb == 3) {
+    if (c.lregcl) return launch_ad_k<RV, DOT, true, 3>(c, g, in, out, din, dout, opt, grid, s);
+    return launch_ad_k<RV, DOT, false, 3>(c, g, in, out, din, dout, opt, grid, s);
   }
-  if (c.lregcl) return launch_ad_k<RV, DOT, true, 3>(c, g, in, out, din, dout, opt, grid, s);
-  return launch_ad_k<RV, DOT, false, 3>(c, g, in, out, din, dout, opt, grid, s);
+#endif
+  if (c.lregcl) return launch_ad_k<RV, DOT, true, 2>(c, g, in, out, din, dout, opt, grid, s);
+  return launch_ad_k<RV, DOT, false, 2>(c, g, in, out, din, dout, opt, grid, s);
 }
 
 cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,

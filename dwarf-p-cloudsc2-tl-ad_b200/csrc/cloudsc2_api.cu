@@ -10,64 +10,11 @@
 #include <thread>
 #include <vector>
 
-#include "cloudsc2_launch.h"
+#include "cloudsc2_ctx.h"
+
+#define G (csc2_ctx())
 
 namespace {
-
-char g_err[1024] = "";
-int fail(int code, const char *fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-  return code;
-}
-#define CK(call)                                                                       \
-  do {                                                                                 \
-    cudaError_t e_ = (call);                                                           \
-    if (e_ != cudaSuccess)                                                             \
-      return fail(100 + (int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                  __FILE__, __LINE__);                                                 \
-  } while (0)
-
-struct DevBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-  int reserve(size_t bytes) {
-    if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return fail(100 + (int)e, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    cap = bytes;
-    return 0;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  double *d() const { return static_cast<double *>(p); }
-};
-
-constexpr int kStreams = 3;
-
-struct Ctx {
-  bool init = false;
-  int device = 0;
-  cloudsc2_params prm;
-  int klev = 0;
-  double ceta[CSC2_KLEV_MAX];
-  double zscalm[CSC2_KLEV_MAX];
-  int kwin0 = 0, kwin1 = -1;
-  cudaStream_t stream = nullptr;
-  cudaStream_t pipe[kStreams] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  long long launches = 0;
-  DevBuf in, out, work, work2, res;   // staging for the host-pointer entry points + scratch
-};
-Ctx g;
 
 // Tuning options: defaults from the environment, changeable through cloudsc2_gpu_set_option.
 struct Options {
@@ -86,15 +33,10 @@ struct Options {
 };
 Options opts;
 
-int require_init() {
-  if (!g.init) return fail(2, "cloudsc2_gpu_init has not been called");
-  return 0;
-}
-
 KConst make_kconst(double ptsphy) {
   KConst c;
   std::memset(&c, 0, sizeof(c));
-  const cloudsc2_params &p = g.prm;
+  const cloudsc2_params &p = G.prm;
   c.rg = p.rg; c.rd = p.rd; c.rcpd = p.rcpd; c.retv = p.retv; c.rlvtt = p.rlvtt;
   c.rlstt = p.rlstt; c.rlmlt = p.rlmlt; c.rtt = p.rtt; c.r2es = p.r2es; c.r3les = p.r3les;
   c.r3ies = p.r3ies; c.r4les = p.r4les; c.r4ies = p.r4ies; c.r5les = p.r5les; c.r5ies = p.r5ies;
@@ -117,15 +59,28 @@ KConst make_kconst(double ptsphy) {
   c.zcons2_inv = ptsphy * p.rg;
   c.zcor_cap = 1.0 / (1.0 - p.retv * CSC2_ZQMAX);
   c.lregcl = p.lregcl;
-  c.klev = g.klev;
-  c.kwin0 = g.kwin0;
-  c.kwin1 = g.kwin1;
+  c.klev = G.klev;
+  c.kwin0 = G.kwin0;
+  c.kwin1 = G.kwin1;
   return c;
 }
 
+// The scratch buffers (work, res) are shared by every entry point of a context, while the _dev entries
+// may run on caller-supplied streams: order each use after the previous one (whatever stream it was
+// on) and leave a marker behind for the next.
+int scratch_begin(cudaStream_t s) {
+  if (G.scratch_used) CK(cudaStreamWaitEvent(s, G.scratch_done, 0));
+  return 0;
+}
+int scratch_end(cudaStream_t s) {
+  CK(cudaEventRecord(G.scratch_done, s));
+  G.scratch_used = true;
+  return 0;
+}
+
 int check_dims(int nproma, int klev, int ngptot) {
-  if (nproma <= 0 || ngptot <= 0) return fail(3, "bad dimensions nproma=%d ngptot=%d", nproma, ngptot);
-  if (klev != g.klev) return fail(3, "klev=%d differs from the klev=%d given to cloudsc2_gpu_init", klev, g.klev);
+  if (nproma <= 0 || ngptot <= 0) return csc2_fail(3, "bad dimensions nproma=%d ngptot=%d", nproma, ngptot);
+  if (klev != G.klev) return csc2_fail(3, "klev=%d differs from the klev=%d given to cloudsc2_gpu_init", klev, G.klev);
   return 0;
 }
 inline int nblocks_of(int ngptot, int nproma) { return ngptot / nproma + std::min(ngptot % nproma, 1); }
@@ -153,12 +108,12 @@ void views_from_fields(const cloudsc2_fields &f, int nproma, int klev, TrajIn &i
 }
 
 int check_fields(const cloudsc2_fields *f) {
-  if (!f) return fail(3, "fields pointer is NULL");
+  if (!f) return csc2_fail(3, "fields pointer is NULL");
   const void *ptrs[] = {f->pt, f->pq, f->pap, f->paph, f->plu, f->plude, f->pmfu, f->pmfd, f->psupsat,
                         f->pclv, f->b_cml, f->b_loc, f->pa, f->pcovptot, f->pfplsl, f->pfplsn,
                         f->pfhpsl, f->pfhpsn};
   for (const void *p : ptrs)
-    if (!p) return fail(3, "a field pointer in cloudsc2_fields is NULL");
+    if (!p) return csc2_fail(3, "a field pointer in cloudsc2_fields is NULL");
   return 0;
 }
 
@@ -173,7 +128,7 @@ struct DevProblem {
 // Inputs always go up.  Outputs are written completely by the kernels except (a) the padding columns of
 // a ragged last block and (b) the B_LOC slabs nobody writes (A, QR, QS: never downloaded), so only the
 // last block's outputs are uploaded when NGPTOT is not a multiple of NPROMA -- or everything when the
-// caller asks for it (all_outputs: the device arrays must start from the host's values, e.g. the
+// caller asks for it (all_outputs: the device arrays must start from the host's values, e.G. the
 // trajectory fluxes of option ad_have_trajectory).
 int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, int nblocks, DevProblem &dp,
                    bool all_outputs = false) {
@@ -183,12 +138,12 @@ int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, i
   dp.n2hb = n2h * nblocks;
   const size_t in_d = 8 * dp.n2b + dp.n2hb + CLOUDSC2_NCLV * dp.n2b + CLOUDSC2_NSTATE * dp.n2b;
   const size_t out_d = CLOUDSC2_NSTATE * dp.n2b + 2 * dp.n2b + 4 * dp.n2hb;
-  if (int rc = g.in.reserve(in_d * sizeof(double))) return rc;
-  if (int rc = g.out.reserve(out_d * sizeof(double))) return rc;
-  double *p = g.in.d();
+  if (int rc = G.in.reserve(in_d * sizeof(double))) return rc;
+  if (int rc = G.out.reserve(out_d * sizeof(double))) return rc;
+  double *p = G.in.d();
   auto up = [&](const double *src, size_t n, const double *&dst) -> cudaError_t {
     dst = p;
-    cudaError_t e = cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+    cudaError_t e = cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, G.stream);
     p += n;
     return e;
   };
@@ -198,7 +153,7 @@ int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, i
   CK(up(h->pmfd, dp.n2b, dp.f.pmfd)); CK(up(h->psupsat, dp.n2b, dp.f.psupsat));
   CK(up(h->pclv, CLOUDSC2_NCLV * dp.n2b, dp.f.pclv));
   CK(up(h->b_cml, CLOUDSC2_NSTATE * dp.n2b, dp.f.b_cml));
-  double *q = g.out.d();
+  double *q = G.out.d();
   dp.f.b_loc = q; q += CLOUDSC2_NSTATE * dp.n2b;
   dp.f.pa = q; q += dp.n2b;
   dp.f.pcovptot = q; q += dp.n2b;
@@ -209,13 +164,13 @@ int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, i
     // blocks [b0, nblocks) of every output array start from the caller's values
     const size_t b0 = all_outputs ? 0 : (size_t)nblocks - 1, nb = (size_t)nblocks - b0;
     const size_t D = sizeof(double);
-    CK(cudaMemcpyAsync(dp.f.b_loc + CLOUDSC2_NSTATE * n2 * b0, h->b_loc + CLOUDSC2_NSTATE * n2 * b0, CLOUDSC2_NSTATE * n2 * nb * D, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dp.f.pa + n2 * b0, h->pa + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dp.f.pcovptot + n2 * b0, h->pcovptot + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dp.f.pfplsl + n2h * b0, h->pfplsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dp.f.pfplsn + n2h * b0, h->pfplsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dp.f.pfhpsl + n2h * b0, h->pfhpsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dp.f.pfhpsn + n2h * b0, h->pfhpsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dp.f.b_loc + CLOUDSC2_NSTATE * n2 * b0, h->b_loc + CLOUDSC2_NSTATE * n2 * b0, CLOUDSC2_NSTATE * n2 * nb * D, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemcpyAsync(dp.f.pa + n2 * b0, h->pa + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemcpyAsync(dp.f.pcovptot + n2 * b0, h->pcovptot + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemcpyAsync(dp.f.pfplsl + n2h * b0, h->pfplsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemcpyAsync(dp.f.pfplsn + n2h * b0, h->pfplsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemcpyAsync(dp.f.pfhpsl + n2h * b0, h->pfhpsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
+    CK(cudaMemcpyAsync(dp.f.pfhpsn + n2h * b0, h->pfhpsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
   }
   return 0;
 }
@@ -224,17 +179,17 @@ int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, i
 // anyone").
 int download_outputs(const cloudsc2_fields *h, const DevProblem &dp, bool loc_last) {
   const size_t D = sizeof(double), n2 = dp.n2, pitch = CLOUDSC2_NSTATE * dp.n2 * D;
-  CK(cudaMemcpy2DAsync(h->b_loc, pitch, dp.f.b_loc, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpy2DAsync(h->b_loc + 2 * n2, pitch, dp.f.b_loc + 2 * n2, pitch, 3 * n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpy2DAsync(h->b_loc, pitch, dp.f.b_loc, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpy2DAsync(h->b_loc + 2 * n2, pitch, dp.f.b_loc + 2 * n2, pitch, 3 * n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, G.stream));
   if (loc_last)
-    CK(cudaMemcpy2DAsync(h->b_loc + 7 * n2, pitch, dp.f.b_loc + 7 * n2, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(h->pa, dp.f.pa, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(h->pcovptot, dp.f.pcovptot, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(h->pfplsl, dp.f.pfplsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(h->pfplsn, dp.f.pfplsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(h->pfhpsl, dp.f.pfhpsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaMemcpyAsync(h->pfhpsn, dp.f.pfhpsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpy2DAsync(h->b_loc + 7 * n2, pitch, dp.f.b_loc + 7 * n2, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(h->pa, dp.f.pa, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(h->pcovptot, dp.f.pcovptot, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(h->pfplsl, dp.f.pfplsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(h->pfplsn, dp.f.pfplsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(h->pfhpsl, dp.f.pfhpsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaMemcpyAsync(h->pfhpsn, dp.f.pfhpsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 
@@ -252,7 +207,7 @@ int host_worker_threads() {
 // Device-side aliases of page-locked, mapped host arrays; false if any array is not mapped.
 bool map_host_fields(const cloudsc2_fields &h, cloudsc2_fields &d) {
   int can = 0;
-  if (cudaDeviceGetAttribute(&can, cudaDevAttrCanMapHostMemory, g.device) != cudaSuccess || !can) return false;
+  if (cudaDeviceGetAttribute(&can, cudaDevAttrCanMapHostMemory, G.device) != cudaSuccess || !can) return false;
   auto map = [](const void *p, void **out) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -279,94 +234,28 @@ bool map_host_fields(const cloudsc2_fields &h, cloudsc2_fields &d) {
 
 // context access for the per-block Fortran-ABI shims (cloudsc2_fortran_shims.cu)
 int csc2_shim_context(KConst *kc, double ptsphy, int klev, cudaStream_t *stream, long long *launches) {
-  if (!g.init || klev != g.klev) return 1;
+  // called from the host's OpenMP worker threads: make the context's device current on this thread
+  if (csc2_require_init() || klev != G.klev) return 1;
   *kc = make_kconst(ptsphy);
-  *stream = g.stream;
-  *launches = g.launches;
+  *stream = G.stream;
+  *launches = G.launches;
   return 0;
 }
-void csc2_shim_count_launch() { g.launches += 1; }
+void csc2_shim_count_launch() { G.launches += 1; }
 
 extern "C" {
-
-const char *cloudsc2_gpu_last_error(void) { return g_err; }
-
-int cloudsc2_gpu_available(void) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
-  return n > 0 ? 1 : 0;
-}
-
-int cloudsc2_gpu_device_count(void) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
-  return n;
-}
-
-long long cloudsc2_gpu_launch_count(void) { return g.launches; }
-
-int cloudsc2_gpu_init(const cloudsc2_params *params, int klev, const double *ceta, int device) {
-  if (!params || !ceta) return fail(3, "cloudsc2_gpu_init: NULL argument");
-  if (klev < 2 || klev > CSC2_KLEV_MAX) return fail(3, "klev=%d outside [2,%d]", klev, CSC2_KLEV_MAX);
-  // Only the configuration the three dwarf programs run is implemented on the device
-  // (cloudsc2_{nl,tl,ad}/dwarf_cloudsc.F90:105-107; LDRAIN1D = .FALSE. in every driver).
-  if (!params->lphylin) return fail(4, "LPHYLIN=.FALSE. is not supported (the dwarf forces .TRUE.)");
-  if (params->levapls2 || params->ldrain1d)
-    return fail(4, "LEVAPLS2/LDRAIN1D=.TRUE. (precipitation evaporation) is not supported");
-  if (!cloudsc2_gpu_available()) return fail(5, "no CUDA device available (there is no CPU fallback)");
-  if (g.init) cloudsc2_gpu_finalize();
-  CK(cudaSetDevice(device));
-  g.device = device;
-  g.prm = *params;
-  g.klev = klev;
-  std::memcpy(g.ceta, ceta, sizeof(double) * klev);
-  g.kwin0 = 0; g.kwin1 = -1;
-  bool any = false;
-  for (int jk = 0; jk < klev - 1; ++jk) {        // DO JK=1,KLEV-1 (cloudsc2.F90:318)
-    if (ceta[jk] > 0.1 && ceta[jk] < 0.4) {
-      if (!any) g.kwin0 = jk;
-      g.kwin1 = jk;
-      any = true;
-    }
-  }
-  for (int jk = 0; jk < klev; ++jk)              // cloudsc2.F90:266, ZSCAL = 0.9 (:172)
-    g.zscalm[jk] = 0.9 * std::pow(std::max(ceta[jk] - 0.2, 1.e-12), 0.2);
-  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  for (int i = 0; i < kStreams; ++i) CK(cudaStreamCreateWithFlags(&g.pipe[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&g.ev[i]));
-  {
-    // per-level constants -> __constant__ tables of the three kernel translation units
-    std::vector<double> sq(klev);
-    for (int k = 0; k < klev; ++k) sq[k] = std::sqrt(std::max(1.0 - ceta[k], 0.0));   // cloudsc2.F90:398
-    CK(csc2_upload_levels_nl(g.ceta, g.zscalm, sq.data(), klev, g.stream));
-    CK(csc2_upload_levels_tl(g.ceta, g.zscalm, sq.data(), klev, g.stream));
-    CK(csc2_upload_levels_ad(g.ceta, g.zscalm, sq.data(), klev, g.stream));
-  }
-  g.launches = 0;
-  g.init = true;
-  return 0;
-}
-
-int cloudsc2_gpu_finalize(void) {
-  if (!g.init) return 0;
-  cudaSetDevice(g.device);
-  cudaDeviceSynchronize();
-  g.in.release(); g.out.release(); g.work.release(); g.work2.release(); g.res.release();
-  if (g.stream) cudaStreamDestroy(g.stream);
-  for (int i = 0; i < kStreams; ++i) if (g.pipe[i]) cudaStreamDestroy(g.pipe[i]);
-  for (int i = 0; i < 4; ++i) if (g.ev[i]) cudaEventDestroy(g.ev[i]);
-  g.stream = nullptr;
-  for (int i = 0; i < kStreams; ++i) g.pipe[i] = nullptr;
-  for (int i = 0; i < 4; ++i) g.ev[i] = nullptr;
-  g.init = false;
-  return 0;
-}
+int csc2_nl_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                     double *elapsed_kernel_s, double *elapsed_total_s);
+int csc2_tlad_host_one(bool is_ad, int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                       const cloudsc2_incr_in *a, const cloudsc2_incr_out *b);
+int csc2_taylor_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                         double znormg[10], double *ratios_blk);
+int csc2_adtest_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                         double *znormg, double *norms_col);
 
 /* ---- memory helpers ------------------------------------------------------------------ */
 int cloudsc2_gpu_malloc(void **ptr, unsigned long long bytes) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   CK(cudaMalloc(ptr, bytes));
   return 0;
 }
@@ -376,27 +265,27 @@ int cloudsc2_gpu_free(void *ptr) { CK(cudaFree(ptr)); return 0; }
 // not synchronise -- a cudaMemset of an output array could then land after the kernel that was
 // launched later on the library stream (seen at NGPTOT = 1.3 M: zeroed flux arrays).
 int cloudsc2_gpu_memcpy_h2d(void *dst, const void *src, unsigned long long bytes) {
-  if (int rc = require_init()) return rc;
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  if (int rc = csc2_require_init()) return rc;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 int cloudsc2_gpu_memcpy_d2h(void *dst, const void *src, unsigned long long bytes) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   CK(cudaDeviceSynchronize());      // results may have been produced on a caller stream
-  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 int cloudsc2_gpu_memset(void *dst, int value, unsigned long long bytes) {
-  if (int rc = require_init()) return rc;
-  CK(cudaMemsetAsync(dst, value, bytes, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  if (int rc = csc2_require_init()) return rc;
+  CK(cudaMemsetAsync(dst, value, bytes, G.stream));
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 int cloudsc2_gpu_host_alloc(void **ptr, unsigned long long bytes) {
-  if (int rc = require_init()) return rc;
-  if (!ptr) return fail(3, "cloudsc2_gpu_host_alloc: NULL argument");
+  if (int rc = csc2_require_init()) return rc;
+  if (!ptr) return csc2_fail(3, "cloudsc2_gpu_host_alloc: NULL argument");
   CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
   return 0;
 }
@@ -405,7 +294,7 @@ int cloudsc2_gpu_host_free(void *ptr) {
   return 0;
 }
 int cloudsc2_gpu_host_register(void *ptr, unsigned long long bytes) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   return 0;
 }
@@ -414,41 +303,45 @@ int cloudsc2_gpu_host_unregister(void *ptr) {
   return 0;
 }
 int cloudsc2_gpu_sync(void) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   CK(cudaDeviceSynchronize());     // library streams and any caller stream handed to the _dev entries
   return 0;
 }
 
 int cloudsc2_gpu_satur(long long n, const double *pap, const double *pt, double *pqsat) {
-  if (int rc = require_init()) return rc;
-  if (!pap || !pt || !pqsat || n <= 0) return fail(3, "bad arguments to cloudsc2_gpu_satur");
-  if (int rc = g.work.reserve(3 * (size_t)n * sizeof(double))) return rc;
-  double *d_pap = g.work.d(), *d_pt = d_pap + n, *d_q = d_pt + n;
-  CK(cudaMemcpyAsync(d_pap, pap, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(cudaMemcpyAsync(d_pt, pt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(csc2_launch_satur(make_kconst(1.0), d_pap, d_pt, d_q, n, g.stream));
-  g.launches += 1;
-  CK(cudaMemcpyAsync(pqsat, d_q, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  if (int rc = csc2_require_init()) return rc;
+  if (!pap || !pt || !pqsat || n <= 0) return csc2_fail(3, "bad arguments to cloudsc2_gpu_satur");
+  if (int rc = G.work.reserve(3 * (size_t)n * sizeof(double))) return rc;
+  double *d_pap = G.work.d(), *d_pt = d_pap + n, *d_q = d_pt + n;
+  if (int rc = scratch_begin(G.stream)) return rc;
+  CK(cudaMemcpyAsync(d_pap, pap, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  CK(cudaMemcpyAsync(d_pt, pt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  CK(csc2_launch_satur(make_kconst(1.0), d_pap, d_pt, d_q, n, G.stream));
+  G.launches += 1;
+  CK(cudaMemcpyAsync(pqsat, d_q, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  if (int rc = scratch_end(G.stream)) return rc;
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 
 int cloudsc2_gpu_validate_slabs_dev(const double *ref_src, int nlon, const double *field, int nproma,
                                     int nlev, int ndim, long long blk_stride, int ngptot,
                                     long long gcol0, double out[5]) {
-  if (int rc = require_init()) return rc;
-  if (!ref_src || !field || !out) return fail(3, "NULL argument to cloudsc2_gpu_validate_dev");
+  if (int rc = csc2_require_init()) return rc;
+  if (!ref_src || !field || !out) return csc2_fail(3, "NULL argument to cloudsc2_gpu_validate_dev");
   if (nlon <= 0 || nproma <= 0 || nlev <= 0 || ndim <= 0 || ngptot <= 0 || gcol0 < 0 ||
       blk_stride < (long long)nproma * nlev * ndim)
-    return fail(3, "bad dimensions in cloudsc2_gpu_validate_dev");
-  if (int rc = g.res.reserve(csc2_validate_scratch_bytes() + 8 * sizeof(double))) return rc;
-  double *d_out = g.res.d();
+    return csc2_fail(3, "bad dimensions in cloudsc2_gpu_validate_dev");
+  if (int rc = G.res.reserve(csc2_validate_scratch_bytes() + 8 * sizeof(double))) return rc;
+  double *d_out = G.res.d();
   void *scratch = d_out + 8;
+  if (int rc = scratch_begin(G.stream)) return rc;
   CK(csc2_launch_validate(ref_src, nlon, field, nproma, (long long)nlev * ndim, blk_stride, ngptot,
-                          nblocks_of(ngptot, nproma), gcol0, scratch, d_out, g.stream));
-  g.launches += 2;
-  CK(cudaMemcpyAsync(out, d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+                          nblocks_of(ngptot, nproma), gcol0, scratch, d_out, G.stream));
+  G.launches += 2;
+  CK(cudaMemcpyAsync(out, d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  if (int rc = scratch_end(G.stream)) return rc;
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 
@@ -460,25 +353,29 @@ int cloudsc2_gpu_validate_dev(const double *ref_src, int nlon, const double *fie
 
 int cloudsc2_gpu_set_option(const char *name, int value) {
   opts.load();
-  if (!name) return fail(3, "option name is NULL");
+  if (!name) return csc2_fail(3, "option name is NULL");
   if (!strcmp(name, "e2e_mode")) { opts.e2e_mode = value; return 0; }
   if (!strcmp(name, "e2e_chunk_mb") && value > 0) { opts.e2e_chunk_mb = value; return 0; }
   if (!strcmp(name, "e2e_host_derive")) { opts.e2e_host_derive = value; return 0; }
   if (!strcmp(name, "ad_have_trajectory")) { opts.ad_have_trajectory = value != 0; return 0; }
-  if (!strcmp(name, "nl_variant")) { csc2_set_nl_variant(value); return 0; }
-  return fail(3, "unknown option '%s' (or bad value %d)", name, value);
+#ifdef CSC2_EXPERIMENTS
+  if (!strcmp(name, "nl_variant")) { csc2_set_nl_variant(value); return 0; }   // tools/probes builds only
+#endif
+  return csc2_fail(3, "unknown option '%s' (or bad value %d)", name, value);
 }
 
 int cloudsc2_gpu_math_probe(int fn, const double *x, double *y, int n) {
-  if (int rc = require_init()) return rc;
-  if (!x || !y || n <= 0 || fn < 0 || fn > 5) return fail(3, "bad arguments to cloudsc2_gpu_math_probe");
-  if (int rc = g.work.reserve(2 * (size_t)n * sizeof(double))) return rc;
-  double *dx = g.work.d(), *dy = dx + n;
-  CK(cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-  CK(csc2_launch_math_probe(fn, dx, dy, n, g.stream));
-  g.launches += 1;
-  CK(cudaMemcpyAsync(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  if (int rc = csc2_require_init()) return rc;
+  if (!x || !y || n <= 0 || fn < 0 || fn > 5) return csc2_fail(3, "bad arguments to cloudsc2_gpu_math_probe");
+  if (int rc = G.work.reserve(2 * (size_t)n * sizeof(double))) return rc;
+  double *dx = G.work.d(), *dy = dx + n;
+  if (int rc = scratch_begin(G.stream)) return rc;
+  CK(cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  CK(csc2_launch_math_probe(fn, dx, dy, n, G.stream));
+  G.launches += 1;
+  CK(cudaMemcpyAsync(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
+  if (int rc = scratch_end(G.stream)) return rc;
+  CK(cudaStreamSynchronize(G.stream));
   return 0;
 }
 
@@ -486,16 +383,16 @@ int cloudsc2_gpu_math_probe(int fn, const double *x, double *y, int n) {
 
 int cloudsc2_gpu_nl_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,
                         const double *pqs, void *stream) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(dev)) return rc;
   Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
   TrajIn in; TrajOut out;
   views_from_fields(*dev, nproma, klev, in, out);
   in.pqs = pqs;
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : G.stream;
   CK(csc2_launch_nl(make_kconst(ptsphy), geo, in, out, s));
-  g.launches += 1;
+  G.launches += 1;
   return 0;
 }
 
@@ -503,9 +400,9 @@ int cloudsc2_gpu_nl_dev(int nproma, int klev, int ngptot, double ptsphy, const c
 // chunks on three streams so that H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1
 // overlap (PCIe is full duplex); only the slabs the kernel touches cross the bus
 // (PCLV 2 of 5 species, B_CML 4 of 8 slabs, B_LOC 5 of 8 slabs).
-int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
-                    double *elapsed_kernel_s, double *elapsed_total_s) {
-  if (int rc = require_init()) return rc;
+int csc2_nl_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                     double *elapsed_kernel_s, double *elapsed_total_s) {
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   const int nblocks = nblocks_of(ngptot, nproma);
@@ -522,13 +419,13 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
       Geom geo{nproma, klev, ngptot, nblocks};
       TrajIn in; TrajOut out;
       views_from_fields(d, nproma, klev, in, out);
-      CK(cudaEventRecord(g.ev[0], g.stream));
-      CK(csc2_launch_nl(make_kconst(ptsphy), geo, in, out, g.stream));
-      g.launches += 1;
-      CK(cudaEventRecord(g.ev[1], g.stream));
-      CK(cudaEventSynchronize(g.ev[1]));
+      CK(cudaEventRecord(G.ev[0], G.stream));
+      CK(csc2_launch_nl(make_kconst(ptsphy), geo, in, out, G.stream));
+      G.launches += 1;
+      CK(cudaEventRecord(G.ev[1], G.stream));
+      CK(cudaEventSynchronize(G.ev[1]));
       float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+      CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
       if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
       if (elapsed_kernel_s) *elapsed_kernel_s = ms * 1e-3;
       return 0;
@@ -539,9 +436,9 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
   // compact device layout: [8 plain | paph | cld(2) | cml(4)] and [loc(5) | pa | pcov | 4 flux]
   const size_t in_blk = 8 * n2 + n2h + 2 * n2 + 4 * n2;
   const size_t out_blk = 5 * n2 + 2 * n2 + 4 * n2h;
-  if (int rc = g.in.reserve(in_blk * nblocks * D)) return rc;
-  if (int rc = g.out.reserve(out_blk * nblocks * D)) return rc;
-  double *di = g.in.d(), *dout = g.out.d();
+  if (int rc = G.in.reserve(in_blk * nblocks * D)) return rc;
+  if (int rc = G.out.reserve(out_blk * nblocks * D)) return rc;
+  double *di = G.in.d(), *dout = G.out.d();
   const size_t nb = nblocks;
   double *d_pt = di, *d_pq = d_pt + n2 * nb, *d_pap = d_pq + n2 * nb, *d_plu = d_pap + n2 * nb,
          *d_plude = d_plu + n2 * nb, *d_pmfu = d_plude + n2 * nb, *d_pmfd = d_pmfu + n2 * nb,
@@ -603,12 +500,12 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
     CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i]));
     CK(cudaEventCreateWithFlags(&dn[i], cudaEventDisableTiming));
   }
-  CK(cudaEventRecord(g.ev[0], g.stream));
-  for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(g.pipe[i], g.ev[0], 0));
+  CK(cudaEventRecord(G.ev[0], G.stream));
+  for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(G.pipe[i], G.ev[0], 0));
 
   size_t b0 = 0;
   for (size_t ic = 0; ic < nchunks; b0 += plan[ic], ++ic) {
-    cudaStream_t s = g.pipe[ic % kStreams];
+    cudaStream_t s = G.pipe[ic % kStreams];
     const size_t cb = plan[ic];
     auto h2d = [&](double *dst, const double *src, size_t per_blk) {
       return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyHostToDevice, s);
@@ -648,7 +545,7 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
     CK(cudaEventRecord(k0[ic], s));
     CK(csc2_launch_nl(kc, geo, in, out, s));
     CK(cudaEventRecord(k1[ic], s));
-    g.launches += 1;
+    G.launches += 1;
 
     auto d2h = [&](double *dst, const double *src, size_t per_blk) {
       return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyDeviceToHost, s);
@@ -668,7 +565,7 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
   }
   if (derive) {
     // host side of the derived outputs, chunk by chunk behind the D2H of PFPLSL / PFPLSN
-    const double rlvtt = g.prm.rlvtt, rlstt = g.prm.rlstt;
+    const double rlvtt = G.prm.rlvtt, rlstt = G.prm.rlstt;
     const int nthr = host_worker_threads();
     size_t cb0 = 0;
     for (size_t ic = 0; ic < nchunks; cb0 += plan[ic], ++ic) {
@@ -691,13 +588,13 @@ int cloudsc2_gpu_nl(int nproma, int klev, int ngptot, double ptsphy, const cloud
     }
   }
   for (int i = 0; i < kStreams; ++i) {
-    CK(cudaEventRecord(g.ev[2], g.pipe[i]));
-    CK(cudaStreamWaitEvent(g.stream, g.ev[2], 0));
+    CK(cudaEventRecord(G.ev[2], G.pipe[i]));
+    CK(cudaStreamWaitEvent(G.stream, G.ev[2], 0));
   }
-  CK(cudaEventRecord(g.ev[1], g.stream));
-  CK(cudaEventSynchronize(g.ev[1]));
+  CK(cudaEventRecord(G.ev[1], G.stream));
+  CK(cudaEventSynchronize(G.ev[1]));
   float ms = 0.f, kms = 0.f;
-  CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+  CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
   for (size_t i = 0; i < nchunks; ++i) {
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, k0[i], k1[i]));
@@ -720,19 +617,19 @@ static void inc_views(const cloudsc2_incr_in *a, const cloudsc2_incr_out *b, Inc
   dout.pfhpsn = b->pfhpsn; dout.pcovptot = b->pcovptot;
 }
 static int check_incr(const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
-  if (!a || !b) return fail(3, "increment struct pointer is NULL");
+  if (!a || !b) return csc2_fail(3, "increment struct pointer is NULL");
   const void *pa[] = {a->paph, a->pap, a->pq, a->pqs, a->pt, a->pl, a->pi, a->plude, a->plu, a->pmfu,
                       a->pmfd, a->gtent, a->gtenq, a->gtenl, a->gteni, a->psupsat};
   const void *pb[] = {b->tent, b->tenq, b->tenl, b->teni, b->pclc, b->pfplsl, b->pfplsn, b->pfhpsl,
                       b->pfhpsn, b->pcovptot};
-  for (const void *p : pa) if (!p) return fail(3, "a pointer in cloudsc2_incr_in is NULL");
-  for (const void *p : pb) if (!p) return fail(3, "a pointer in cloudsc2_incr_out is NULL");
+  for (const void *p : pa) if (!p) return csc2_fail(3, "a pointer in cloudsc2_incr_in is NULL");
+  for (const void *p : pb) if (!p) return csc2_fail(3, "a pointer in cloudsc2_incr_out is NULL");
   return 0;
 }
 
 int cloudsc2_gpu_tl_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,
                         const cloudsc2_incr_in *din_, const cloudsc2_incr_out *dout_, void *stream) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(dev)) return rc;
   if (int rc = check_incr(din_, dout_)) return rc;
@@ -742,15 +639,15 @@ int cloudsc2_gpu_tl_dev(int nproma, int klev, int ngptot, double ptsphy, const c
   out.loc_last = nullptr;
   inc_views(din_, dout_, din, dout);
   TLOpts opt{0.0, 0, nullptr, nullptr, 0};
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : G.stream;
   CK(csc2_launch_tl(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
-  g.launches += 1;
+  G.launches += 1;
   return 0;
 }
 
 int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *dev,
                         const cloudsc2_incr_in *din_, const cloudsc2_incr_out *dout_, void *stream) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(dev)) return rc;
   if (int rc = check_incr(din_, dout_)) return rc;
@@ -760,20 +657,22 @@ int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const c
   out.loc_last = nullptr;
   inc_views(din_, dout_, din, dout);
   const long long ncp = pad_cols((long long)geo.nblocks * nproma);
-  if (int rc = g.work.reserve((size_t)2 * klev * ncp * sizeof(double))) return rc;
+  if (int rc = G.work.reserve((size_t)2 * klev * ncp * sizeof(double))) return rc;
   opts.load();
   // option "ad_have_trajectory": dev->pfplsl / pfplsn already hold the trajectory of these inputs
-  ADOpts opt{0.0, 0, nullptr, g.work.d(), ncp, 1, opts.ad_have_trajectory};
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+  ADOpts opt{0.0, 0, nullptr, G.work.d(), ncp, 1, opts.ad_have_trajectory};
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : G.stream;
+  if (int rc = scratch_begin(s)) return rc;
   CK(csc2_launch_ad(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
-  g.launches += opt.have_traj ? 1 : 2;      // forward (NL + check-points) and reverse sweep
+  if (int rc = scratch_end(s)) return rc;
+  G.launches += opt.have_traj ? 1 : 2;      // forward (NL + check-points) and reverse sweep
   return 0;
 }
 
 // Host-pointer wrappers: stage everything on the device in the reference layout.
-static int tlad_host(bool is_ad, int nproma, int klev, int ngptot, double ptsphy,
-                     const cloudsc2_fields *h, const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
-  if (int rc = require_init()) return rc;
+int csc2_tlad_host_one(bool is_ad, int nproma, int klev, int ngptot, double ptsphy,
+                       const cloudsc2_fields *h, const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   if (int rc = check_incr(a, b)) return rc;
@@ -782,8 +681,8 @@ static int tlad_host(bool is_ad, int nproma, int klev, int ngptot, double ptsphy
   opts.load();
   if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks, dp, is_ad && opts.ad_have_trajectory)) return rc;
   const size_t tot = 15 * dp.n2b + dp.n2hb + 6 * dp.n2b + 4 * dp.n2hb;
-  if (int rc = g.work2.reserve(tot * sizeof(double))) return rc;
-  double *p = g.work2.d();
+  if (int rc = G.work2.reserve(tot * sizeof(double))) return rc;
+  double *p = G.work2.d();
   cloudsc2_incr_in da; cloudsc2_incr_out db;
   struct Item { double **dev; double *host; size_t n; };
   std::vector<Item> items = {
@@ -799,47 +698,39 @@ static int tlad_host(bool is_ad, int nproma, int klev, int ngptot, double ptsphy
       {&db.pfhpsn, b->pfhpsn, dp.n2hb}};
   for (auto &it : items) {
     *it.dev = p;
-    CK(cudaMemcpyAsync(p, it.host, it.n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(p, it.host, it.n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
     p += it.n;
   }
   int rc = is_ad ? cloudsc2_gpu_ad_dev(nproma, klev, ngptot, ptsphy, &dp.f, &da, &db, nullptr)
                  : cloudsc2_gpu_tl_dev(nproma, klev, ngptot, ptsphy, &dp.f, &da, &db, nullptr);
   if (rc) return rc;
   for (auto &it : items)
-    CK(cudaMemcpyAsync(it.host, *it.dev, it.n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(it.host, *it.dev, it.n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
   return download_outputs(h, dp, false);
 }
-int cloudsc2_gpu_tl(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
-                    const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
-  return tlad_host(false, nproma, klev, ngptot, ptsphy, h, a, b);
-}
-int cloudsc2_gpu_ad(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
-                    const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
-  return tlad_host(true, nproma, klev, ngptot, ptsphy, h, a, b);
-}
-
 /* ---- Taylor test ----------------------------------------------------------------------- */
 
 int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
                                const cloudsc2_fields *dev, double znormg[10], double *ratios_blk) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(dev)) return rc;
-  if (!znormg) return fail(3, "znormg is NULL");
+  if (!znormg) return csc2_fail(3, "znormg is NULL");
   Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
   const long long ncp = pad_cols((long long)geo.nblocks * nproma);
   // scratch: tlsum[10][ncp] | diffsum[10][10][ncp]
-  if (int rc = g.work.reserve((size_t)110 * ncp * sizeof(double))) return rc;
+  if (int rc = G.work.reserve((size_t)110 * ncp * sizeof(double))) return rc;
   // results: znormg[10] | degenerate flag | ratios[nblocks][10]
-  if (int rc = g.res.reserve((size_t)(16 + 10 * (size_t)geo.nblocks) * sizeof(double))) return rc;
-  double *tlsum = g.work.d(), *diffsum = tlsum + 10 * ncp;
-  double *d_z = g.res.d();
+  if (int rc = G.res.reserve((size_t)(16 + 10 * (size_t)geo.nblocks) * sizeof(double))) return rc;
+  double *tlsum = G.work.d(), *diffsum = tlsum + 10 * ncp;
+  double *d_z = G.res.d();
   int *d_deg = reinterpret_cast<int *>(d_z + 10);
   double *d_rat = d_z + 16;
   const KConst kc = make_kconst(ptsphy);
   TrajIn in; TrajOut out;
   views_from_fields(*dev, nproma, klev, in, out);
-  cudaStream_t s = g.stream;
+  cudaStream_t s = G.stream;
+  if (int rc = scratch_begin(s)) return rc;
   // baseline NL (cloudsc_driver_tl_mod.F90:135-151)
   CK(csc2_launch_nl(kc, geo, in, out, s));
   // TL with dx = 0.01 x (:156-194); re-emits the trajectory outputs like the reference
@@ -852,22 +743,34 @@ int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
   CK(csc2_launch_taylor_nl(kc, geo, in, out, diffsum, ncp, s));
   // ERROR_NORM and max over blocks (:233-252)
   CK(csc2_launch_taylor_finalize(geo, tlsum, diffsum, ncp, d_rat, d_z, d_deg, s));
-  g.launches += 4;
+  G.launches += 4;
+  if (G.comm) {
+    // reduction(max:znormg) over the ranks of the communicator (cloudsc_driver_tl_mod.F90:125), on the
+    // device-resident values: non-finite ratios become a huge sentinel first (MAX drops NaN), the
+    // count of degenerate blocks travels as a double and is summed
+    CK(csc2_launch_norms_prepare(d_z, 10, d_deg, d_z + 11, s));
+    G.launches += 1;
+    if (int rc = csc2_allreduce(G, d_z, 10, 0, s)) return rc;
+    if (int rc = csc2_allreduce(G, d_z + 11, 1, 2, s)) return rc;
+  }
   double hz[16];
   CK(cudaMemcpyAsync(hz, d_z, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (ratios_blk)
     CK(cudaMemcpyAsync(ratios_blk, d_rat, (size_t)10 * geo.nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (int rc = scratch_end(s)) return rc;
   CK(cudaStreamSynchronize(s));
   for (int i = 0; i < 10; ++i) znormg[i] = hz[i];
   int deg;
   std::memcpy(&deg, &hz[10], sizeof(int));
-  if (deg) return fail(3, "TL is totally wrong: %d block(s) with ZNORM==0 or ZCOUNT==0 (cloudsc_driver_tl_mod.F90:247)", deg);
+  if (G.comm) deg = (int)hz[11];
+  // distinct from the argument errors (3): the results are valid numbers, the reference STOPs here
+  if (deg) return csc2_fail(6, "TL is totally wrong: %d block(s) with ZNORM==0 or ZCOUNT==0 (cloudsc_driver_tl_mod.F90:247)", deg);
   return 0;
 }
 
-int cloudsc2_gpu_tl_taylor(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
-                           double znormg[10], double *ratios_blk) {
-  if (int rc = require_init()) return rc;
+int csc2_taylor_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+                         double znormg[10], double *ratios_blk) {
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   DevProblem dp;
@@ -881,28 +784,29 @@ int cloudsc2_gpu_tl_taylor(int nproma, int klev, int ngptot, double ptsphy, cons
 
 int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
                              const cloudsc2_fields *dev, double *znormg, double *norms_col) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(dev)) return rc;
-  if (!znormg) return fail(3, "znormg is NULL");
+  if (!znormg) return csc2_fail(3, "znormg is NULL");
   Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
   const size_t n2b = (size_t)nproma * klev * geo.nblocks, n2hb = (size_t)nproma * (klev + 1) * geo.nblocks;
   const long long ncp = pad_cols((long long)geo.nblocks * nproma);
   // scratch: y (6 n2b + 4 n2hb) | ckpt 2*klev*ncp | n1[ncp] | n2[ncp]
   const size_t ny = 6 * n2b + 4 * n2hb;
-  if (int rc = g.work.reserve((ny + (size_t)2 * klev * ncp + 2 * ncp) * sizeof(double))) return rc;
-  if (int rc = g.res.reserve((size_t)(16 + 3 * (size_t)ncp) * sizeof(double))) return rc;
-  double *y = g.work.d();
+  if (int rc = G.work.reserve((ny + (size_t)2 * klev * ncp + 2 * ncp) * sizeof(double))) return rc;
+  if (int rc = G.res.reserve((size_t)(16 + 3 * (size_t)ncp) * sizeof(double))) return rc;
+  double *y = G.work.d();
   IncOut dout;
   dout.tent = y; dout.tenq = y + n2b; dout.tenl = y + 2 * n2b; dout.teni = y + 3 * n2b;
   dout.pclc = y + 4 * n2b; dout.pcovptot = y + 5 * n2b; dout.pfplsl = y + 6 * n2b;
   dout.pfplsn = dout.pfplsl + n2hb; dout.pfhpsl = dout.pfplsn + n2hb; dout.pfhpsn = dout.pfhpsl + n2hb;
   double *ckpt = y + ny, *n1 = ckpt + (size_t)2 * klev * ncp, *n2 = n1 + ncp;
-  double *d_z = g.res.d(), *d_norms = d_z + 16;
+  double *d_z = G.res.d(), *d_norms = d_z + 16;
   const KConst kc = make_kconst(ptsphy);
   TrajIn in; TrajOut out;
   views_from_fields(*dev, nproma, klev, in, out);
-  cudaStream_t s = g.stream;
+  cudaStream_t s = G.stream;
+  if (int rc = scratch_begin(s)) return rc;
   // the driver zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV) of every block (:112-113)
   CK(cudaMemsetAsync(out.pcovptot, 0, n2b * sizeof(double), s));
   {
@@ -920,19 +824,23 @@ int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
   ADOpts aopt{0.01, 1, n2, ckpt, ncp, 1, 1};
   CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
   CK(csc2_launch_ad_finalize(geo, n1, n2, d_norms, d_z, s));
-  g.launches += 3;      // TL, AD reverse sweep, finalize
+  G.launches += 3;      // TL, AD reverse sweep, finalize
+  // reduction(max:znormg) over the ranks (cloudsc_driver_ad_mod.F90:107); k_ad_finalize has already
+  // mapped non-finite norms to a huge value
+  if (int rc = csc2_allreduce(G, d_z, 1, 0, s)) return rc;
   double hz;
   CK(cudaMemcpyAsync(&hz, d_z, sizeof(double), cudaMemcpyDeviceToHost, s));
   if (norms_col)
     CK(cudaMemcpyAsync(norms_col, d_norms, (size_t)3 * ngptot * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (int rc = scratch_end(s)) return rc;
   CK(cudaStreamSynchronize(s));
   *znormg = hz;
   return 0;
 }
 
-int cloudsc2_gpu_ad_test(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
+int csc2_adtest_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
                          double *znormg, double *norms_col) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   DevProblem dp;
@@ -974,12 +882,12 @@ int cloudsc2_adjoint_verdict(double znormg) { return znormg < 10000.0 ? 1 : 0; }
 
 int cloudsc2_gpu_expand_shard_dev(const double *src, int nlon, int nlev, int ndim, double *dst,
                                   int nproma, int ngptot, long long gcol0, void *stream) {
-  if (int rc = require_init()) return rc;
+  if (int rc = csc2_require_init()) return rc;
   if (!src || !dst || nlon <= 0 || nlev <= 0 || ndim <= 0 || nproma <= 0 || ngptot <= 0 || gcol0 < 0)
-    return fail(3, "cloudsc2_gpu_expand_dev: bad argument");
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    return csc2_fail(3, "cloudsc2_gpu_expand_dev: bad argument");
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : G.stream;
   CK(csc2_launch_expand(src, nlon, (long long)nlev * ndim, dst, nproma, ngptot, nblocks_of(ngptot, nproma), gcol0, s));
-  g.launches += 1;
+  G.launches += 1;
   return 0;
 }
 int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim, double *dst, int nproma,

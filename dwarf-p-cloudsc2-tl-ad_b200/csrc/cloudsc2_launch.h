@@ -75,6 +75,10 @@ cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *
                                  long long rows, long long blk_stride, int ngptot, int nblocks,
                                  long long gcol0, void *scratch, double *out5, cudaStream_t s);
 
+// Cross-rank reductions of the test norms (cloudsc2_validate_kernel.cu): see k_norms_prepare / k_fill.
+cudaError_t csc2_launch_norms_prepare(double *z, int n, const int *deg, double *deg_as_double, cudaStream_t s);
+cudaError_t csc2_launch_fill(double *z, int n, double v, cudaStream_t s);
+
 // SATUR alone, elementwise over n points (device pointers).
 cudaError_t csc2_launch_satur(const KConst &c, const double *pap, const double *pt, double *pqsat,
                               long long n, cudaStream_t s);

@@ -88,15 +88,18 @@ __device__ __forceinline__ LevIn csc2_read_level(const double *d, int jk, int kl
 }
 
 // Opt a kernel in to more than 48 kB of dynamic shared memory, once per (kernel, device): the
-// attribute is per device, and cloudsc2_gpu_init may move the library to another device.
-// `done_for_device` is a static of the calling launcher (one per kernel instantiation).
+// attribute is per device, and one process may drive several devices from several threads.
+// `flags` is a static of the calling launcher (one per kernel instantiation): bit d = done on device d.
+#include <atomic>
+typedef std::atomic<unsigned long long> CSC2_SMEM_FLAGS;
 template <typename K>
-static inline cudaError_t csc2_allow_smem(K kern, size_t smem, int &done_for_device) {
+static inline cudaError_t csc2_allow_smem(K kern, size_t smem, CSC2_SMEM_FLAGS &flags) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev == done_for_device) return cudaSuccess;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (flags.load(std::memory_order_acquire) & bit) return cudaSuccess;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) done_for_device = dev;
+  if (e == cudaSuccess) flags.fetch_or(bit, std::memory_order_release);
   return e;
 }

@@ -344,7 +344,7 @@ static cudaError_t launch_tl_k(const KConst &c, const Geom &g, const TrajIn &in,
   const int grid = (int)((ncol + TNT - 1) / TNT);
   const size_t smem = (size_t)STAGES * TL_NF * TNT * sizeof(double);
   auto kern = k_cloudsc2_tl<ONFLY, STAGES, RV, LREG, MINB, TNT>;
-  static int smem_ok_on_device = -1;
+  static CSC2_SMEM_FLAGS smem_ok_on_device{0};
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   kern<<<grid, TNT, smem, s>>>(c, g, in, out, din, dout, opt);
   return cudaGetLastError();
@@ -360,6 +360,7 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
     if (lreg) return launch_tl_k<ONFLY, 2, true, true>(c, g, in, out, din, dout, opt, grid, s);
     return launch_tl_k<ONFLY, 2, true, false>(c, g, in, out, din, dout, opt, grid, s);
   }
+#ifdef CSC2_EXPERIMENTS   // occupancy variants measured in DESIGN.md 3.3 (CSC2_TL_MINB); the product has one shape
   static const int minb = [] { const char *e = getenv("CSC2_TL_MINB"); return e ? atoi(e) : 2; }();
   if (minb == 8)   // 32-thread CTAs, 8 per SM = 8 warps at 255 registers (finer tail)
     return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 8, 32>(c, g, in, out, din, dout, opt, grid, s)
@@ -376,23 +377,21 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
     if (lreg) return launch_tl_k<ONFLY, STAGES, false, true, 3>(c, g, in, out, din, dout, opt, grid, s);
     return launch_tl_k<ONFLY, STAGES, false, false, 3>(c, g, in, out, din, dout, opt, grid, s);
   }
+#endif
   if (lreg) return launch_tl_k<ONFLY, STAGES, false, true>(c, g, in, out, din, dout, opt, grid, s);
   return launch_tl_k<ONFLY, STAGES, false, false>(c, g, in, out, din, dout, opt, grid, s);
 }
 
-static int g_tl_stages = 0;
-void csc2_set_tl_stages(int v) { g_tl_stages = v; }
 
 cudaError_t csc2_launch_tl(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            const IncIn &din, const IncOut &dout, const TLOpts &opt, cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + CSC2_TL_THREADS - 1) / CSC2_TL_THREADS);
-  if (g_tl_stages == 0) {
-    const char *e = getenv("CSC2_TL_STAGES");
-    g_tl_stages = e && atoi(e) == 3 ? 3 : 2;
-  }
   if (opt.pert_scale != 0.0) return launch_tl_variant<true, 2>(c, g, in, out, din, dout, opt, grid, s);
-  if (g_tl_stages == 3) return launch_tl_variant<false, 3>(c, g, in, out, din, dout, opt, grid, s);
+#ifdef CSC2_EXPERIMENTS
+  static const int stages = [] { const char *e = getenv("CSC2_TL_STAGES"); return e && atoi(e) == 3 ? 3 : 2; }();
+  if (stages == 3) return launch_tl_variant<false, 3>(c, g, in, out, din, dout, opt, grid, s);
+#endif
   return launch_tl_variant<false, 2>(c, g, in, out, din, dout, opt, grid, s);
 }
 
@@ -409,7 +408,7 @@ static cudaError_t launch_taylor_nl_k(const KConst &c, const Geom &g, const Traj
   const unsigned ncta = (unsigned)((ncol + NT - 1) / NT);
   const size_t smem = (size_t)2 * TY_NF * NT * sizeof(double);
   auto kern = k_taylor_nl<HAS_PQS, RV>;
-  static int smem_ok_on_device = -1;
+  static CSC2_SMEM_FLAGS smem_ok_on_device{0};
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok_on_device)) return e0;
   kern<<<ncta * 10u, NT, smem, s>>>(c, g, in, base, make_lambdas(), diffsum, ncol_pad);
   return cudaGetLastError();

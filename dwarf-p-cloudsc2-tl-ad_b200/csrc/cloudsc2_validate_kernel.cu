@@ -68,7 +68,9 @@ k_validate_partial(const double *__restrict__ ref_src, int nlon, const double *_
     s.vmax = fmax(s.vmax, v);
     if (col < ngptot) {
       const double ref = __ldg(ref_src + r * nlon + (gcol0 + col) % nlon);
-      const double d = fabs(v - ref);
+      // a NaN result must fail the validation: fmax / fmin drop NaN, so give it the largest error
+      const double d0 = fabs(v - ref);
+      const double d = (d0 == d0) ? d0 : 1.7976931348623157e308;
       s.maxerr = fmax(s.maxerr, d);
       s.sumerr += d;
       s.sumref += fabs(ref);
@@ -88,7 +90,35 @@ k_validate_final(const Stats *__restrict__ partial, int n, double *__restrict__ 
   }
 }
 
+// Before a cross-rank MAX (which drops NaN): non-finite norms become a huge sentinel, so that a rank
+// whose kernels produced NaN fails the test for everybody; the count of degenerate blocks (int) is
+// copied as a double so that it can be summed by the same collective.
+__global__ void k_norms_prepare(double *__restrict__ z, int n, const int *__restrict__ deg,
+                                double *__restrict__ deg_as_double) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    const double v = z[i];
+    if (!(fabs(v) <= 1.7976931348623157e308)) z[i] = 1.0e300;
+  }
+  if (i == 0 && deg && deg_as_double) *deg_as_double = (double)*deg;
+}
+
+// identity of MAX / MIN / SUM for a rank that owns no block
+__global__ void k_fill(double *__restrict__ z, int n, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = v;
+}
+
 }  // namespace
+
+cudaError_t csc2_launch_norms_prepare(double *z, int n, const int *deg, double *deg_as_double, cudaStream_t s) {
+  k_norms_prepare<<<1, 32, 0, s>>>(z, n, deg, deg_as_double);
+  return cudaGetLastError();
+}
+cudaError_t csc2_launch_fill(double *z, int n, double v, cudaStream_t s) {
+  k_fill<<<(n + 127) / 128, 128, 0, s>>>(z, n, v);
+  return cudaGetLastError();
+}
 
 size_t csc2_validate_scratch_bytes() { return (size_t)CSC2_VALIDATE_MAX_CTAS * sizeof(Stats); }
 

@@ -23,6 +23,40 @@ class Cloudsc2Error(RuntimeError):
     pass
 
 
+# cloudsc2_gpu_tl_taylor*: "TL is totally wrong" (cloudsc_driver_tl_mod.F90:247-249), distinct from
+# the argument errors (3)
+DEGENERATE_RC = 6
+
+
+def source_struct(src) -> tuple["_abi.Source", list]:
+    """struct cloudsc2_source view of a SourceColumns (the arrays are kept alive by the 2nd item)."""
+    s = _abi.Source()
+    s.klon, s.klev, s.ptsphy = src.klon, src.klev, src.ptsphy
+    keep = []
+    for n in ("pt", "pq", "pap", "paph", "plu", "plude", "pmfu", "pmfd", "pa", "psupsat", "pclv",
+              "tend_cml"):
+        a = np.ascontiguousarray(src.f[n], dtype=np.float64)
+        keep.append(a)
+        setattr(s, n, a.ctypes.data_as(_abi.c_double_p))
+    c = np.ascontiguousarray(src.ceta, dtype=np.float64)
+    keep.append(c)
+    s.ceta = c.ctypes.data_as(_abi.c_double_p)
+    return s, keep
+
+
+def reference_struct(ref: dict, klon: int, klev: int) -> tuple["_abi.Reference", list]:
+    """struct cloudsc2_reference from un-expanded reference columns: a dict with plude, pcovptot
+    (KLEV,KLON), pfplsl, pfplsn, pfhpsl, pfhpsn (KLEV+1,KLON) and tend_loc (8,KLEV,KLON)."""
+    r = _abi.Reference()
+    r.klon, r.klev = klon, klev
+    keep = []
+    for n in ("plude", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "tend_loc"):
+        a = np.ascontiguousarray(ref[n], dtype=np.float64)
+        keep.append(a)
+        setattr(r, n, a.ctypes.data_as(_abi.c_double_p))
+    return r, keep
+
+
 def gpu_available() -> bool:
     return bool(_abi.load_library().cloudsc2_gpu_available())
 
@@ -149,11 +183,18 @@ class Cloudsc2:
 
     _owner = None     # the object whose constants are currently loaded in the library
 
-    def __init__(self, params: _abi.Params, klev: int, ceta, device: int = 0):
+    def __init__(self, params: _abi.Params, klev: int, ceta, device: int = 0, ngpus: int | None = None,
+                 devices=None):
+        """device: one GPU (cloudsc2_gpu_init, what one rank of a process-per-GPU job uses);
+        ngpus / devices: a device set driven by this one process (cloudsc2_gpu_init_multi /
+        _init_devices): host-pointer and resident-state entries shard the blocks over the set and
+        all-reduce the norms with the library's own NCCL communicator."""
         self.lib = _abi.load_library()
         self.params = params
         self.klev = int(klev)
         self.device = int(device)
+        self.ngpus = None if ngpus is None else int(ngpus)
+        self.devices = None if devices is None else [int(d) for d in devices]
         self.ceta = np.ascontiguousarray(ceta, dtype=np.float64)
         self._launches = 0
         self._open = False
@@ -173,9 +214,16 @@ class Cloudsc2:
         if prev is not None:
             prev._launches += int(self.lib.cloudsc2_gpu_launch_count())
         Cloudsc2._owner = None
-        self._check(self.lib.cloudsc2_gpu_init(C.byref(self.params), self.klev,
-                                               self.ceta.ctypes.data_as(_abi.c_double_p),
-                                               self.device))
+        ceta = self.ceta.ctypes.data_as(_abi.c_double_p)
+        if self.devices is not None:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            rc = self.lib.cloudsc2_gpu_init_devices(C.byref(self.params), self.klev, ceta,
+                                                    len(self.devices), arr)
+        elif self.ngpus is not None:
+            rc = self.lib.cloudsc2_gpu_init_multi(C.byref(self.params), self.klev, ceta, self.ngpus)
+        else:
+            rc = self.lib.cloudsc2_gpu_init(C.byref(self.params), self.klev, ceta, self.device)
+        self._check(rc)
         Cloudsc2._owner = self
 
     def close(self):
@@ -279,7 +327,7 @@ class Cloudsc2:
         fn = self.lib.cloudsc2_gpu_tl_taylor_dev if dev else self.lib.cloudsc2_gpu_tl_taylor
         rc = fn(st.nproma, st.klev, st.ngptot, ptsphy if dev else st.ptsphy, C.byref(f),
                 z.ctypes.data_as(_abi.c_double_p), rb.ctypes.data_as(_abi.c_double_p))
-        if not (allow_degenerate and rc == 3):
+        if not (allow_degenerate and rc == DEGENERATE_RC):
             self._check(rc)
         return z, rb
 
@@ -294,6 +342,123 @@ class Cloudsc2:
         self._check(fn(st.nproma, st.klev, st.ngptot, ptsphy if dev else st.ptsphy, C.byref(f),
                        C.byref(zn), nc.ctypes.data_as(_abi.c_double_p)))
         return zn.value, nc
+
+    # -- device set / resident sharded state (cloudsc2_gpu_state_*) -------------------------------
+    def num_devices(self) -> int:
+        self._bind()
+        return int(self.lib.cloudsc2_gpu_num_devices())
+
+    def comm_info(self) -> tuple[int, int, int]:
+        """(rank, size, NCCL version) of the library's communicator."""
+        self._bind()
+        r, n, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self.lib.cloudsc2_gpu_comm_info(C.byref(r), C.byref(n), C.byref(v)))
+        return r.value, n.value, v.value
+
+    def select_device(self, index: int):
+        self._bind()
+        self._check(self.lib.cloudsc2_gpu_select_device(int(index)))
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.cloudsc2_gpu_comm_unique_id(buf, 128))
+        return buf.raw
+
+    def comm_init_rank(self, rank: int, nranks: int, uid: bytes):
+        """Join a job-wide NCCL communicator (one process per GPU): the test norms are then
+        all-reduced inside the library."""
+        self._bind()
+        self._check(self.lib.cloudsc2_gpu_comm_init_rank(int(rank), int(nranks), uid, len(uid)))
+
+    def state_load(self, src, nproma: int, ngptot: int):
+        """GLOBAL_STATE%LOAD on the devices: upload the un-expanded columns, expand every device's
+        block shard there."""
+        self._bind()
+        s, keep = source_struct(src)
+        self._check(self.lib.cloudsc2_gpu_state_load(C.byref(s), int(nproma), int(ngptot)))
+        self._state_dims = (int(nproma), int(src.klev), int(ngptot))
+        del keep
+
+    def state_free(self):
+        self._check(self.lib.cloudsc2_gpu_state_free())
+
+    def state_info(self) -> list[dict]:
+        out = []
+        for i in range(max(1, self.num_devices())):
+            dev, nb, ng, g0 = C.c_int(0), C.c_int(0), C.c_int(0), C.c_longlong(0)
+            self._check(self.lib.cloudsc2_gpu_state_info(i, C.byref(dev), C.byref(nb), C.byref(ng),
+                                                         C.byref(g0)))
+            out.append({"device": dev.value, "nblocks": nb.value, "ngptot": ng.value, "gcol0": g0.value})
+        return out
+
+    def state_nl(self) -> tuple[float, np.ndarray]:
+        """CLOUDSC_DRIVER on the resident state, all devices concurrently -> (seconds of the slowest
+        device's kernel, per-device seconds)."""
+        self._bind()
+        t = C.c_double(0)
+        per = np.zeros(max(1, self.num_devices()))
+        self._check(self.lib.cloudsc2_gpu_state_nl(C.byref(t), per.ctypes.data_as(_abi.c_double_p)))
+        return t.value, per
+
+    def state_tl_taylor(self, allow_degenerate: bool = False) -> tuple[np.ndarray, float, np.ndarray]:
+        self._bind()
+        z = np.zeros(10)
+        t = C.c_double(0)
+        per = np.zeros(max(1, self.num_devices()))
+        rc = self.lib.cloudsc2_gpu_state_tl_taylor(z.ctypes.data_as(_abi.c_double_p), C.byref(t),
+                                                   per.ctypes.data_as(_abi.c_double_p))
+        if not (allow_degenerate and rc == DEGENERATE_RC):
+            self._check(rc)
+        return z, t.value, per
+
+    def state_ad_test(self) -> tuple[float, float, np.ndarray]:
+        self._bind()
+        zn, t = C.c_double(0), C.c_double(0)
+        per = np.zeros(max(1, self.num_devices()))
+        self._check(self.lib.cloudsc2_gpu_state_ad_test(C.byref(zn), C.byref(t),
+                                                        per.ctypes.data_as(_abi.c_double_p)))
+        return zn.value, t.value, per
+
+    def state_validate(self, ref: dict, klon: int) -> np.ndarray:
+        """GLOBAL_STATE%VALIDATE on the devices -> stats[10][5] in the order of _abi.VALIDATED_NAMES."""
+        self._bind()
+        r, keep = reference_struct(ref, klon, self.klev)
+        out = np.zeros((_abi.NVALIDATED, 5))
+        self._check(self.lib.cloudsc2_gpu_state_validate(C.byref(r), out.ctypes.data_as(_abi.c_double_p)))
+        del keep
+        return out
+
+    def state_get(self, name: str) -> np.ndarray:
+        """One array of the resident state, all shards in block order, as the host would own it."""
+        self._bind()
+        nproma, klev, ngptot = self._state_dims
+        nb = nblocks(ngptot, nproma)
+        shape = {"paph": (nb, klev + 1, nproma), "pfplsl": (nb, klev + 1, nproma),
+                 "pfplsn": (nb, klev + 1, nproma), "pfhpsl": (nb, klev + 1, nproma),
+                 "pfhpsn": (nb, klev + 1, nproma), "pclv": (nb, _abi.NCLV, klev, nproma),
+                 "b_cml": (nb, _abi.NSTATE, klev, nproma), "b_loc": (nb, _abi.NSTATE, klev, nproma)
+                 }.get(name, (nb, klev, nproma))
+        out = np.zeros(shape)
+        self._check(self.lib.cloudsc2_gpu_state_get(name.encode(), out.ctypes.data_as(_abi.c_double_p)))
+        return out
+
+    def nl_source(self, src, nproma: int, ngptot: int, ref: dict | None = None):
+        """The NL program's work flow in one call (dwarf_cloudsc.F90:84-122): LOAD with device-side
+        expansion, CLOUDSC_DRIVER, VALIDATE -> (stats[10][5] or None, kernel seconds, total seconds)."""
+        self._bind()
+        s, keep = source_struct(src)
+        tk, tt = C.c_double(0), C.c_double(0)
+        stats = None
+        rp = None
+        if ref is not None:
+            r, keep2 = reference_struct(ref, src.klon, src.klev)
+            rp = C.byref(r)
+            stats = np.zeros((_abi.NVALIDATED, 5))
+        self._check(self.lib.cloudsc2_gpu_nl_source(
+            C.byref(s), rp, int(nproma), int(ngptot),
+            stats.ctypes.data_as(_abi.c_double_p) if stats is not None else None, C.byref(tk), C.byref(tt)))
+        self._state_dims = (int(nproma), int(src.klev), int(ngptot))
+        return stats, tk.value, tt.value
 
     # -- expansion --------------------------------------------------------------------------------
     def expand_dev(self, src_ptr: int, nlon: int, nlev: int, ndim: int, dst_ptr: int, nproma: int,

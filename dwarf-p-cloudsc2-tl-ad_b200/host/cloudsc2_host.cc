@@ -271,7 +271,9 @@ void cloudsc2_validate_host(const double *ref, const double *field, int nproma, 
         zmax = std::max(zmax, field[o + jl]);
       }
       for (int jl = 0; jl < bsize; ++jl) {
-        const double d = std::fabs(field[o + jl] - ref[o + jl]);
+        // a NaN result must fail the validation (std::max drops NaN): give it the largest error
+        const double d0 = std::fabs(field[o + jl] - ref[o + jl]);
+        const double d = (d0 == d0) ? d0 : std::numeric_limits<double>::max();
         zmaxerr = std::max(zmaxerr, d);
         zsumerr += d;
         zsumref += std::fabs(ref[o + jl]);

@@ -80,17 +80,49 @@ typedef struct cloudsc2_incr_out {  /* perturbations of the 10 outputs */
 /* ---- life cycle ------------------------------------------------------------------ */
 
 /* Select CUDA device `device`, upload the constants and the CETA(KLEV) vector
- * (cloudsc2_nl/dwarf_cloudsc.F90:100-102; YRECLD%CETA) and create the stream.
- * Replaces the implicit module state used by CLOUDSC2/TL/AD (cloudsc2.F90:104-111,222-224). */
+ * (cloudsc2_nl/dwarf_cloudsc.F90:100-102; YRECLD%CETA) and create the streams.
+ * Replaces the implicit module state used by CLOUDSC2/TL/AD (cloudsc2.F90:104-111,222-224).
+ * A single-device set: what one MPI rank of the reference's host uses (one rank per GPU). */
 int cloudsc2_gpu_init(const cloudsc2_params *params, int klev, const double *ceta, int device);
+/* The same for a set of `ngpus` devices driven by THIS process (devices 0..ngpus-1; ngpus <= 0: all
+ * visible; cloudsc2_gpu_init_devices: an explicit list).  Creates one context, one stream set and one
+ * host worker thread per device and an NCCL communicator over the set (ncclCommInitAll).  From then
+ * on every host-pointer entry point (cloudsc2_gpu_nl / _tl / _ad / _tl_taylor / _ad_test) and the
+ * cloudsc2_gpu_state_* entries shard the NPROMA blocks over the devices: device r of R owns blocks
+ * [r*per, min(NB,(r+1)*per)), per = (NB-1)/R+1 -- the arithmetic the reference applies to MPI ranks
+ * (cloudsc2_nl/dwarf_cloudsc.F90:65-69) -- and the test norms / validation statistics are all-reduced
+ * on the devices over NVLink (replaces reduction(max:znormg), cloudsc_driver_tl_mod.F90:125,
+ * cloudsc_driver_ad_mod.F90:107, and CLOUDSC_MPI_REDUCE_*, validate_mod.F90:197-199).  A single
+ * Fortran process calling CLOUDSC_DRIVER once -- what the reference does -- thus uses all GPUs. */
+int cloudsc2_gpu_init_multi(const cloudsc2_params *params, int klev, const double *ceta, int ngpus);
+int cloudsc2_gpu_init_devices(const cloudsc2_params *params, int klev, const double *ceta, int ngpus,
+                              const int *devices);
 int cloudsc2_gpu_finalize(void);
+/* Number of devices in the set (0 before init). */
+int cloudsc2_gpu_num_devices(void);
+/* Make device `index` of the set the calling thread's current context for the _dev entry points and
+ * the memory helpers (thread-local; index < 0: back to the default = device 0 / the whole set). */
+int cloudsc2_gpu_select_device(int index);
+/* Multi-PROCESS jobs (one process per GPU, e.g. MPI ranks or torchrun): attach the single-device
+ * context to a job-wide NCCL communicator so that the test norms are all-reduced across processes
+ * inside the library.  Rank 0 obtains the 128-byte id, the host broadcasts it (MPI_BCAST / any
+ * channel), every rank calls comm_init_rank. */
+int cloudsc2_gpu_comm_unique_id(void *id128, int bytes);
+int cloudsc2_gpu_comm_init_rank(int rank, int nranks, const void *id128, int bytes);
+/* rank / size of the current context's communicator (0 / 1 without one) and the NCCL version in use. */
+int cloudsc2_gpu_comm_info(int *rank, int *size, int *nccl_version);
+/* All-reduce n device-resident doubles in place over the communicator: op 0 = MAX, 1 = MIN, 2 = SUM
+ * (CLOUDSC_MPI_REDUCE_MAX / MIN / SUM, cloudsc_mpi_mod.F90).  Synchronous; no-op without a communicator. */
+int cloudsc2_gpu_allreduce_dev(double *dev, int n, int op);
+/* Text of the calling thread's last error. */
 const char *cloudsc2_gpu_last_error(void);
 /* 1 if a usable CUDA device is visible, else 0 (never falls back to CPU). */
 int cloudsc2_gpu_available(void);
 /* Number of visible CUDA devices (0 without a GPU): what a multi-rank host uses to map rank -> device,
  * like the reference maps MPI ranks to cores (cloudsc_mpi_mod.F90). */
 int cloudsc2_gpu_device_count(void);
-/* number of kernels launched by this library since init (bench.py: gpu_launches). */
+/* number of kernels (and NCCL collectives) launched by this library since init, all devices
+ * (bench.py: gpu_launches). */
 long long cloudsc2_gpu_launch_count(void);
 
 /* ---- nonlinear: replaces the block loop of CLOUDSC_DRIVER -------------------------- */
@@ -138,8 +170,9 @@ int cloudsc2_gpu_ad(int nproma, int klev, int ngptot, double ptsphy,
 /* Taylor test (cloudsc2_tl/cloudsc_driver_tl_mod.F90:126-254): per block 1 NL + 1 TL + 10
  * perturbed NL, ERROR_NORM (:21-31) over 10 fields, max over blocks.  znormg[10] receives the
  * ratios BEFORE the |1-r| redefinition (:278).  ratios_blk (may be NULL) receives the
- * per-block values ZNORM/ZCOUNT, layout [nblocks][10].  Returns 3 if a block is degenerate
- * (ZNORM==0 or ZCOUNT==0; reference STOPs, :247-249). Host pointers. */
+ * per-block values ZNORM/ZCOUNT, layout [nblocks][10].  Returns 6 if a block is degenerate
+ * (ZNORM==0 or ZCOUNT==0; reference STOPs, :247-249) -- distinct from 3 = bad arguments.
+ * With a communicator (device set or comm_init_rank) znormg is the MAX over all ranks. Host pointers. */
 int cloudsc2_gpu_tl_taylor(int nproma, int klev, int ngptot, double ptsphy,
                            const cloudsc2_fields *host, double znormg[10], double *ratios_blk);
 int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
@@ -172,6 +205,45 @@ int cloudsc2_gpu_expand_dev(const double *src, int nlon, int nlev, int ndim,
  * (gcol0 + j) mod nlon, for the ngptot local columns of this shard. */
 int cloudsc2_gpu_expand_shard_dev(const double *src, int nlon, int nlev, int ndim, double *dst,
                                   int nproma, int ngptot, long long gcol0, void *stream);
+
+/* ---- device-resident sharded state (SURVEY 8b "Ownership", 8f-1) --------------------------- */
+
+struct cloudsc2_source;      /* include/cloudsc2_host.h: un-expanded columns in the input.h5 layout */
+struct cloudsc2_reference;   /* include/cloudsc2_host.h: un-expanded reference columns               */
+#define CLOUDSC2_NVALIDATED 10
+
+/* GLOBAL_STATE%LOAD on the devices (cloudsc2_array_state_mod.F90:153-203): upload the KLON
+ * un-expanded source columns once per device (about 4 MB), expand every device's block shard of the
+ * NGPTOT columns there (expand_mod.F90:270-335, global column g <- source column g mod KLON) and zero
+ * the outputs.  Nothing else crosses PCIe.  The state stays resident until cloudsc2_gpu_state_free /
+ * the next load / finalize. */
+int cloudsc2_gpu_state_load(const struct cloudsc2_source *src, int nproma, int ngptot);
+int cloudsc2_gpu_state_free(void);
+/* Shard of device `index`: CUDA ordinal, number of blocks, valid columns, first global column. */
+int cloudsc2_gpu_state_info(int index, int *device, int *nblocks, int *ngptot, long long *gcol0);
+/* Device pointers of the calling thread's current device's shard (for the _dev entry points). */
+int cloudsc2_gpu_state_fields(cloudsc2_fields *out);
+/* CLOUDSC_DRIVER / CLOUDSC_DRIVER_TL / CLOUDSC_DRIVER_AD on the resident state, all devices
+ * concurrently.  elapsed_s: the slowest device (NL: CUDA events around its kernel; tests: wall time of
+ * its launches + norm all-reduce); per_device_s: [num_devices] or NULL.  znormg is all-reduced (MAX)
+ * on the devices.  _tl_taylor returns 6 if a block is degenerate (reference STOPs, :247-249). */
+int cloudsc2_gpu_state_nl(double *elapsed_s, double *per_device_s);
+int cloudsc2_gpu_state_tl_taylor(double znormg[10], double *elapsed_s, double *per_device_s);
+int cloudsc2_gpu_state_ad_test(double *znormg, double *elapsed_s, double *per_device_s);
+/* GLOBAL_STATE%VALIDATE (cloudsc2_array_state_mod.F90:205-252) on the devices: stats[10][5] =
+ * min, max, max|err|, sum|err|, sum|ref| of PLUDE, PCOVPTOT, PFPLSL, PFPLSN, PFHPSL, PFHPSN,
+ * TENDENCY_LOC%A, %Q, %T, %CLD against the un-expanded reference columns, reduced over the devices
+ * with MIN / MAX / SUM all-reduces (validate_mod.F90:197-199). */
+int cloudsc2_gpu_state_validate(const struct cloudsc2_reference *ref, double *stats);
+/* Copy one array of the state ("pt" ... "pfhpsn", the member names of cloudsc2_fields), all shards in
+ * block order, into a host array of the full blocked size (what the Fortran host would own). */
+int cloudsc2_gpu_state_get(const char *name, double *host);
+/* The NL program's work flow in ONE call (cloudsc2_nl/dwarf_cloudsc.F90:84-122): LOAD with device-side
+ * expansion, CLOUDSC_DRIVER, VALIDATE (skipped when ref or stats is NULL).  elapsed_kernel_s: slowest
+ * device's kernel; elapsed_total_s: wall time of the call. */
+int cloudsc2_gpu_nl_source(const struct cloudsc2_source *src, const struct cloudsc2_reference *ref,
+                           int nproma, int ngptot, double *stats, double *elapsed_kernel_s,
+                           double *elapsed_total_s);
 
 /* ---- device-side validation (next row 8f-2) ------------------------------------------------ */
 
@@ -228,7 +300,6 @@ int cloudsc2_gpu_host_free(void *ptr);
  *                                      cloudsc2_gpu_nl_dev / _tl_dev call ran before, as in every
  *                                      4D-Var inner loop) and skips its forward sweep; 0 (default):
  *                                      CLOUDSC2AD as written, trajectory recomputed (cloudsc2ad.F90:364-866)
- *   "nl_variant"   (CSC2_NL_VARIANT)   launch shape of the NL kernel (csrc/cloudsc2_nl_kernel.cu)
  * Nothing like this exists in the reference (its only knobs are NUMOMP and NPROMA). */
 int cloudsc2_gpu_set_option(const char *name, int value);
 

@@ -22,7 +22,7 @@ void cloudsc2_default_params(cloudsc2_params *p);
 
 /* Un-expanded source columns in the layout of input.h5: every field is
  * (KLON,KLEV[,NDIM]) column-major, i.e. C-order (NDIM,KLEV,KLON), KLON contiguous. */
-typedef struct cloudsc2_source {
+typedef struct cloudsc2_source {   /* (tag declared in cloudsc2_b200.h) */
   int klon, klev;
   double ptsphy;
   double *pt, *pq, *pap, *paph /*klev+1*/, *plu, *plude, *pmfu, *pmfd, *pa, *psupsat;
@@ -87,7 +87,7 @@ int cloudsc2_h5_write(const char *path, const cloudsc2_h5_dataset *ds, int n);
 int cloudsc2_source_load_h5(cloudsc2_source *s, cloudsc2_params *p, const char *path);
 /* The un-expanded columns of reference.h5 that VALIDATE compares with
  * (cloudsc2_array_state_mod.F90:225-233); tend_loc is (KLON,KLEV,8): slabs T,A,Q,CLD(5). */
-typedef struct cloudsc2_reference {
+typedef struct cloudsc2_reference {   /* (tag declared in cloudsc2_b200.h) */
   int klon, klev;
   double *plude, *pcovptot, *pfplsl, *pfplsn, *pfhpsl, *pfhpsn; /* fluxes: klev+1 */
   double *tend_loc;

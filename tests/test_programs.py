@@ -84,12 +84,6 @@ def test_input_h5_writer_roundtrip(pkg, tmp_path):
     assert np.isclose(pkg.read_h5_f8(path, "RV")[0], 461.5249933083879)
 
 
-class _Reference(C.Structure):
-    _fields_ = [("klon", C.c_int), ("klev", C.c_int)] + [
-        (n, C.POINTER(C.c_double)) for n in ("plude", "pcovptot", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn",
-                                             "tend_loc")]
-
-
 def test_reference_h5_loader(pkg, tmp_path):
     rng = np.random.default_rng(11)
     klon, klev = 5, 9
@@ -102,7 +96,7 @@ def test_reference_h5_loader(pkg, tmp_path):
     path = tmp_path / "reference.h5"
     write_h5(path, d)
     lib = pkg.load_library()
-    r = _Reference()
+    r = pkg._abi.Reference()
     assert lib.cloudsc2_reference_load_h5(C.byref(r), str(path).encode()) == 0
     try:
         assert (r.klon, r.klev) == (klon, klev)
