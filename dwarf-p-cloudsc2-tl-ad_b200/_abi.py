@@ -12,7 +12,10 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "csrc" / "libcloudsc2_b200.so"
+# CLOUDSC2_LIB: an alternative build of the same library (e.g. tools/probes/libcloudsc2_b200_experiments.so,
+# the product plus the measured-slower kernel variants); never a different implementation
+LIB_PATH = Path(os.environ["CLOUDSC2_LIB"]).resolve() if os.environ.get("CLOUDSC2_LIB") else \
+    PKG_DIR / "csrc" / "libcloudsc2_b200.so"
 
 NCLV = 5
 NSTATE = 8

@@ -298,6 +298,11 @@ def test_nl_launch_variants_agree(pkg, src100, gpu_nl, variant):
     """The tuning variants of the NL kernel (CSC2_NL_VARIANT / option nl_variant: 12 warps per SM, a DMA warp
     with TMA bulk copies into an mbarrier ring, warp-private TMA staging) compute the same fields as the
     default cp.async kernel; geometries the TMA variants do not take (ragged, NPROMA % 32 != 0) fall back."""
+    try:
+        gpu_nl.set_option("nl_variant", 0)
+    except pkg.Cloudsc2Error:
+        pytest.skip("the product library carries one NL kernel; the variants live in the experiments build: "
+                    "make -C tools/probes experiments && CLOUDSC2_LIB=tools/probes/libcloudsc2_b200_experiments.so")
     for nproma, ngptot in ((128, 4096), (32, 640), (64, 1000), (100, 100)):
         a, b = pkg.ArrayState(src100, nproma, ngptot), pkg.ArrayState(src100, nproma, ngptot)
         gpu_nl.set_option("nl_variant", 0)

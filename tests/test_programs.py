@@ -157,6 +157,7 @@ def test_dwarf_nl_baseline_config(built, pkg):
     assert len(tot) == 1
     nums = tot[0].replace("x", " ").replace(":", " ").split()
     assert nums[:6] == ["1", "4", "160000", "160000", "5000", "32"]
+    assert "SELF-CONSISTENCY only" in r.stdout and "UNVERIFIED" in r.stdout   # no reference.h5 in this image
     v = _validation_lines(r.stdout)
     want = ["PLUDE", "PCOVPTOT", "PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN", "TENDENCY_LOC%A",
             "TENDENCY_LOC%Q", "TENDENCY_LOC%T", "TENDENCY_LOC%CLD"]
@@ -169,29 +170,37 @@ def test_dwarf_nl_baseline_config(built, pkg):
 
 
 @pytest.mark.gpu
-def test_dwarf_ranks_do_not_change_results(built, pkg):
-    """CLOUDSC2_NUMPROC=3 (three processes, sharing the GPU when the box has fewer): rank r expands from
-    its global column offset, so the validation table, the Taylor ratios' verdict and the adjoint norm
-    are those of the single-process run; the timer table has one TOTAL line per rank."""
+def test_dwarf_gpus_do_not_change_results(built, pkg):
+    """CLOUDSC2_NGPUS=N: ONE process drives N GPUs through the library's device set (no fork, no pipes):
+    a device expands from its global column offset, so the validation table, the Taylor ratios' verdict
+    and the adjoint norm are those of the one-GPU run; the timer table has one line per GPU."""
+    ndev = int(pkg.load_library().cloudsc2_gpu_device_count())
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    n = min(ndev, 4)
     one = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64)
-    three = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NUMPROC": "3"})
-    assert one.returncode == 0 and three.returncode == 0, three.stderr
-    assert "NUMPROC=3, NUMOMP=1, NGPTOTG=10000, NPROMA=64, NGPBLKS=53" in three.stderr   # 3334 columns on rank 0
-    ranks = [l for l in three.stderr.splitlines() if "TOTAL @ rank#" in l]
-    assert len(ranks) == 3 and [int(l.split()[1]) for l in ranks] == [3334, 3334, 3332]
-    grand = [l for l in three.stderr.splitlines() if l.rstrip().endswith(": TOTAL")][0].replace("x", " ").split()
-    assert grand[:4] == ["3", "1", "10000", "10000"]
-    v1, v3 = _validation_lines(one.stdout), _validation_lines(three.stdout)
-    assert list(v1) == list(v3) and len(v3) == 10
+    many = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NGPUS": str(n)})
+    assert one.returncode == 0 and many.returncode == 0, many.stderr
+    assert f"NUMPROC=1, NUMOMP=1, NGPTOTG=10000, NPROMA=64, NGPBLKS=157   (GPUs: {n})" in many.stderr
+    per_gpu = [l for l in many.stderr.splitlines() if re.search(r": GPU \d+$", l)]
+    assert len(per_gpu) == n and sum(int(l.split()[2]) for l in per_gpu) == 10000
+    assert f"ranks={n}" in many.stderr
+    v1, vn = _validation_lines(one.stdout), _validation_lines(many.stdout)
+    assert list(v1) == list(vn) and len(vn) == 10
     for name in v1:
-        assert v1[name][0][:3] == v3[name][0][:3] and v3[name][0][2] == 0.0 and not v3[name][1], name
+        assert v1[name][0][:3] == vn[name][0][:3] and vn[name][0][2] == 0.0 and not vn[name][1], name
+    hosted = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NGPUS": str(n), "CLOUDSC2_HOST_ARRAYS": "1"})
+    assert hosted.returncode == 0 and _validation_lines(hosted.stdout) == vn
     a1 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50)
-    a2 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50, env={"CLOUDSC2_NUMPROC": "2"})
+    a2 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50, env={"CLOUDSC2_NGPUS": "2"})
     pat = r"The maximum error is\s+([0-9.]+)"
     assert a1.returncode == 0 and a2.returncode == 0
     assert float(re.search(pat, a1.stdout).group(1)) == float(re.search(pat, a2.stdout).group(1))
-    t2 = _run(built, "dwarf-cloudsc2-tl", 1, 200, 1, env={"CLOUDSC2_NUMPROC": "2"})
+    t1 = _run(built, "dwarf-cloudsc2-tl", 1, 200, 1)
+    t2 = _run(built, "dwarf-cloudsc2-tl", 1, 200, 1, env={"CLOUDSC2_NGPUS": "2"})
     assert t2.returncode == 0 and "TEST PASSED" in t2.stdout
+    rows = lambda r: re.findall(r"^\s+(\d+)\s+([0-9.]+)\s*$", r.stdout, flags=re.M)
+    assert rows(t1) == rows(t2)
 
 
 @pytest.mark.gpu
@@ -250,12 +259,25 @@ def test_dwarf_nl_from_input_h5_and_host_arrays(built, pkg, src100, tmp_path):
             assert not warn and nums5[2] == 0.0, (name, nums5)
         outs.append(v)
     assert outs[0] == outs[1]
-    # a perturbed reference is flagged with the reference's own "!!!!" marker
-    ref["PFPLSN"] = ref["PFPLSN"] * (1.0 + 1e-9)
+    # a perturbed reference is flagged with the reference's own "!!!!" marker; the exit status has its
+    # own tolerance (relative L1 error 1e-11 by default): 1e-13 passes with marks, 1e-9 fails
+    good = ref["PFPLSN"].copy()
+    ref["PFPLSN"] = good * (1.0 + 1e-13)
     write_h5(tmp_path / "reference.h5", {k: np.ascontiguousarray(v) for k, v in ref.items()})
     r = _run(built, "dwarf-cloudsc2-nl", 1, 1000, 32, cwd=tmp_path)
     v = _validation_lines(r.stdout)
-    assert v["PFPLSN"][1] and not v["PFPLSL"][1]
+    assert r.returncode == 0 and v["PFPLSN"][1] and not v["PFPLSL"][1]
+    ref["PFPLSN"] = good * (1.0 + 1e-9)
+    write_h5(tmp_path / "reference.h5", {k: np.ascontiguousarray(v) for k, v in ref.items()})
+    r = _run(built, "dwarf-cloudsc2-nl", 1, 1000, 32, cwd=tmp_path)
+    v = _validation_lines(r.stdout)
+    assert r.returncode == 3 and v["PFPLSN"][1] and not v["PFPLSL"][1]
+    # a NaN in the reference (or, equally, in the results) can never pass
+    ref["PFPLSN"] = good.copy()
+    ref["PFPLSN"][50, 7] = np.nan
+    write_h5(tmp_path / "reference.h5", {k: np.ascontiguousarray(v) for k, v in ref.items()})
+    r = _run(built, "dwarf-cloudsc2-nl", 1, 1000, 32, cwd=tmp_path)
+    assert r.returncode == 3, r.stdout
 
 
 @pytest.mark.gpu
