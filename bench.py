@@ -14,8 +14,14 @@ tangent-linear and adjoint kernels and reported under "modes".
 
 Printed keys (one JSON line, rank 0):
   value / ms_per_step : NL columns/s over all ranks, inputs resident in HBM, CUDA events, max over ranks
-  e2e                 : same metric through the host-pointer C ABI call cloudsc2_gpu_nl (pinned HOST
-                        arrays in the reference layout, H2D and D2H inside the timed region)
+  e2e                 : same metric through the host-pointer C ABI call cloudsc2_gpu_nl on arrays the HOST
+                        allocated itself (NumPy = malloc, like the Fortran ALLOCATEs of expand_mod.F90:110)
+                        and page-locked once with cloudsc2_gpu_host_register (time reported); H2D and D2H
+                        inside the timed region.  Beside it: e2e.pageable (no registration at all),
+                        e2e.host_alloc (arrays from cloudsc2_gpu_host_alloc) and e2e_source (the dwarf's own
+                        work flow in one call: 100 source columns up, device expansion, NL, device validation)
+  strong_<NGPTOT>     : BASELINE config 5: a FIXED total of 1 310 720 (and, N >= 2, 5 242 880) columns
+                        block-sharded over the N ranks: NL / TL / AD ms and columns/s
   roofline            : NL kernel, algorithmic bytes 27 440 B/column / launch duration
   cpu_baseline        : the CPU oracle's CLOUDSC_DRIVER loop (C restatement of the reference; the
                         Fortran reference cannot be built in this image) on the host cores
@@ -45,14 +51,18 @@ AD_BYTES_PER_COL = 10564 * 8                                                    
 # what our kernels actually have to move:
 #  TL: 2056 traj in (SATUR fused) + 2193 incr in + 1374 traj out + 1374 incr out
 TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
-# DRAM traffic per column measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch
-# over 163 840 columns, profiles/r1_{nl,tl,ad}_ncu.md) and FP64-pipe utilisation of the same capture
-NCU = {"nl": {"dram_bytes_per_column": 4.739e9 / 163840, "fp64_pipe_pct": 60.5, "profile": "profiles/r1c_nl_ncu.md"},
-       "tl": {"dram_bytes_per_column": 9.236e9 / 163840, "fp64_pipe_pct": 56.9, "profile": "profiles/r1_tl_ncu.md"},
-       # AD = forward sweep (the NL kernel, 4.74 GB; its flux outputs are the check-points) + reverse sweep
-       # kernel (12.108 GB)
-       "ad": {"dram_bytes_per_column": (12.108e9 + 4.741e9) / 163840, "fp64_pipe_pct": 43.3,
-              "profile": "profiles/r1_ad_ncu.md"}}
+# DRAM traffic per column measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over
+# 163 840 columns) and FP64-pipe utilisation of the same capture.  Every entry names the capture it comes
+# from (kernel instantiation + profiles/ file); tools/profile_r2*.sh regenerate them.
+NCU = {"nl": {"dram_bytes_per_column": 4.739e9 / 163840, "fp64_pipe_pct": 60.5, "profile": "profiles/r1c_nl_ncu.md",
+              "kernel": "k_cloudsc2_nl<0,2,128,128,0,0,0>"},
+       "tl": {"dram_bytes_per_column": 9.236e9 / 163840, "fp64_pipe_pct": 55.9, "profile": "profiles/r2a_tl_ncu.md",
+              "kernel": "k_cloudsc2_tl<0,2,0,0,2,128>"},
+       # AD = forward sweep (the NL kernel with flux check-points = its own PFPLSL/PFPLSN outputs, 4.562 GB,
+       # profiles/r2a_adfwd_ncu.md) + reverse sweep kernel (12.107 GB, profiles/r2a_ad_ncu.md)
+       "ad": {"dram_bytes_per_column": (12.107e9 + 4.562e9) / 163840, "fp64_pipe_pct": 43.6,
+              "profile": "profiles/r2a_ad_ncu.md + profiles/r2a_adfwd_ncu.md",
+              "kernel": "k_cloudsc2_nl<0,2,128,128,0,1,0> + k_cloudsc2_ad<0,0,0,2>"}}
 METRIC = "NL columns/s (KLEV=137)"
 UNIT = "columns/s"
 
@@ -117,6 +127,33 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def numa_bind(gpu_index: int) -> dict:
+    """Bind this process (and hence the first-touch placement of the host arrays it allocates next) to the
+    CPUs of the NUMA node its GPU hangs off, as read from sysfs.  On a virtualised box the node is -1."""
+    info = {"bound": False}
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={gpu_index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("0000") and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        info["pci_bus_id"] = bus
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        info["numa_node"] = node
+        if node >= 0:
+            cpus = set()
+            for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"] = True
+                info["cpus"] = len(cpus)
+    except Exception as e:
+        info["error"] = repr(e)
+    return info
+
+
 def host_threads() -> int:
     """All host cores this process may use.  Not omp_get_max_threads(): torchrun exports
     OMP_NUM_THREADS=1 to every rank, which would silently make the CPU arm single-threaded."""
@@ -153,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-sweep", action="store_true", help="skip the NPROMA sweep of BASELINE config 4")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-total blocks of BASELINE config 5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -182,6 +220,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # The reference's own CPU implementation of the path: the C restatement of CLOUDSC_DRIVER's block loop
+        # (oracle/, OpenMP over blocks like cloudsc_driver_mod.F90:73-81) -- the Fortran itself cannot be built
+        # in this image.  None of the repo's kernels run here: libcloudsc2_b200.so is mapped by this process
+        # ONLY because the synthetic input generator and the host-side expansion (pkg.synth_source,
+        # pkg.ArrayState) live in that library; no cloudsc2_gpu_* compute entry is called.
         from tests import oracle_binding as ob
         threads = host_threads()
         sample = min(ngp, 32768)
@@ -192,10 +235,16 @@ def main():
             t = ob.driver_nl(prm, src.ceta, st, numomp=threads)
             if i >= args.warmup:
                 t_steps.append(t)
-        ms = 1e3 * float(np.mean(t_steps))
-        val = sample / (ms * 1e-3)
+        ms_sample = 1e3 * float(np.mean(t_steps))
+        val = sample / (ms_sample * 1e-3)
+        # one step of the stated workload = ngp columns: the sample's time scaled to it (the block loop is
+        # embarrassingly parallel and the sample is >= 256 blocks per thread-team pass, so time is linear)
+        ms = ms_sample * ngp / sample
         line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "ms_per_step_note": f"scaled to the stated {ngp} columns from the timed sample of {sample} "
+                                    f"({ms_sample:.3f} ms per sample pass)",
+                "cores": threads, "sample_columns": sample, "ms_per_sample": ms_sample,
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
@@ -237,7 +286,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    gpu = pkg.Cloudsc2(prm, KLEV, src.ceta, device=local_rank)
+    # one process per GPU here (the driver's launch contract); the norms / validation statistics are reduced by
+    # the LIBRARY's own NCCL communicator, joined after every context initialisation
+    gpu = pkg.Cloudsc2(prm, KLEV, src.ceta, device=local_rank,
+                       after_init=pkg.driver.torch_comm_factory(rank, world))
+    comm_rank, comm_size, nccl_version = gpu.comm_info()
     sh = pkg.shard_blocks(ngp_total, nproma, rank, world)
     assert sh.ngptot == ngp
     # a non-default torch stream: the kernels are launched on it through the ABI's `stream`
@@ -280,7 +333,7 @@ def main():
     def ncu_part(mode, ms):
         n = NCU[mode]
         return {"dram_gbs_actual": n["dram_bytes_per_column"] * ngp / (ms * 1e-3) / 1e9,
-                "fp64_pipe_pct_ncu": n["fp64_pipe_pct"], "ncu_profile": n["profile"]}
+                "fp64_pipe_pct_ncu": n["fp64_pipe_pct"], "ncu_profile": n["profile"], "ncu_kernel": n["kernel"]}
 
     results["nl"] = {"columns_per_s": value, "ms_per_step": ms_nl, "gbs_per_gpu": nl_gbs,
                      "frac_of_hbm": nl_gbs / peak, "bytes_per_column": NL_BYTES_PER_COL,
@@ -388,56 +441,109 @@ def main():
 
     # ---- e2e through the host-pointer C ABI call ----------------------------------------------
     e2e = None
+    e2e_source = None
     if not args.no_e2e:
-        st = pkg.ArrayState(src, nproma, ngp, gcol0=sh.gcol0)
-        # host arrays in page-locked memory obtained from the library (cloudsc2_gpu_host_alloc);
-        # BENCH_E2E_HOSTMEM=register page-locks the NumPy allocations instead (~15 % slower DMA)
-        pinned, host_ptrs = [], []
-        if os.environ.get("BENCH_E2E_HOSTMEM", "alloc") == "register":
-            for n, a in st.a.items():
-                gpu.pin(a)
-                pinned.append(a)
-        else:
-            for n in list(st.a):
-                st.a[n], p = gpu.host_alloc_like(st.a[n])
-                host_ptrs.append(p)
+        numa = numa_bind(local_rank) if world > 1 or os.environ.get("BENCH_NUMA_BIND") else {"bound": False}
+        st = pkg.ArrayState(src, nproma, ngp, gcol0=sh.gcol0)      # NumPy = malloc'ed, pageable: the unchanged host
         n2 = nproma * KLEV * st.nblocks
         n2h = nproma * (KLEV + 1) * st.nblocks
         h2d = 8 * (8 * n2 + n2h + 2 * n2 + 4 * n2)          # 8 plain + PAPH + PCLV(QL,QI) + B_CML(T,Q,QL,QI)
         d2h = 8 * (4 * n2 + n2 + 2 * n2h)                   # B_LOC(T,Q,QL,QI) + PA + PFPLSL/PFPLSN; the zero fields and
         #                                                     PFHPSL/PFHPSN = -L*flux are filled on the host (e2e_host_derive)
-        gpu.nl(st)                                           # warm-up (allocates staging buffers)
-        gpu.nl(st)
-        barrier()
+
+        def time_nl(steps):
+            gpu.nl(st)                                       # warm-up (allocates staging buffers)
+            gpu.nl(st)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                gpu.nl(st)                                   # synchronous: returns with results on the host
+            t = (time.perf_counter() - t0) / steps
+            barrier()
+            return max_over_ranks(t)
+
+        # (1) no help from the host at all: pageable arrays
+        t_page = time_nl(max(1, args.e2e_steps - 1))
+        # (2) THE DEFAULT: the host's own arrays, page-locked once with cloudsc2_gpu_host_register
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            gpu.nl(st)                                       # synchronous: returns with results on the host
-        t_e2e = (time.perf_counter() - t0) / args.e2e_steps
-        barrier()
-        t_e2e = max_over_ranks(t_e2e)
-        e2e = {"value": ngp_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e,
-               "api": "cloudsc2_gpu_nl (host arrays in the reference layout, page-locked memory from "
-                      "cloudsc2_gpu_host_alloc)",
-               "checksum_tend_t": float(np.abs(st.a["b_loc"][:, 0]).sum())}
-        for a in pinned:
+        for a in st.a.values():
+            gpu.pin(a)
+        t_reg = max_over_ranks(time.perf_counter() - t0)
+        t_e2e = time_nl(args.e2e_steps)
+        checksum = float(np.abs(st.a["b_loc"][:, 0]).sum())
+        t0 = time.perf_counter()
+        for a in st.a.values():
             gpu.unpin(a)
+        t_unreg = max_over_ranks(time.perf_counter() - t0)
+        # (3) arrays allocated by the library (cudaHostAlloc): needs a changed host (C_F_POINTER)
+        host_ptrs = []
+        for n in list(st.a):
+            st.a[n], p = gpu.host_alloc_like(st.a[n])
+            host_ptrs.append(p)
+        t_alloc = time_nl(args.e2e_steps)
+        assert float(np.abs(st.a["b_loc"][:, 0]).sum()) == checksum
         del st
         for p in host_ptrs:
             gpu.host_free(p)
+        e2e = {"value": ngp_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e,
+               "api": "cloudsc2_gpu_nl on caller-allocated (malloc) arrays in the reference layout, page-locked "
+                      "once with cloudsc2_gpu_host_register",
+               "host_register_ms_once": 1e3 * t_reg, "host_unregister_ms_once": 1e3 * t_unreg,
+               "h2d_gbs_per_gpu": h2d / t_e2e / 1e9, "d2h_gbs_per_gpu": d2h / t_e2e / 1e9,
+               "pageable": {"value": ngp_total / t_page, "ms_per_step": 1e3 * t_page,
+                            "note": "same call, arrays neither registered nor library-allocated"},
+               "host_alloc": {"value": ngp_total / t_alloc, "ms_per_step": 1e3 * t_alloc,
+                              "note": "arrays from cloudsc2_gpu_host_alloc (cudaHostAlloc)"},
+               "numa": numa, "checksum_tend_t": checksum}
+
+        # (4) what the dwarf itself does (dwarf_cloudsc.F90:84-122): LOAD the un-expanded columns, expand on the
+        # device, CLOUDSC_DRIVER, VALIDATE on the device -- one call, nothing but the source / reference columns
+        # (4 + 2.6 MB) and 50 statistics cross PCIe.  Under torchrun the ranks of the library communicator shard
+        # the GLOBAL problem and the statistics are all-reduced by the library.
+        st1 = pkg.ArrayState(src, src.klon, src.klon)
+        gpu.nl(st1)
+        ref = {"plude": st1.a["plude"][0], "pcovptot": st1.a["pcovptot"][0], "pfplsl": st1.a["pfplsl"][0],
+               "pfplsn": st1.a["pfplsn"][0], "pfhpsl": st1.a["pfhpsl"][0], "pfhpsn": st1.a["pfhpsn"][0],
+               "tend_loc": st1.a["b_loc"][0]}
+        ds.free()                                            # make room: the resident state is a second copy
+        ds = None
+        gpu.nl_source(src, nproma, ngp_total, ref)
+        barrier()
+        t0 = time.perf_counter()
+        tk_sum = 0.0
+        for _ in range(args.e2e_steps):
+            stats, tk, tt = gpu.nl_source(src, nproma, ngp_total, ref)
+            tk_sum += tk
+        t_src = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        gpu.state_free()
+        src_bytes = 8 * sum(int(np.asarray(v).size) for v in src.f.values())
+        ref_bytes = 8 * sum(int(np.asarray(v).size) for v in ref.values())
+        e2e_source = {"value": ngp_total / t_src, "unit": UNIT, "ms_per_step": 1e3 * t_src,
+                      "kernel_ms_per_step": 1e3 * tk_sum / args.e2e_steps,
+                      "h2d_bytes_per_step": src_bytes + ref_bytes, "d2h_bytes_per_step": 8 * int(stats.size),
+                      "api": "cloudsc2_gpu_nl_source: 100 un-expanded source columns in, device-side expansion "
+                             "(expand_mod.F90:270-335), NL, device-side validation statistics out",
+                      "max_abs_err_vs_unexpanded_columns": float(stats[:, 2].max()),
+                      "stats_finite": bool(np.isfinite(stats).all())}
+        ds = pkg.DeviceState.from_source(gpu, src, nproma, ngp, gcol0=sh.gcol0, stream=stream)
+        torch.cuda.synchronize()
 
     total_launches = int(sum_over_ranks(float(launches)))
 
     # ---- the path's only collective, on the real interconnect: block-sharded Taylor and adjoint
-    # self-tests (BASELINE configs 2/3 scaled to 6400 columns per rank), norms all-reduced (MAX)
-    # over the ranks with NCCL (cloudsc_driver_tl_mod.F90:125, cloudsc_driver_ad_mod.F90:107)
+    # self-tests (BASELINE configs 2/3 scaled to 6400 columns per rank); the norms are all-reduced (MAX) over
+    # the ranks INSIDE the library by its own NCCL communicator (cloudsc_driver_tl_mod.F90:125,
+    # cloudsc_driver_ad_mod.F90:107) -- every rank gets the global ZNORMG back from the call
     selftests = None
     try:
         t0 = time.perf_counter()
-        z, _ = pkg.sharded_taylor(gpu, src, nproma, 6400 * world, rank, world, device=dev)
+        shs = pkg.shard_blocks(6400 * world, nproma, rank, world)
+        st_s = pkg.ArrayState(src, nproma, shs.ngptot, gcol0=shs.gcol0)
+        z, _ = gpu.tl_taylor(st_s)
         pen, istart = pkg.taylor_verdict(z)
-        gpu_ad = pkg.Cloudsc2(pkg.default_params(lregcl=True), KLEV, src.ceta, device=local_rank)
-        zn, _ = pkg.sharded_adjoint(gpu_ad, src, nproma, 6400 * world, rank, world, device=dev)
+        gpu.set_option("lregcl", 1)                  # the AD program's switch (cloudsc2_ad/dwarf_cloudsc.F90:105)
+        zn, _ = gpu.ad_test(st_s)
         # the reference's TL / AD PROGRAMS time their whole test loop (per block 1 NL + 1 TL + 10 perturbed
         # NL, resp. 1 TL + 1 AD; cloudsc_driver_tl_mod.F90:126-254, cloudsc_driver_ad_mod.F90:108-271):
         # the same loops as one library call each on this rank's device-resident columns
@@ -449,30 +555,88 @@ def main():
                 fn()
             torch.cuda.synchronize()
             return max_over_ranks((time.perf_counter() - t) / n)
-        t_ad_drv = host_timed(lambda: gpu_ad.ad_test(ds, src.ptsphy))
-        gpu_ad.close()
-        gpu._bind()
+        t_ad_drv = host_timed(lambda: gpu.ad_test(ds, src.ptsphy))
+        gpu.set_option("lregcl", 0)
         t_tl_drv = host_timed(lambda: gpu.tl_taylor(ds, src.ptsphy))
         results["tl_taylor_driver"] = {"columns_per_s": ngp_total / t_tl_drv, "ms_per_step": 1e3 * t_tl_drv,
                                        "note": "dwarf-cloudsc2-tl's timed loop as one call: 1 NL + 1 TL + 10 perturbed "
-                                               "NL sweeps + ERROR_NORM, max over blocks"}
+                                               "NL sweeps + ERROR_NORM, max over blocks, all-reduced over the ranks"}
         results["ad_test_driver"] = {"columns_per_s": ngp_total / t_ad_drv, "ms_per_step": 1e3 * t_ad_drv,
-                                     "note": "dwarf-cloudsc2-ad's timed loop as one call: 1 TL + 1 AD + dot products"}
-        # cost of the collective itself: MAX all-reduce of the ten Taylor norms, device tensor, 20 calls
-        torch.cuda.synchronize()
+                                     "note": "dwarf-cloudsc2-ad's timed loop as one call: 1 TL + 1 AD + dot products, "
+                                             "ZNORMG all-reduced over the ranks"}
+        # cost of the collective itself: the library's MAX all-reduce of ten device-resident norms, 20 calls
+        dz = gpu.malloc(80)
+        gpu.h2d(dz, np.ascontiguousarray(z))
+        gpu.allreduce_dev(dz, 10, "max")
         ta = time.perf_counter()
         for _ in range(20):
-            pkg.allreduce_norms(z, "max", dev)
-        torch.cuda.synchronize()
+            gpu.allreduce_dev(dz, 10, "max")
         allreduce_us = (time.perf_counter() - ta) / 20 * 1e6
+        gpu.free(dz)
         selftests = {"ngptot_total": 6400 * world, "taylor_penalty": pen, "taylor_passed": 0 <= pen <= 5,
                      "allreduce_us_per_call": allreduce_us,
                      "taylor_ratios": [float(v) for v in z], "adjoint_znormg_eps": zn,
                      "adjoint_passed": bool(pkg.adjoint_verdict(zn)),
-                     "allreduce": "nccl max over %d rank(s)" % world if world > 1 else "single rank",
+                     "allreduce": (f"library NCCL communicator (ncclAllReduce max, NCCL {nccl_version}), "
+                                   f"rank {comm_rank} of {comm_size}") if comm_size > 1 else "single rank",
+                     "comm_size": comm_size,
                      "seconds": time.perf_counter() - t0}
     except Exception as e:                          # evidence only: never lose the bench line over it
-        selftests = {"error": str(e)}
+        selftests = {"error": repr(e)}
+
+    # ---- BASELINE config 5: strong scaling, a FIXED total sharded over the ranks ---------------------
+    strong_blocks = {}
+    if not strong and not args.no_strong:
+        ds.free()
+        ds = None
+        for total in (1310720, 5242880):
+            if total == 5242880 and world < 2:
+                continue                                        # 207 GB of state: does not fit one GPU
+            key = f"strong_{total}"
+            if total == ngp_total:
+                strong_blocks[key] = {"note": "identical to the weak-scaling configuration of this run",
+                                      "ngptot_per_gpu": ngp,
+                                      **{m: {"ms_per_step": results[m]["ms_per_step"],
+                                             "columns_per_s": results[m]["columns_per_s"]}
+                                         for m in ("nl", "tl", "ad") if m in results and "ms_per_step" in results[m]}}
+                continue
+            try:
+                shx = pkg.shard_blocks(total, nproma, rank, world)
+                # the same decision on every rank (a rank that skipped would hang the others' barrier): sized
+                # on rank 0's shard, the largest, against the device's total memory
+                big = pkg.shard_blocks(total, nproma, 0, world).ngptot
+                cap = 0.85 * torch.cuda.get_device_properties(dev).total_memory
+                need_state = big * 36.1 * (KLEV + 1) * 8
+                need_incr = big * 26.1 * (KLEV + 1) * 8
+                blk = {"ngptot_per_gpu": shx.ngptot}
+                if need_state > cap:
+                    blk["skipped"] = f"state of {need_state / 1e9:.0f} GB does not fit {cap / 1e9:.0f} GB"
+                    strong_blocks[key] = blk
+                    continue
+                dx = pkg.DeviceState.from_source(gpu, src, nproma, shx.ngptot, gcol0=shx.gcol0, stream=stream)
+                torch.cuda.synchronize()
+                ms = timed(lambda: gpu.nl_dev(dx, src.ptsphy, stream=stream), 5, 3)
+                blk["nl"] = {"ms_per_step": ms, "columns_per_s": total / (ms * 1e-3),
+                             "frac_of_hbm": NL_BYTES_PER_COL * shx.ngptot / (ms * 1e-3) / 1e9 / peak}
+                if ("tl" in modes or "ad" in modes) and need_state + need_incr < cap:
+                    ax, bx, m2, m2h = make_increments(dx)
+                    if "tl" in modes:
+                        ms = timed(lambda: gpu.tl_dev(dx, src.ptsphy, ax, bx, stream=stream), 3, 3)
+                        blk["tl"] = {"ms_per_step": ms, "columns_per_s": total / (ms * 1e-3),
+                                     "frac_of_hbm": TL_BYTES_PER_COL * shx.ngptot / (ms * 1e-3) / 1e9 / peak}
+                    if "ad" in modes:
+                        fill_output_adjoints(bx, m2, m2h)
+                        ms = timed(lambda: gpu.ad_dev(dx, src.ptsphy, ax, bx, stream=stream), 3, 3)
+                        blk["ad"] = {"ms_per_step": ms, "columns_per_s": total / (ms * 1e-3),
+                                     "frac_of_hbm": AD_BYTES_PER_COL * shx.ngptot / (ms * 1e-3) / 1e9 / peak}
+                    for q in list(ax.values()) + list(bx.values()):
+                        gpu.free(q)
+                elif "tl" in modes or "ad" in modes:
+                    blk["tl_ad_skipped"] = f"increments of {need_incr / 1e9:.0f} GB do not fit beside the state"
+                dx.free()
+                strong_blocks[key] = blk
+            except Exception as e:
+                strong_blocks[key] = {"error": repr(e)}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
@@ -519,12 +683,14 @@ def main():
                              "algorithmic_bytes_per_launch": NL_BYTES_PER_COL * ngp,
                              "fp64_pipe_pct_ncu": NCU["nl"]["fp64_pipe_pct"]},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
+                "e2e_source": e2e_source, **strong_blocks,
                 "modes": results, "nproma_sweep_ngptot160000": sweep, "selftests": selftests}
         # the reference's own report lines (timer_mod.F90:114-174), on stderr
         sys.stderr.write(pkg.report.performance_table(1, ngp_total, pkg.nblocks(ngp_total, nproma), nproma,
                                                       ms_nl * 1e-3, numproc=world) + "\n")
         print(json.dumps(line))
-    ds.free()
+    if ds is not None:
+        ds.free()
     gpu.close()
     if world > 1:
         dist.destroy_process_group()

@@ -358,6 +358,13 @@ int cloudsc2_gpu_set_option(const char *name, int value) {
   if (!strcmp(name, "e2e_chunk_mb") && value > 0) { opts.e2e_chunk_mb = value; return 0; }
   if (!strcmp(name, "e2e_host_derive")) { opts.e2e_host_derive = value; return 0; }
   if (!strcmp(name, "ad_have_trajectory")) { opts.ad_have_trajectory = value != 0; return 0; }
+  if (!strcmp(name, "lregcl")) {
+    // YRNCL%LREGCL is a module variable the programs set before the driver call
+    // (cloudsc2_tl/dwarf_cloudsc.F90:105, cloudsc2_ad/dwarf_cloudsc.F90:105): switchable without a new init
+    if (int rc = csc2_require_init()) return rc;
+    for (int i = 0; i < csc2_num_devices(); ++i) csc2_ctx_at(i).prm.lregcl = value != 0;
+    return 0;
+  }
 #ifdef CSC2_EXPERIMENTS
   if (!strcmp(name, "nl_variant")) { csc2_set_nl_variant(value); return 0; }   // tools/probes builds only
 #endif

@@ -612,7 +612,11 @@ static int load_job(int idx, void *p) {
   Ctx &c = csc2_ctx();
   DevState &st = c.state;
   const cloudsc2_source &s = *j.src;
-  const Shard sh = csc2_shard(idx, std::max(1, set_.n), j.nproma, j.ngptot);
+  // shards: the devices of an in-process set, or -- one process per GPU with a job-wide communicator
+  // (cloudsc2_gpu_comm_init_rank) -- the ranks of that communicator; NGPTOT is the global NGPTOTG then
+  const bool by_rank = set_.n <= 1 && c.comm && c.comm_size > 1;
+  const Shard sh = by_rank ? csc2_shard(c.comm_rank, c.comm_size, j.nproma, j.ngptot)
+                           : csc2_shard(idx, std::max(1, set_.n), j.nproma, j.ngptot);
   st.loaded = false;
   st.nproma = j.nproma; st.klev = s.klev; st.ngptot = sh.ngptot; st.nblocks = sh.nb; st.gcol0 = sh.gcol0;
   st.ptsphy = s.ptsphy;

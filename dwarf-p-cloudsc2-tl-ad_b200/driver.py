@@ -28,6 +28,20 @@ class Cloudsc2Error(RuntimeError):
 DEGENERATE_RC = 6
 
 
+def torch_comm_factory(rank: int, world: int):
+    """after_init hook for process-per-GPU jobs under torch.distributed: rank 0 makes an NCCL unique id,
+    torch broadcasts it (the job's existing channel, like MPI_BCAST in the Fortran host), every rank
+    joins -- from then on the test norms are all-reduced INSIDE the library."""
+    def hook(gpu):
+        if world <= 1:
+            return
+        import torch.distributed as dist
+        box = [gpu.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        gpu.comm_init_rank(rank, world, box[0])
+    return hook
+
+
 def source_struct(src) -> tuple["_abi.Source", list]:
     """struct cloudsc2_source view of a SourceColumns (the arrays are kept alive by the 2nd item)."""
     s = _abi.Source()
@@ -184,11 +198,13 @@ class Cloudsc2:
     _owner = None     # the object whose constants are currently loaded in the library
 
     def __init__(self, params: _abi.Params, klev: int, ceta, device: int = 0, ngpus: int | None = None,
-                 devices=None):
+                 devices=None, after_init=None):
         """device: one GPU (cloudsc2_gpu_init, what one rank of a process-per-GPU job uses);
         ngpus / devices: a device set driven by this one process (cloudsc2_gpu_init_multi /
         _init_devices): host-pointer and resident-state entries shard the blocks over the set and
-        all-reduce the norms with the library's own NCCL communicator."""
+        all-reduce the norms with the library's own NCCL communicator.
+        after_init(self): called after every (re-)initialisation of the library context, e.g. to join
+        a job-wide communicator again (torch_comm_factory below)."""
         self.lib = _abi.load_library()
         self.params = params
         self.klev = int(klev)
@@ -198,6 +214,7 @@ class Cloudsc2:
         self.ceta = np.ascontiguousarray(ceta, dtype=np.float64)
         self._launches = 0
         self._open = False
+        self._after_init = after_init
         self._bind()
         self._open = True
 
@@ -225,6 +242,8 @@ class Cloudsc2:
             rc = self.lib.cloudsc2_gpu_init(C.byref(self.params), self.klev, ceta, self.device)
         self._check(rc)
         Cloudsc2._owner = self
+        if self._after_init is not None:
+            self._after_init(self)
 
     def close(self):
         if getattr(self, "_open", False):
@@ -360,6 +379,7 @@ class Cloudsc2:
         self._check(self.lib.cloudsc2_gpu_select_device(int(index)))
 
     def comm_unique_id(self) -> bytes:
+        self._bind()
         buf = C.create_string_buffer(128)
         self._check(self.lib.cloudsc2_gpu_comm_unique_id(buf, 128))
         return buf.raw
@@ -369,6 +389,11 @@ class Cloudsc2:
         all-reduced inside the library."""
         self._bind()
         self._check(self.lib.cloudsc2_gpu_comm_init_rank(int(rank), int(nranks), uid, len(uid)))
+
+    def allreduce_dev(self, dptr: int, n: int, op: str = "max"):
+        """CLOUDSC_MPI_REDUCE_MAX / MIN / SUM of n device-resident doubles over the library communicator."""
+        self._bind()
+        self._check(self.lib.cloudsc2_gpu_allreduce_dev(dptr, int(n), {"max": 0, "min": 1, "sum": 2}[op]))
 
     def state_load(self, src, nproma: int, ngptot: int):
         """GLOBAL_STATE%LOAD on the devices: upload the un-expanded columns, expand every device's
@@ -495,7 +520,11 @@ class Cloudsc2:
         return out
 
     def set_option(self, name: str, value: int):
-        """cloudsc2_gpu_set_option: 'e2e_mode', 'e2e_chunk_mb', 'nl_variant'."""
+        """cloudsc2_gpu_set_option: 'e2e_mode', 'e2e_chunk_mb', 'e2e_host_derive', 'ad_have_trajectory',
+        'lregcl' (YRNCL%LREGCL without a new init)."""
+        if name == "lregcl":
+            self._bind()
+            self.params.lregcl = int(bool(value))
         self._check(self.lib.cloudsc2_gpu_set_option(name.encode(), int(value)))
 
     def math_probe(self, fn: int, x: np.ndarray) -> np.ndarray:

@@ -216,7 +216,10 @@ struct cloudsc2_reference;   /* include/cloudsc2_host.h: un-expanded reference c
  * un-expanded source columns once per device (about 4 MB), expand every device's block shard of the
  * NGPTOT columns there (expand_mod.F90:270-335, global column g <- source column g mod KLON) and zero
  * the outputs.  Nothing else crosses PCIe.  The state stays resident until cloudsc2_gpu_state_free /
- * the next load / finalize. */
+ * the next load / finalize.  In a process-per-GPU job with a job-wide communicator
+ * (cloudsc2_gpu_comm_init_rank) NGPTOT is the global NGPTOTG and every process loads the block shard of
+ * its rank (dwarf_cloudsc.F90:65-69 on blocks); _state_validate / the test norms are then global, while
+ * _state_get fills only this process' blocks of the full-size host array. */
 int cloudsc2_gpu_state_load(const struct cloudsc2_source *src, int nproma, int ngptot);
 int cloudsc2_gpu_state_free(void);
 /* Shard of device `index`: CUDA ordinal, number of blocks, valid columns, first global column. */
@@ -295,6 +298,10 @@ int cloudsc2_gpu_host_free(void *ptr);
  *                                      PCOVPTOT, TENDENCY_LOC%CLD(:,:,NCLV) (identically zero) and
  *                                      PFHPSL/PFHPSN (= -PFPLSL*RLVTT, -PFPLSN*RLSTT) back over PCIe
  *                                      but fills them on the host, bit-identically; 0: copy all
+ *   "lregcl"                           YRNCL%LREGCL (the regularised TL / AD, cloudsc2tl.F90:575-580 ...) of every
+ *                                      context of the device set, without a new init: the reference's programs
+ *                                      set this module variable before the driver call
+ *                                      (cloudsc2_tl/dwarf_cloudsc.F90:105, cloudsc2_ad/dwarf_cloudsc.F90:105)
  *   "ad_have_trajectory"               1: cloudsc2_gpu_ad_dev trusts that dev->pfplsl / dev->pfplsn
  *                                      already hold the trajectory fluxes of the same inputs (a
  *                                      cloudsc2_gpu_nl_dev / _tl_dev call ran before, as in every
