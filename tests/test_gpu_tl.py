@@ -161,3 +161,64 @@ def test_tl_kernel_matches_finite_differences_of_reference_python_kernel(pkg, go
         d = fd["d_" + n]
         tol = (1e-6 if n == "pclc" else 1e-7) * max(np.abs(d).max(), 1e-300)   # finite-difference error: measured <= 2e-8
         assert np.abs(incr[n] - d).max() <= tol, n
+
+
+ORDER26 = ("paphp1", "papp1", "pqm1", "pqs", "ptm1", "pl", "pi", "plude", "plu", "pmfu", "pmfd",
+           "ptent", "pgtent", "ptenq", "pgtenq", "ptenl", "pgtenl", "pteni", "pgteni", "psupsat",
+           "pclc", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "pcovptot")
+OUT10 = ("ptent", "ptenq", "ptenl", "pteni", "pclc", "pfplsl", "pfplsn", "pfhpsl", "pfhpsn", "pcovptot")
+
+
+def _dirs_case():
+    from pathlib import Path
+    from tests.fd_directions import NCOL
+    gdir = Path(__file__).resolve().parent / "golden"
+    g, fd = np.load(gdir / "nl_pyref.npz"), np.load(gdir / "tl_fd_dirs.npz")
+    x5 = {k[3:]: np.ascontiguousarray(g[k][:, :NCOL]) for k in g.files if k.startswith("in_")}
+    x5["pqs"] = np.ascontiguousarray(g["pqs"][:, :NCOL])
+    return g, fd, x5
+
+
+def test_tl_and_ad_kernels_match_reference_derivative_input_by_input(pkg):
+    """tests/golden/tl_fd_dirs.npz (finite differences of the reference's Python NL kernel along 16
+    single-input and 2 random directions): every column of the CUDA TL Jacobian on its own, and every row
+    of the CUDA adjoint through <D_k, y> = <dx_k, M'^T y>.  Per-block Fortran-ABI entries, PQS5 / PQS'
+    supplied like CALL CLOUDSC2TL / CLOUDSC2AD."""
+    import ctypes as C
+    from tests.fd_directions import IN16, NAMES, OUT7, directions
+    g, fd, x5 = _dirs_case()
+    lib = pkg.load_library()
+    klev, klon = x5["ptm1"].shape
+    half = lambda n: klev + (1 if n == "paphp1" or n.startswith("pf") else 0)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ref = lambda v: C.byref(C.c_int(v))
+    ptsphy = float(g["ptsphy"])
+    dirs = directions(x5)
+    rng = np.random.default_rng(23)
+    y = {n: np.zeros((half(n), klon)) for n in OUT10}
+    for n in OUT7:
+        m = np.ones_like(fd[f"m00_{n}"], dtype=bool)
+        for i in range(len(dirs)):
+            m &= fd[f"m{i:02d}_{n}"]
+        y[n] = np.ascontiguousarray(rng.uniform(0.5, 1.5, m.shape) * m)
+    with pkg.Cloudsc2(pkg.default_params(lregcl=False), klev, g["ceta"]) as gpu:
+        gpu._bind()
+        for i, dx in enumerate(dirs):
+            traj = {**x5, **{n: np.zeros((half(n), klon)) for n in OUT10}}
+            incr = {**{k: v.copy() for k, v in dx.items()}, **{n: np.zeros((half(n), klon)) for n in OUT10}}
+            lib.cloudsc2tl_(ref(1), ref(klon), ref(klon), ref(1), ref(klev), ref(0), C.byref(C.c_double(ptsphy)),
+                            *[dp(traj[n]) for n in ORDER26], *[dp(incr[n]) for n in ORDER26])
+            for n in OUT7:
+                d, m = fd[f"d{i:02d}_{n}"], fd[f"m{i:02d}_{n}"]
+                tol = 1e-6 * max(np.abs(d).max(), 1e-300) + 2e-10 * np.abs(traj[n]).max()
+                assert (np.abs(incr[n] - d) * m).max() <= tol, (NAMES[i], n)
+        traj = {**x5, **{n: np.zeros((half(n), klon)) for n in OUT10}}
+        adj = {**{k: np.zeros_like(v) for k, v in x5.items()}, **{n: v.copy() for n, v in y.items()}}
+        lib.cloudsc2ad_(ref(1), ref(klon), ref(klon), ref(1), ref(klev), ref(0), C.byref(C.c_double(ptsphy)),
+                        *[dp(traj[n]) for n in ORDER26], *[dp(adj[n]) for n in ORDER26])
+    for i, dx in enumerate(dirs):
+        lhs = sum(float((fd[f"d{i:02d}_{n}"] * y[n]).sum()) for n in OUT7)
+        rhs = sum(float((dx[k] * adj[k]).sum()) for k in IN16 if k != "psupsat")
+        rhs += float((dx["psupsat"] * adj["psupsat"]).sum()) / ptsphy      # cloudsc2ad.F90:1733
+        scale = sum(float(np.abs(fd[f"d{i:02d}_{n}"] * y[n]).sum()) for n in OUT7)
+        assert scale > 0 and abs(lhs - rhs) <= 2e-6 * scale, (NAMES[i], lhs, rhs)

@@ -2,6 +2,7 @@
 own Python kernel, and against the reference's own known-answer properties (Taylor test,
 adjoint dot-product test).  No GPU, no /root/reference."""
 import numpy as np
+import pytest
 
 # |oracle - reference python| <= RTOL_PY * max|field| : the two differ only by libm-vs-numpy exp and
 # x**2-vs-x*x rounding (measured 2e-15).
@@ -126,6 +127,62 @@ def test_tl_oracle_matches_finite_differences_of_reference_python_kernel(pkg, ob
         tol = (1e-6 if n == "pclc" else 1e-7) * max(np.abs(d).max(), 1e-300)   # finite-difference error: measured <= 2e-8
         assert np.abs(dy[n] - d).max() <= tol, n
         assert fd["curv_" + n].max() <= 1e-6 * max(np.abs(d).max(), 1e-300) * float(fd["eps"]) * 1e4, n
+
+
+def _dirs_case():
+    from pathlib import Path
+    from tests.fd_directions import NCOL
+    gdir = Path(__file__).resolve().parent / "golden"
+    g, fd = np.load(gdir / "nl_pyref.npz"), np.load(gdir / "tl_fd_dirs.npz")
+    x5 = {k[3:]: np.ascontiguousarray(g[k][:, :NCOL]) for k in g.files if k.startswith("in_")}
+    x5["pqs"] = np.ascontiguousarray(g["pqs"][:, :NCOL])
+    return g, fd, x5
+
+
+@pytest.mark.parametrize("obname", ["ob", "obref"])
+def test_tl_matches_reference_derivative_input_by_input(pkg, request, obname):
+    """tests/golden/tl_fd_dirs.npz: finite differences of the reference's Python NL kernel along 16
+    single-input directions and 2 random ones.  Every column of the TL Jacobian is checked on its own
+    (the one-direction golden could hide errors that compensate between inputs).  Tolerance: 1e-6 of
+    the direction's largest derivative + the rounding noise of the difference quotient
+    (2e-10 max|F|), on the points whose second difference is smooth.  Both the hand oracle and the
+    transliterated Fortran (oracle/_ref) must pass."""
+    from tests.fd_directions import NAMES, OUT7, directions
+    o = request.getfixturevalue(obname)
+    g, fd, x5 = _dirs_case()
+    for i, dx in enumerate(directions(x5)):
+        y5, dy = o.cloudsc2tl_block(pkg.default_params(lregcl=False), g["ceta"], float(g["ptsphy"]), x5, dx)
+        for n in OUT7:
+            d, m = fd[f"d{i:02d}_{n}"], fd[f"m{i:02d}_{n}"]
+            tol = 1e-6 * max(np.abs(d).max(), 1e-300) + 2e-10 * np.abs(y5[n]).max()
+            assert (np.abs(dy[n] - d) * m).max() <= tol, (NAMES[i], n)
+            assert m.mean() > 0.9, (NAMES[i], n)
+
+
+def test_ad_is_the_transpose_input_by_input(pkg, ob):
+    """<D_k, y> = <dx_k, M'^T y> for each of the 16 single-input directions: row k of the adjoint against
+    column k of the reference derivative."""
+    from tests.fd_directions import IN16, NAMES, OUT7, directions
+    g, fd, x5 = _dirs_case()
+    klev, klon = x5["ptm1"].shape
+    rng = np.random.default_rng(23)
+    ptsphy = float(g["ptsphy"])
+    dirs = directions(x5)
+    # one adjoint run with a fixed y supported on the smooth points of every direction
+    y = {n: np.zeros((klev + (1 if n.startswith("pf") else 0), klon)) for n in ob.OUT10}
+    for n in OUT7:
+        m = np.ones_like(fd[f"m00_{n}"], dtype=bool)
+        for i in range(len(dirs)):
+            m &= fd[f"m{i:02d}_{n}"]
+        y[n] = np.ascontiguousarray(rng.uniform(0.5, 1.5, m.shape) * m)
+    adj = ob.alloc16(klev, klon)
+    ob.cloudsc2ad_block(pkg.default_params(lregcl=False), g["ceta"], ptsphy, x5, adj, {n: v.copy() for n, v in y.items()})
+    for i, dx in enumerate(dirs):
+        lhs = sum(float((fd[f"d{i:02d}_{n}"] * y[n]).sum()) for n in OUT7)
+        rhs = sum(float((dx[k] * adj[k]).sum()) for k in IN16 if k != "psupsat")
+        rhs += float((dx["psupsat"] * adj["psupsat"]).sum()) / ptsphy      # cloudsc2ad.F90:1733, see above
+        scale = sum(float(np.abs(fd[f"d{i:02d}_{n}"] * y[n]).sum()) for n in OUT7)
+        assert scale > 0 and abs(lhs - rhs) <= 2e-6 * scale, (NAMES[i], lhs, rhs)
 
 
 def test_ad_oracle_is_the_transpose_of_the_reference_derivative(pkg, ob, golden_fd):
