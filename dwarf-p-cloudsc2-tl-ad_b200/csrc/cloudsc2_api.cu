@@ -117,79 +117,224 @@ int check_fields(const cloudsc2_fields *f) {
   return 0;
 }
 
-// Device copy of a whole problem in the reference layout (used by the host-pointer wrappers of
-// the TL / AD / test entry points, which are correctness paths, not throughput paths).
-struct DevProblem {
-  cloudsc2_fields f;
-  size_t n2b, n2hb;   // doubles per plain array / per half-level array
-  size_t n2, n2h;     // doubles per block of a plain / half-level array
-  int nblocks;
-};
-// Inputs always go up.  Outputs are written completely by the kernels except (a) the padding columns of
-// a ragged last block and (b) the B_LOC slabs nobody writes (A, QR, QS: never downloaded), so only the
-// last block's outputs are uploaded when NGPTOT is not a multiple of NPROMA -- or everything when the
-// caller asks for it (all_outputs: the device arrays must start from the host's values, e.G. the
-// trajectory fluxes of option ad_have_trajectory).
-int upload_problem(const cloudsc2_fields *h, int nproma, int klev, int ngptot, int nblocks, DevProblem &dp,
-                   bool all_outputs = false) {
-  const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
-  dp.n2 = n2; dp.n2h = n2h; dp.nblocks = nblocks;
-  dp.n2b = n2 * nblocks;
-  dp.n2hb = n2h * nblocks;
-  const size_t in_d = 8 * dp.n2b + dp.n2hb + CLOUDSC2_NCLV * dp.n2b + CLOUDSC2_NSTATE * dp.n2b;
-  const size_t out_d = CLOUDSC2_NSTATE * dp.n2b + 2 * dp.n2b + 4 * dp.n2hb;
-  if (int rc = G.in.reserve(in_d * sizeof(double))) return rc;
-  if (int rc = G.out.reserve(out_d * sizeof(double))) return rc;
-  double *p = G.in.d();
-  auto up = [&](const double *src, size_t n, const double *&dst) -> cudaError_t {
-    dst = p;
-    cudaError_t e = cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, G.stream);
-    p += n;
-    return e;
-  };
-  CK(up(h->pt, dp.n2b, dp.f.pt)); CK(up(h->pq, dp.n2b, dp.f.pq)); CK(up(h->pap, dp.n2b, dp.f.pap));
-  CK(up(h->paph, dp.n2hb, dp.f.paph)); CK(up(h->plu, dp.n2b, dp.f.plu));
-  CK(up(h->plude, dp.n2b, dp.f.plude)); CK(up(h->pmfu, dp.n2b, dp.f.pmfu));
-  CK(up(h->pmfd, dp.n2b, dp.f.pmfd)); CK(up(h->psupsat, dp.n2b, dp.f.psupsat));
-  CK(up(h->pclv, CLOUDSC2_NCLV * dp.n2b, dp.f.pclv));
-  CK(up(h->b_cml, CLOUDSC2_NSTATE * dp.n2b, dp.f.b_cml));
-  double *q = G.out.d();
-  dp.f.b_loc = q; q += CLOUDSC2_NSTATE * dp.n2b;
-  dp.f.pa = q; q += dp.n2b;
-  dp.f.pcovptot = q; q += dp.n2b;
-  dp.f.pfplsl = q; q += dp.n2hb; dp.f.pfplsn = q; q += dp.n2hb;
-  dp.f.pfhpsl = q; q += dp.n2hb; dp.f.pfhpsn = q; q += dp.n2hb;
-  const bool ragged = ngptot % nproma != 0;
-  if (all_outputs || ragged) {
-    // blocks [b0, nblocks) of every output array start from the caller's values
-    const size_t b0 = all_outputs ? 0 : (size_t)nblocks - 1, nb = (size_t)nblocks - b0;
+int host_worker_threads();
+
+// ---- chunked host pipeline, shared by the five host-pointer entry points ---------------------------
+// The blocked HOST arrays of the caller are processed in chunks of whole blocks on three streams so that
+// the H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full
+// duplex).  Only the slabs the kernels touch cross the bus -- PCLV 2 of 5 species, B_CML 4 of 8 slabs,
+// B_LOC 4 (5) of 8 slabs -- into a compact device layout:
+//   in : [8 plain | paph | cld(2) | cml(4)]      out : [loc(5) | pa | pcov | 4 flux]     (x nblocks each)
+struct HostPipe {
+  int nproma = 0, klev = 0, ngptot = 0;
+  size_t nb = 0, n2 = 0, n2h = 0;
+  const cloudsc2_fields *h = nullptr;
+  double *d_pt = nullptr, *d_pq = nullptr, *d_pap = nullptr, *d_plu = nullptr, *d_plude = nullptr, *d_pmfu = nullptr,
+         *d_pmfd = nullptr, *d_psupsat = nullptr, *d_paph = nullptr, *d_cld = nullptr, *d_cml = nullptr;
+  double *d_loc = nullptr, *d_pa = nullptr, *d_pcov = nullptr, *d_fl = nullptr, *d_fn = nullptr, *d_hl = nullptr,
+         *d_hn = nullptr;
+  std::vector<size_t> plan;      // blocks per chunk
+  // derive: PCOVPTOT, TENDENCY_LOC%CLD(:,:,NCLV) (identically zero) and PFHPSL/PFHPSN (= -PFPLSL*RLVTT,
+  // -PFPLSN*RLSTT) are filled on the host instead of crossing PCIe (NL entry only, option e2e_host_derive)
+  bool derive = false;
+  // driver_level: the DRIVER zeroes PCOVPTOT and CLD(:,:,NCLV) of whole blocks (cloudsc_driver_mod.F90:87-88);
+  // otherwise (CLOUDSC2TL / CLOUDSC2AD call semantics) slab 7 is not touched and padding columns keep PCOVPTOT
+  bool driver_level = true;
+
+  int init(int nproma_, int klev_, int ngptot_, const cloudsc2_fields *h_, size_t extra_doubles_per_block) {
+    nproma = nproma_; klev = klev_; ngptot = ngptot_; h = h_;
+    nb = (size_t)nblocks_of(ngptot, nproma);
+    n2 = (size_t)nproma * klev; n2h = (size_t)nproma * (klev + 1);
     const size_t D = sizeof(double);
-    CK(cudaMemcpyAsync(dp.f.b_loc + CLOUDSC2_NSTATE * n2 * b0, h->b_loc + CLOUDSC2_NSTATE * n2 * b0, CLOUDSC2_NSTATE * n2 * nb * D, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaMemcpyAsync(dp.f.pa + n2 * b0, h->pa + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaMemcpyAsync(dp.f.pcovptot + n2 * b0, h->pcovptot + n2 * b0, n2 * nb * D, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaMemcpyAsync(dp.f.pfplsl + n2h * b0, h->pfplsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaMemcpyAsync(dp.f.pfplsn + n2h * b0, h->pfplsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaMemcpyAsync(dp.f.pfhpsl + n2h * b0, h->pfhpsl + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
-    CK(cudaMemcpyAsync(dp.f.pfhpsn + n2h * b0, h->pfhpsn + n2h * b0, n2h * nb * D, cudaMemcpyHostToDevice, G.stream));
+    const size_t in_blk = 8 * n2 + n2h + 2 * n2 + 4 * n2;
+    const size_t out_blk = 5 * n2 + 2 * n2 + 4 * n2h;
+    if (int rc = G.in.reserve(in_blk * nb * D)) return rc;
+    if (int rc = G.out.reserve(out_blk * nb * D)) return rc;
+    double *di = G.in.d(), *dout = G.out.d();
+    d_pt = di; d_pq = d_pt + n2 * nb; d_pap = d_pq + n2 * nb; d_plu = d_pap + n2 * nb; d_plude = d_plu + n2 * nb;
+    d_pmfu = d_plude + n2 * nb; d_pmfd = d_pmfu + n2 * nb; d_psupsat = d_pmfd + n2 * nb; d_paph = d_psupsat + n2 * nb;
+    d_cld = d_paph + n2h * nb; d_cml = d_cld + 2 * n2 * nb;
+    d_loc = dout; d_pa = d_loc + 5 * n2 * nb; d_pcov = d_pa + n2 * nb; d_fl = d_pcov + n2 * nb; d_fn = d_fl + n2h * nb;
+    d_hl = d_fn + n2h * nb; d_hn = d_hl + n2h * nb;
+    // Chunk plan: each async copy costs ~10 us of host enqueue time, so chunks should be large
+    // (measured at 163 840 columns: 8-48 MB chunks 68-69 ms, 128 MB 61 ms, 400 MB 59 ms), but the
+    // first H2D and the last D2H are not overlapped with anything, so the plan ramps up from 16 MB,
+    // doubling to the cap (CSC2_E2E_CHUNK_MB, default 256), and ramps down again at the end.
+    opts.load();
+    const size_t chunk_mb = (size_t)opts.e2e_chunk_mb;
+    const size_t blk_bytes = (in_blk + extra_doubles_per_block) * D;
+    auto blocks_of = [&](size_t mb) { return std::max<size_t>(1, (mb << 20) / blk_bytes); };
+    std::vector<size_t> up;
+    for (size_t mb = 16; mb < chunk_mb; mb *= 2) up.push_back(blocks_of(mb));
+    size_t ramp = 0;
+    for (size_t b : up) ramp += b;
+    plan.clear();
+    if (2 * ramp >= nb) {
+      // small problem: equal chunks of at most 16 MB, at least 3 so that the streams overlap
+      const size_t per = std::max<size_t>(1, std::min(blocks_of(16), (nb + 2) / 3));
+      for (size_t b0 = 0; b0 < nb; b0 += per) plan.push_back(std::min(per, nb - b0));
+    } else {
+      for (size_t b : up) plan.push_back(b);
+      size_t mid = nb - 2 * ramp;
+      const size_t cap = blocks_of(chunk_mb);
+      const size_t nmid = (mid + cap - 1) / cap;
+      for (size_t i = 0; i < nmid; ++i) {
+        const size_t b = mid / (nmid - i);
+        plan.push_back(b);
+        mid -= b;
+      }
+      for (size_t i = up.size(); i-- > 0;) plan.push_back(up[i]);
+    }
+    return 0;
   }
-  return 0;
-}
-// B_LOC: only the slabs the kernels write come back -- T (0) and Q, QL, QI (2-4); CLD(:,:,NCLV) (7) when
-// the driver-level zeroing ran (loc_last).  A, QR, QS keep the host's values ("never written by
-// anyone").
-int download_outputs(const cloudsc2_fields *h, const DevProblem &dp, bool loc_last) {
-  const size_t D = sizeof(double), n2 = dp.n2, pitch = CLOUDSC2_NSTATE * dp.n2 * D;
-  CK(cudaMemcpy2DAsync(h->b_loc, pitch, dp.f.b_loc, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpy2DAsync(h->b_loc + 2 * n2, pitch, dp.f.b_loc + 2 * n2, pitch, 3 * n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, G.stream));
-  if (loc_last)
-    CK(cudaMemcpy2DAsync(h->b_loc + 7 * n2, pitch, dp.f.b_loc + 7 * n2, pitch, n2 * D, dp.nblocks, cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpyAsync(h->pa, dp.f.pa, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpyAsync(h->pcovptot, dp.f.pcovptot, dp.n2b * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpyAsync(h->pfplsl, dp.f.pfplsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpyAsync(h->pfplsn, dp.f.pfplsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpyAsync(h->pfhpsl, dp.f.pfhpsl, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaMemcpyAsync(h->pfhpsn, dp.f.pfhpsn, dp.n2hb * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  CK(cudaStreamSynchronize(G.stream));
+
+  Geom geom(size_t b0, size_t cb) const {
+    return Geom{nproma, klev, (int)std::min<long long>((long long)cb * nproma, (long long)ngptot - (long long)b0 * nproma), (int)cb};
+  }
+  void views(size_t b0, TrajIn &in, TrajOut &out) const {
+    in.paph = d_paph + n2h * b0; in.pap = d_pap + n2 * b0; in.pq = d_pq + n2 * b0; in.pt = d_pt + n2 * b0;
+    in.pl = d_cld + 2 * n2 * b0; in.pi = in.pl + n2; in.plude = d_plude + n2 * b0; in.plu = d_plu + n2 * b0;
+    in.pmfu = d_pmfu + n2 * b0; in.pmfd = d_pmfd + n2 * b0;
+    in.gt = d_cml + 4 * n2 * b0; in.gq = in.gt + n2; in.gl = in.gt + 2 * n2; in.gi = in.gt + 3 * n2;
+    in.psupsat = d_psupsat + n2 * b0; in.pqs = nullptr; in.bs_cld = 2 * n2; in.bs_cml = 4 * n2;
+    out.tent = d_loc + 5 * n2 * b0; out.tenq = out.tent + n2; out.tenl = out.tent + 2 * n2;
+    out.teni = out.tent + 3 * n2; out.loc_last = driver_level ? out.tent + 4 * n2 : nullptr; out.bs_loc = 5 * n2;
+    out.pclc = d_pa + n2 * b0; out.pcovptot = d_pcov + n2 * b0; out.pfplsl = d_fl + n2h * b0;
+    out.pfplsn = d_fn + n2h * b0; out.pfhpsl = d_hl + n2h * b0; out.pfhpsn = d_hn + n2h * b0;
+  }
+
+  // inputs of blocks [b0, b0+cb); outputs of the blocks whose device copy must start from the caller's values:
+  // the ragged last block (padding columns keep them) or all of them (all_outputs)
+  int upload(size_t b0, size_t cb, cudaStream_t s, bool all_outputs) const {
+    const size_t D = sizeof(double);
+    auto h2d = [&](double *dst, const double *src, size_t per_blk) {
+      return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyHostToDevice, s);
+    };
+    CK(h2d(d_pt, h->pt, n2)); CK(h2d(d_pq, h->pq, n2)); CK(h2d(d_pap, h->pap, n2));
+    CK(h2d(d_plu, h->plu, n2)); CK(h2d(d_plude, h->plude, n2)); CK(h2d(d_pmfu, h->pmfu, n2));
+    CK(h2d(d_pmfd, h->pmfd, n2)); CK(h2d(d_psupsat, h->psupsat, n2)); CK(h2d(d_paph, h->paph, n2h));
+    // PCLV species QL,QI (slabs 0-1 of 5)
+    CK(cudaMemcpy2DAsync(d_cld + 2 * n2 * b0, 2 * n2 * D, h->pclv + 5 * n2 * b0, 5 * n2 * D, 2 * n2 * D, cb, cudaMemcpyHostToDevice, s));
+    // B_CML slab T (0) and slabs Q,QL,QI (2-4) of 8
+    CK(cudaMemcpy2DAsync(d_cml + 4 * n2 * b0, 4 * n2 * D, h->b_cml + 8 * n2 * b0, 8 * n2 * D, n2 * D, cb, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpy2DAsync(d_cml + 4 * n2 * b0 + n2, 4 * n2 * D, h->b_cml + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, 3 * n2 * D, cb, cudaMemcpyHostToDevice, s));
+    const bool ragged = geom(b0, cb).ngptot < (int)(cb * nproma);
+    if (all_outputs || ragged) {
+      const size_t lb = all_outputs ? b0 : b0 + cb - 1, nbk = b0 + cb - lb;
+      CK(cudaMemcpy2DAsync(d_loc + 5 * n2 * lb, 5 * n2 * D, h->b_loc + 8 * n2 * lb, 8 * n2 * D, n2 * D, nbk, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpy2DAsync(d_loc + 5 * n2 * lb + n2, 5 * n2 * D, h->b_loc + 8 * n2 * lb + 2 * n2, 8 * n2 * D, 3 * n2 * D, nbk, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_pa + n2 * lb, h->pa + n2 * lb, n2 * nbk * D, cudaMemcpyHostToDevice, s));
+      if (!driver_level) CK(cudaMemcpyAsync(d_pcov + n2 * lb, h->pcovptot + n2 * lb, n2 * nbk * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_fl + n2h * lb, h->pfplsl + n2h * lb, n2h * nbk * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_fn + n2h * lb, h->pfplsn + n2h * lb, n2h * nbk * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_hl + n2h * lb, h->pfhpsl + n2h * lb, n2h * nbk * D, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_hn + n2h * lb, h->pfhpsn + n2h * lb, n2h * nbk * D, cudaMemcpyHostToDevice, s));
+    }
+    return 0;
+  }
+
+  // B_LOC: only the slabs the kernels write come back -- T (0) and Q, QL, QI (2-4); CLD(:,:,NCLV) (7) when
+  // the driver-level zeroing ran.  A, QR, QS keep the host's values ("never written by anyone").
+  int download(size_t b0, size_t cb, cudaStream_t s) const {
+    const size_t D = sizeof(double);
+    auto d2h = [&](double *dst, const double *src, size_t per_blk) {
+      return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyDeviceToHost, s);
+    };
+    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0, 8 * n2 * D, d_loc + 5 * n2 * b0, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + n2, 5 * n2 * D, 3 * n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    if (driver_level && !derive)
+      CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 7 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + 4 * n2, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
+    CK(d2h(h->pa, d_pa, n2));
+    CK(d2h(h->pfplsl, d_fl, n2h)); CK(d2h(h->pfplsn, d_fn, n2h));
+    if (!derive) {
+      CK(d2h(h->pcovptot, d_pcov, n2));
+      CK(d2h(h->pfhpsl, d_hl, n2h)); CK(d2h(h->pfhpsn, d_hn, n2h));
+    }
+    return 0;
+  }
+
+  // host side of the derived outputs of blocks [b0, b0+cb), after their PFPLSL / PFPLSN have landed
+  void derive_host(size_t b0, size_t cb) const {
+    const double rlvtt = G.prm.rlvtt, rlstt = G.prm.rlstt;
+    const int nthr = host_worker_threads();
+    const size_t D = sizeof(double);
+    const long long blk_lo = (long long)b0, blk_hi = (long long)(b0 + cb);
+    const cloudsc2_fields *hh = h;
+    const int np = nproma, kl = klev, ng = ngptot;
+    const size_t m2 = n2, m2h = n2h;
+#pragma omp parallel for schedule(static) num_threads(nthr)
+    for (long long b = blk_lo; b < blk_hi; ++b) {
+      const int icend = (int)std::min<long long>(np, (long long)ng - b * np);
+      std::memset(hh->pcovptot + m2 * b, 0, m2 * D);                  // whole block (driver_mod.F90:87)
+      std::memset(hh->b_loc + 8 * m2 * b + 7 * m2, 0, m2 * D);        // %CLD(:,:,NCLV) (:88)
+      const double *fl = hh->pfplsl + m2h * b, *fn = hh->pfplsn + m2h * b;
+      double *hl = hh->pfhpsl + m2h * b, *hn = hh->pfhpsn + m2h * b;
+      for (int jk = 0; jk <= kl; ++jk)
+        for (int jl = 0; jl < icend; ++jl) {                          // columns beyond ICEND keep their values
+          const size_t i = (size_t)jk * np + jl;
+          hl[i] = -fl[i] * rlvtt;
+          hn[i] = -fn[i] * rlstt;
+        }
+    }
+  }
+};
+
+// per-chunk events; destroyed on every exit path (an error return must not leak them)
+struct Events {
+  std::vector<cudaEvent_t> v;
+  explicit Events(size_t n) : v(n, nullptr) {}
+  ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+  cudaEvent_t &operator[](size_t i) { return v[i]; }
+};
+
+// Run the pipeline: per chunk  upload -> launch(b0, cb, geo, in, out, stream) -> download  on stream ic % 3.
+// `launch` enqueues the chunk's kernels (and any extra copies of its own) and returns 0 or an error code.
+// On return every stream has been joined into the context's main stream and synchronised.
+template <class Launch>
+int run_pipeline(HostPipe &P, bool all_outputs, Launch &&launch, double *elapsed_kernel_s, double *elapsed_total_s) {
+  const size_t nchunks = P.plan.size();
+  Events k0(nchunks), k1(nchunks), dn(nchunks);
+  for (size_t i = 0; i < nchunks; ++i) {
+    CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i]));
+    CK(cudaEventCreateWithFlags(&dn[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(G.ev[0], G.stream));
+  for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(G.pipe[i], G.ev[0], 0));
+  size_t b0 = 0;
+  for (size_t ic = 0; ic < nchunks; b0 += P.plan[ic], ++ic) {
+    cudaStream_t s = G.pipe[ic % kStreams];
+    const size_t cb = P.plan[ic];
+    if (int rc = P.upload(b0, cb, s, all_outputs)) return rc;
+    TrajIn in; TrajOut out;
+    P.views(b0, in, out);
+    CK(cudaEventRecord(k0[ic], s));
+    if (int rc = launch(b0, cb, P.geom(b0, cb), in, out, s)) return rc;
+    CK(cudaEventRecord(k1[ic], s));
+    if (int rc = P.download(b0, cb, s)) return rc;
+    CK(cudaEventRecord(dn[ic], s));
+  }
+  if (P.derive) {
+    size_t c0 = 0;
+    for (size_t ic = 0; ic < nchunks; c0 += P.plan[ic], ++ic) {
+      CK(cudaEventSynchronize(dn[ic]));
+      P.derive_host(c0, P.plan[ic]);
+    }
+  }
+  for (int i = 0; i < kStreams; ++i) {
+    CK(cudaEventRecord(G.ev[2], G.pipe[i]));
+    CK(cudaStreamWaitEvent(G.stream, G.ev[2], 0));
+  }
+  CK(cudaEventRecord(G.ev[1], G.stream));
+  CK(cudaEventSynchronize(G.ev[1]));
+  float ms = 0.f, kms = 0.f;
+  CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
+  for (size_t i = 0; i < nchunks; ++i) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, k0[i], k1[i]));
+    kms += t;
+  }
+  if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
+  if (elapsed_kernel_s) *elapsed_kernel_s = kms * 1e-3;
   return 0;
 }
 
@@ -438,178 +583,24 @@ int csc2_nl_host_one(int nproma, int klev, int ngptot, double ptsphy, const clou
       return 0;
     }
   }
-  const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
-  const size_t D = sizeof(double);
-  // compact device layout: [8 plain | paph | cld(2) | cml(4)] and [loc(5) | pa | pcov | 4 flux]
-  const size_t in_blk = 8 * n2 + n2h + 2 * n2 + 4 * n2;
-  const size_t out_blk = 5 * n2 + 2 * n2 + 4 * n2h;
-  if (int rc = G.in.reserve(in_blk * nblocks * D)) return rc;
-  if (int rc = G.out.reserve(out_blk * nblocks * D)) return rc;
-  double *di = G.in.d(), *dout = G.out.d();
-  const size_t nb = nblocks;
-  double *d_pt = di, *d_pq = d_pt + n2 * nb, *d_pap = d_pq + n2 * nb, *d_plu = d_pap + n2 * nb,
-         *d_plude = d_plu + n2 * nb, *d_pmfu = d_plude + n2 * nb, *d_pmfd = d_pmfu + n2 * nb,
-         *d_psupsat = d_pmfd + n2 * nb, *d_paph = d_psupsat + n2 * nb, *d_cld = d_paph + n2h * nb,
-         *d_cml = d_cld + 2 * n2 * nb;
-  double *d_loc = dout, *d_pa = d_loc + 5 * n2 * nb, *d_pcov = d_pa + n2 * nb,
-         *d_fl = d_pcov + n2 * nb, *d_fn = d_fl + n2h * nb, *d_hl = d_fn + n2h * nb,
-         *d_hn = d_hl + n2h * nb;
-
-  // chunking: ~48 MB of input per chunk, at least 1 block, at most 64 chunks
-  // Chunk plan: each async copy costs ~10 us of host enqueue time, so chunks should be large
-  // (measured at 163 840 columns: 8-48 MB chunks 68-69 ms, 128 MB 61 ms, 400 MB 59 ms), but the
-  // first H2D and the last D2H are not overlapped with anything, so the plan ramps up from 16 MB,
-  // doubling to the cap (CSC2_E2E_CHUNK_MB, default 256), and ramps down again at the end.
-  const size_t chunk_mb = (size_t)opts.e2e_chunk_mb;
-  std::vector<size_t> plan;            // blocks per chunk
-  {
-    const size_t blk_bytes = in_blk * D;
-    auto blocks_of = [&](size_t mb) { return std::max<size_t>(1, (mb << 20) / blk_bytes); };
-    std::vector<size_t> up;
-    for (size_t mb = 16; mb < chunk_mb; mb *= 2) up.push_back(blocks_of(mb));
-    size_t ramp = 0;
-    for (size_t b : up) ramp += b;
-    if (2 * ramp >= nb) {
-      // small problem: equal chunks of at most 16 MB, at least 3 so that the streams overlap
-      const size_t per = std::max<size_t>(1, std::min(blocks_of(16), (nb + 2) / 3));
-      for (size_t b0 = 0; b0 < nb; b0 += per) plan.push_back(std::min(per, nb - b0));
-    } else {
-      for (size_t b : up) plan.push_back(b);
-      size_t mid = nb - 2 * ramp;
-      const size_t cap = blocks_of(chunk_mb);
-      const size_t nmid = (mid + cap - 1) / cap;
-      for (size_t i = 0; i < nmid; ++i) {
-        const size_t b = mid / (nmid - i);
-        plan.push_back(b);
-        mid -= b;
-      }
-      for (size_t i = up.size(); i-- > 0;) plan.push_back(up[i]);
-    }
-  }
-  const size_t nchunks = plan.size();
-  const KConst kc = make_kconst(ptsphy);
-
   // Four of the eleven output arrays need not cross PCIe: PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV)
   // are identically zero (cloudsc_driver_mod.F90:87-88; cloudsc2.F90 never raises PCOVPTOT with
   // LEVAPLS2 off), PFHPSL = -PFPLSL*RLVTT and PFHPSN = -PFPLSN*RLSTT (:730-735) are one exact
   // multiplication of arrays that are copied anyway.  The host fills them per chunk as soon as the
   // chunk's D2H has landed, overlapped with the transfers of the later chunks; that leaves the
   // H2D direction -- the bound of this call -- less disturbed by D2H traffic.
-  const bool derive = opts.e2e_host_derive != 0;
-  // per-chunk events; destroyed on every exit path (an error return must not leak them)
-  struct Events {
-    std::vector<cudaEvent_t> v;
-    explicit Events(size_t n) : v(n, nullptr) {}
-    ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
-    cudaEvent_t &operator[](size_t i) { return v[i]; }
-  } k0(nchunks), k1(nchunks), dn(nchunks);
-  for (size_t i = 0; i < nchunks; ++i) {
-    CK(cudaEventCreate(&k0[i])); CK(cudaEventCreate(&k1[i]));
-    CK(cudaEventCreateWithFlags(&dn[i], cudaEventDisableTiming));
-  }
-  CK(cudaEventRecord(G.ev[0], G.stream));
-  for (int i = 0; i < kStreams; ++i) CK(cudaStreamWaitEvent(G.pipe[i], G.ev[0], 0));
-
-  size_t b0 = 0;
-  for (size_t ic = 0; ic < nchunks; b0 += plan[ic], ++ic) {
-    cudaStream_t s = G.pipe[ic % kStreams];
-    const size_t cb = plan[ic];
-    auto h2d = [&](double *dst, const double *src, size_t per_blk) {
-      return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyHostToDevice, s);
-    };
-    CK(h2d(d_pt, h->pt, n2)); CK(h2d(d_pq, h->pq, n2)); CK(h2d(d_pap, h->pap, n2));
-    CK(h2d(d_plu, h->plu, n2)); CK(h2d(d_plude, h->plude, n2)); CK(h2d(d_pmfu, h->pmfu, n2));
-    CK(h2d(d_pmfd, h->pmfd, n2)); CK(h2d(d_psupsat, h->psupsat, n2)); CK(h2d(d_paph, h->paph, n2h));
-    // PCLV species QL,QI (slabs 0-1 of 5)
-    CK(cudaMemcpy2DAsync(d_cld + 2 * n2 * b0, 2 * n2 * D, h->pclv + 5 * n2 * b0, 5 * n2 * D, 2 * n2 * D, cb, cudaMemcpyHostToDevice, s));
-    // B_CML slab T (0) and slabs Q,QL,QI (2-4) of 8
-    CK(cudaMemcpy2DAsync(d_cml + 4 * n2 * b0, 4 * n2 * D, h->b_cml + 8 * n2 * b0, 8 * n2 * D, n2 * D, cb, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpy2DAsync(d_cml + 4 * n2 * b0 + n2, 4 * n2 * D, h->b_cml + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, 3 * n2 * D, cb, cudaMemcpyHostToDevice, s));
-
-    Geom geo{nproma, klev, (int)std::min<long long>((long long)cb * nproma, (long long)ngptot - (long long)b0 * nproma), (int)cb};
-    TrajIn in;
-    in.paph = d_paph + n2h * b0; in.pap = d_pap + n2 * b0; in.pq = d_pq + n2 * b0; in.pt = d_pt + n2 * b0;
-    in.pl = d_cld + 2 * n2 * b0; in.pi = in.pl + n2; in.plude = d_plude + n2 * b0; in.plu = d_plu + n2 * b0;
-    in.pmfu = d_pmfu + n2 * b0; in.pmfd = d_pmfd + n2 * b0;
-    in.gt = d_cml + 4 * n2 * b0; in.gq = in.gt + n2; in.gl = in.gt + 2 * n2; in.gi = in.gt + 3 * n2;
-    in.psupsat = d_psupsat + n2 * b0; in.pqs = nullptr; in.bs_cld = 2 * n2; in.bs_cml = 4 * n2;
-    TrajOut out;
-    out.tent = d_loc + 5 * n2 * b0; out.tenq = out.tent + n2; out.tenl = out.tent + 2 * n2;
-    out.teni = out.tent + 3 * n2; out.loc_last = out.tent + 4 * n2; out.bs_loc = 5 * n2;
-    out.pclc = d_pa + n2 * b0; out.pcovptot = d_pcov + n2 * b0; out.pfplsl = d_fl + n2h * b0;
-    out.pfplsn = d_fn + n2h * b0; out.pfhpsl = d_hl + n2h * b0; out.pfhpsn = d_hn + n2h * b0;
-    if (geo.ngptot < (int)(cb * nproma)) {
-      // the last block has padding columns whose outputs must keep the caller's values
-      const size_t lb = b0 + cb - 1;
-      CK(cudaMemcpy2DAsync(d_loc + 5 * n2 * lb, n2 * D, h->b_loc + 8 * n2 * lb, n2 * D, n2 * D, 1, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_loc + 5 * n2 * lb + n2, h->b_loc + 8 * n2 * lb + 2 * n2, 3 * n2 * D, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_pa + n2 * lb, h->pa + n2 * lb, n2 * D, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_fl + n2h * lb, h->pfplsl + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_fn + n2h * lb, h->pfplsn + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_hl + n2h * lb, h->pfhpsl + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_hn + n2h * lb, h->pfhpsn + n2h * lb, n2h * D, cudaMemcpyHostToDevice, s));
-    }
-    CK(cudaEventRecord(k0[ic], s));
-    CK(csc2_launch_nl(kc, geo, in, out, s));
-    CK(cudaEventRecord(k1[ic], s));
-    G.launches += 1;
-
-    auto d2h = [&](double *dst, const double *src, size_t per_blk) {
-      return cudaMemcpyAsync(dst + per_blk * b0, src + per_blk * b0, per_blk * cb * D, cudaMemcpyDeviceToHost, s);
-    };
-    // B_LOC slabs T (0), Q,QL,QI (2-4) and the zeroed CLD(:,:,NCLV) (7)
-    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0, 8 * n2 * D, d_loc + 5 * n2 * b0, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 2 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + n2, 5 * n2 * D, 3 * n2 * D, cb, cudaMemcpyDeviceToHost, s));
-    if (!derive)
-      CK(cudaMemcpy2DAsync(h->b_loc + 8 * n2 * b0 + 7 * n2, 8 * n2 * D, d_loc + 5 * n2 * b0 + 4 * n2, 5 * n2 * D, n2 * D, cb, cudaMemcpyDeviceToHost, s));
-    CK(d2h(h->pa, d_pa, n2));
-    CK(d2h(h->pfplsl, d_fl, n2h)); CK(d2h(h->pfplsn, d_fn, n2h));
-    if (!derive) {
-      CK(d2h(h->pcovptot, d_pcov, n2));
-      CK(d2h(h->pfhpsl, d_hl, n2h)); CK(d2h(h->pfhpsn, d_hn, n2h));
-    }
-    CK(cudaEventRecord(dn[ic], s));
-  }
-  if (derive) {
-    // host side of the derived outputs, chunk by chunk behind the D2H of PFPLSL / PFPLSN
-    const double rlvtt = G.prm.rlvtt, rlstt = G.prm.rlstt;
-    const int nthr = host_worker_threads();
-    size_t cb0 = 0;
-    for (size_t ic = 0; ic < nchunks; cb0 += plan[ic], ++ic) {
-      CK(cudaEventSynchronize(dn[ic]));
-      const long long blk_lo = (long long)cb0, blk_hi = (long long)(cb0 + plan[ic]);
-#pragma omp parallel for schedule(static) num_threads(nthr)
-      for (long long b = blk_lo; b < blk_hi; ++b) {
-        const int icend = (int)std::min<long long>(nproma, (long long)ngptot - b * nproma);
-        std::memset(h->pcovptot + n2 * b, 0, n2 * D);                  // whole block (driver_mod.F90:87)
-        std::memset(h->b_loc + 8 * n2 * b + 7 * n2, 0, n2 * D);        // %CLD(:,:,NCLV) (:88)
-        const double *fl = h->pfplsl + n2h * b, *fn = h->pfplsn + n2h * b;
-        double *hl = h->pfhpsl + n2h * b, *hn = h->pfhpsn + n2h * b;
-        for (int jk = 0; jk <= klev; ++jk)
-          for (int jl = 0; jl < icend; ++jl) {                         // columns beyond ICEND keep their values
-            const size_t i = (size_t)jk * nproma + jl;
-            hl[i] = -fl[i] * rlvtt;
-            hn[i] = -fn[i] * rlstt;
-          }
-      }
-    }
-  }
-  for (int i = 0; i < kStreams; ++i) {
-    CK(cudaEventRecord(G.ev[2], G.pipe[i]));
-    CK(cudaStreamWaitEvent(G.stream, G.ev[2], 0));
-  }
-  CK(cudaEventRecord(G.ev[1], G.stream));
-  CK(cudaEventSynchronize(G.ev[1]));
-  float ms = 0.f, kms = 0.f;
-  CK(cudaEventElapsedTime(&ms, G.ev[0], G.ev[1]));
-  for (size_t i = 0; i < nchunks; ++i) {
-    float t = 0.f;
-    CK(cudaEventElapsedTime(&t, k0[i], k1[i]));
-    kms += t;
-  }
-  if (elapsed_total_s) *elapsed_total_s = ms * 1e-3;
-  if (elapsed_kernel_s) *elapsed_kernel_s = kms * 1e-3;
-  return 0;
+  HostPipe P;
+  if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
+  P.derive = opts.e2e_host_derive != 0;
+  P.driver_level = true;
+  const KConst kc = make_kconst(ptsphy);
+  return run_pipeline(P, false,
+                      [&](size_t, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
+                        CK(csc2_launch_nl(kc, geo, in, out, s));
+                        G.launches += 1;
+                        return 0;
+                      },
+                      elapsed_kernel_s, elapsed_total_s);
 }
 
 /* ---- tangent linear / adjoint on full fields ----------------------------------------- */
@@ -676,94 +667,133 @@ int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const c
   return 0;
 }
 
-// Host-pointer wrappers: stage everything on the device in the reference layout.
+// Host-pointer wrappers of CLOUDSC2TL / CLOUDSC2AD on full fields: the same chunked pipeline; the 16 + 10
+// increment arrays of a chunk travel with it.  TL: increments-in go up, increments-out come back (and go up
+// first for a ragged last block, whose padding columns keep the caller's values); AD: both sets go up
+// (input adjoints are accumulated, output adjoints consumed) and both come back (the latter zeroed).
 int csc2_tlad_host_one(bool is_ad, int nproma, int klev, int ngptot, double ptsphy,
                        const cloudsc2_fields *h, const cloudsc2_incr_in *a, const cloudsc2_incr_out *b) {
   if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
   if (int rc = check_incr(a, b)) return rc;
-  const int nblocks = nblocks_of(ngptot, nproma);
-  DevProblem dp;
   opts.load();
-  if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks, dp, is_ad && opts.ad_have_trajectory)) return rc;
-  const size_t tot = 15 * dp.n2b + dp.n2hb + 6 * dp.n2b + 4 * dp.n2hb;
-  if (int rc = G.work2.reserve(tot * sizeof(double))) return rc;
-  double *p = G.work2.d();
-  cloudsc2_incr_in da; cloudsc2_incr_out db;
-  struct Item { double **dev; double *host; size_t n; };
-  std::vector<Item> items = {
-      {&da.paph, a->paph, dp.n2hb}, {&da.pap, a->pap, dp.n2b}, {&da.pq, a->pq, dp.n2b},
-      {&da.pqs, a->pqs, dp.n2b}, {&da.pt, a->pt, dp.n2b}, {&da.pl, a->pl, dp.n2b},
-      {&da.pi, a->pi, dp.n2b}, {&da.plude, a->plude, dp.n2b}, {&da.plu, a->plu, dp.n2b},
-      {&da.pmfu, a->pmfu, dp.n2b}, {&da.pmfd, a->pmfd, dp.n2b}, {&da.gtent, a->gtent, dp.n2b},
-      {&da.gtenq, a->gtenq, dp.n2b}, {&da.gtenl, a->gtenl, dp.n2b}, {&da.gteni, a->gteni, dp.n2b},
-      {&da.psupsat, a->psupsat, dp.n2b}, {&db.tent, b->tent, dp.n2b}, {&db.tenq, b->tenq, dp.n2b},
-      {&db.tenl, b->tenl, dp.n2b}, {&db.teni, b->teni, dp.n2b}, {&db.pclc, b->pclc, dp.n2b},
-      {&db.pcovptot, b->pcovptot, dp.n2b}, {&db.pfplsl, b->pfplsl, dp.n2hb},
-      {&db.pfplsn, b->pfplsn, dp.n2hb}, {&db.pfhpsl, b->pfhpsl, dp.n2hb},
-      {&db.pfhpsn, b->pfhpsn, dp.n2hb}};
-  for (auto &it : items) {
-    *it.dev = p;
-    CK(cudaMemcpyAsync(p, it.host, it.n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
-    p += it.n;
+  HostPipe P;
+  const size_t n2 = (size_t)nproma * klev, n2h = (size_t)nproma * (klev + 1);
+  if (int rc = P.init(nproma, klev, ngptot, h, 21 * n2 + 5 * n2h)) return rc;
+  P.derive = false;
+  P.driver_level = false;           // CLOUDSC2TL / CLOUDSC2AD call semantics: no driver-level zeroing
+  const size_t nb = P.nb, D = sizeof(double);
+  if (int rc = G.work2.reserve((21 * n2 + 5 * n2h) * nb * D)) return rc;
+  struct Item { double *host; size_t per_blk; double *dev; bool is_out; };
+  Item items[26] = {
+      {a->paph, n2h, nullptr, false}, {a->pap, n2, nullptr, false}, {a->pq, n2, nullptr, false},
+      {a->pqs, n2, nullptr, false}, {a->pt, n2, nullptr, false}, {a->pl, n2, nullptr, false},
+      {a->pi, n2, nullptr, false}, {a->plude, n2, nullptr, false}, {a->plu, n2, nullptr, false},
+      {a->pmfu, n2, nullptr, false}, {a->pmfd, n2, nullptr, false}, {a->gtent, n2, nullptr, false},
+      {a->gtenq, n2, nullptr, false}, {a->gtenl, n2, nullptr, false}, {a->gteni, n2, nullptr, false},
+      {a->psupsat, n2, nullptr, false}, {b->tent, n2, nullptr, true}, {b->tenq, n2, nullptr, true},
+      {b->tenl, n2, nullptr, true}, {b->teni, n2, nullptr, true}, {b->pclc, n2, nullptr, true},
+      {b->pcovptot, n2, nullptr, true}, {b->pfplsl, n2h, nullptr, true}, {b->pfplsn, n2h, nullptr, true},
+      {b->pfhpsl, n2h, nullptr, true}, {b->pfhpsn, n2h, nullptr, true}};
+  {
+    double *p = G.work2.d();
+    for (Item &it : items) { it.dev = p; p += it.per_blk * nb; }
   }
-  int rc = is_ad ? cloudsc2_gpu_ad_dev(nproma, klev, ngptot, ptsphy, &dp.f, &da, &db, nullptr)
-                 : cloudsc2_gpu_tl_dev(nproma, klev, ngptot, ptsphy, &dp.f, &da, &db, nullptr);
-  if (rc) return rc;
-  for (auto &it : items)
-    CK(cudaMemcpyAsync(it.host, *it.dev, it.n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
-  return download_outputs(h, dp, false);
+  const KConst kc = make_kconst(ptsphy);
+  const bool have_traj = is_ad && opts.ad_have_trajectory;
+  auto launch = [&](size_t b0, size_t cb, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
+    const bool ragged = geo.ngptot < (int)(cb * nproma);
+    for (const Item &it : items) {
+      // TL writes every valid element of its outputs: only a ragged last block needs the caller's values first
+      size_t lb = b0, nbk = cb;
+      if (!is_ad && it.is_out) {
+        if (!ragged) continue;
+        lb = b0 + cb - 1; nbk = 1;
+      }
+      CK(cudaMemcpyAsync(it.dev + it.per_blk * lb, it.host + it.per_blk * lb, it.per_blk * nbk * D, cudaMemcpyHostToDevice, s));
+    }
+    IncIn din; IncOut dout;
+    cloudsc2_incr_in da; cloudsc2_incr_out db;
+    double **pa[16] = {&da.paph, &da.pap, &da.pq, &da.pqs, &da.pt, &da.pl, &da.pi, &da.plude, &da.plu, &da.pmfu,
+                       &da.pmfd, &da.gtent, &da.gtenq, &da.gtenl, &da.gteni, &da.psupsat};
+    double **pb[10] = {&db.tent, &db.tenq, &db.tenl, &db.teni, &db.pclc, &db.pcovptot, &db.pfplsl, &db.pfplsn,
+                       &db.pfhpsl, &db.pfhpsn};
+    for (int i = 0; i < 16; ++i) *pa[i] = items[i].dev + items[i].per_blk * b0;
+    for (int i = 0; i < 10; ++i) *pb[i] = items[16 + i].dev + items[16 + i].per_blk * b0;
+    inc_views(&da, &db, din, dout);
+    if (is_ad) {
+      // trajectory fluxes written by the forward sweep ARE the check-points (write_traj = 1): no scratch
+      ADOpts opt{0.0, 0, nullptr, nullptr, 0, 1, have_traj ? 1 : 0};
+      CK(csc2_launch_ad(kc, geo, in, out, din, dout, opt, s));
+      G.launches += have_traj ? 1 : 2;
+    } else {
+      TLOpts opt{0.0, 0, nullptr, nullptr, 0};
+      CK(csc2_launch_tl(kc, geo, in, out, din, dout, opt, s));
+      G.launches += 1;
+    }
+    for (const Item &it : items) {
+      if (!is_ad && !it.is_out) continue;                 // TL leaves its input increments alone
+      CK(cudaMemcpyAsync(it.host + it.per_blk * b0, it.dev + it.per_blk * b0, it.per_blk * cb * D, cudaMemcpyDeviceToHost, s));
+    }
+    return 0;
+  };
+  return run_pipeline(P, have_traj, launch, nullptr, nullptr);
 }
 /* ---- Taylor test ----------------------------------------------------------------------- */
 
-int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
-                               const cloudsc2_fields *dev, double znormg[10], double *ratios_blk) {
-  if (int rc = csc2_require_init()) return rc;
-  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
-  if (int rc = check_fields(dev)) return rc;
-  if (!znormg) return csc2_fail(3, "znormg is NULL");
-  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
-  const long long ncp = pad_cols((long long)geo.nblocks * nproma);
-  // scratch: tlsum[10][ncp] | diffsum[10][10][ncp]
-  if (int rc = G.work.reserve((size_t)110 * ncp * sizeof(double))) return rc;
-  // results: znormg[10] | degenerate flag | ratios[nblocks][10]
-  if (int rc = G.res.reserve((size_t)(16 + 10 * (size_t)geo.nblocks) * sizeof(double))) return rc;
-  double *tlsum = G.work.d(), *diffsum = tlsum + 10 * ncp;
-  double *d_z = G.res.d();
-  int *d_deg = reinterpret_cast<int *>(d_z + 10);
-  double *d_rat = d_z + 16;
-  const KConst kc = make_kconst(ptsphy);
-  TrajIn in; TrajOut out;
-  views_from_fields(*dev, nproma, klev, in, out);
-  cudaStream_t s = G.stream;
-  if (int rc = scratch_begin(s)) return rc;
+// scratch of one Taylor test over `whole` (all blocks of this context's shard)
+struct TaylorScratch {
+  double *tlsum = nullptr, *diffsum = nullptr;   // [10][ncp], [10][10][ncp]
+  double *d_z = nullptr, *d_rat = nullptr;       // znormg[10] | flag | ... , ratios[nblocks][10]
+  int *d_deg = nullptr;
+  long long ncp = 0;
+};
+static int taylor_reserve(const Geom &whole, TaylorScratch &t) {
+  t.ncp = pad_cols((long long)whole.nblocks * whole.nproma);
+  if (int rc = G.work.reserve((size_t)110 * t.ncp * sizeof(double))) return rc;
+  if (int rc = G.res.reserve((size_t)(16 + 10 * (size_t)whole.nblocks) * sizeof(double))) return rc;
+  t.tlsum = G.work.d();
+  t.diffsum = t.tlsum + 10 * t.ncp;
+  t.d_z = G.res.d();
+  t.d_deg = reinterpret_cast<int *>(t.d_z + 10);
+  t.d_rat = t.d_z + 16;
+  return 0;
+}
+// the three sweeps over the blocks of `geo`, whose first column is column col0 of the shard
+static int taylor_enqueue(const KConst &kc, const Geom &geo, const TrajIn &in, const TrajOut &out,
+                          const TaylorScratch &t, long long col0, cudaStream_t s) {
   // baseline NL (cloudsc_driver_tl_mod.F90:135-151)
   CK(csc2_launch_nl(kc, geo, in, out, s));
   // TL with dx = 0.01 x (:156-194); re-emits the trajectory outputs like the reference
   TrajOut out_tl = out;
   out_tl.loc_last = nullptr;
   IncIn din{}; IncOut dout{};
-  TLOpts topt{0.01, 0, tlsum, nullptr, ncp};
+  TLOpts topt{0.01, 0, t.tlsum + col0, nullptr, t.ncp};
   CK(csc2_launch_tl(kc, geo, in, out_tl, din, dout, topt, s));
   // 10 perturbed NL sweeps (:197-230) + sums of F - F5
-  CK(csc2_launch_taylor_nl(kc, geo, in, out, diffsum, ncp, s));
-  // ERROR_NORM and max over blocks (:233-252)
-  CK(csc2_launch_taylor_finalize(geo, tlsum, diffsum, ncp, d_rat, d_z, d_deg, s));
-  G.launches += 4;
+  CK(csc2_launch_taylor_nl(kc, geo, in, out, t.diffsum + col0, t.ncp, s));
+  G.launches += 3;
+  return 0;
+}
+// ERROR_NORM, max over blocks and over ranks, results to the host (synchronises s)
+static int taylor_finish(const Geom &whole, const TaylorScratch &t, double znormg[10], double *ratios_blk,
+                         cudaStream_t s) {
+  CK(csc2_launch_taylor_finalize(whole, t.tlsum, t.diffsum, t.ncp, t.d_rat, t.d_z, t.d_deg, s));   // (:233-252)
+  G.launches += 1;
   if (G.comm) {
     // reduction(max:znormg) over the ranks of the communicator (cloudsc_driver_tl_mod.F90:125), on the
     // device-resident values: non-finite ratios become a huge sentinel first (MAX drops NaN), the
     // count of degenerate blocks travels as a double and is summed
-    CK(csc2_launch_norms_prepare(d_z, 10, d_deg, d_z + 11, s));
+    CK(csc2_launch_norms_prepare(t.d_z, 10, t.d_deg, t.d_z + 11, s));
     G.launches += 1;
-    if (int rc = csc2_allreduce(G, d_z, 10, 0, s)) return rc;
-    if (int rc = csc2_allreduce(G, d_z + 11, 1, 2, s)) return rc;
+    if (int rc = csc2_allreduce(G, t.d_z, 10, 0, s)) return rc;
+    if (int rc = csc2_allreduce(G, t.d_z + 11, 1, 2, s)) return rc;
   }
   double hz[16];
-  CK(cudaMemcpyAsync(hz, d_z, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(hz, t.d_z, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (ratios_blk)
-    CK(cudaMemcpyAsync(ratios_blk, d_rat, (size_t)10 * geo.nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ratios_blk, t.d_rat, (size_t)10 * whole.nblocks * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (int rc = scratch_end(s)) return rc;
   CK(cudaStreamSynchronize(s));
   for (int i = 0; i < 10; ++i) znormg[i] = hz[i];
@@ -775,19 +805,115 @@ int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
   return 0;
 }
 
+int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
+                               const cloudsc2_fields *dev, double znormg[10], double *ratios_blk) {
+  if (int rc = csc2_require_init()) return rc;
+  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+  if (int rc = check_fields(dev)) return rc;
+  if (!znormg) return csc2_fail(3, "znormg is NULL");
+  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  TaylorScratch t;
+  if (int rc = taylor_reserve(geo, t)) return rc;
+  TrajIn in; TrajOut out;
+  views_from_fields(*dev, nproma, klev, in, out);
+  cudaStream_t s = G.stream;
+  if (int rc = scratch_begin(s)) return rc;
+  if (int rc = taylor_enqueue(make_kconst(ptsphy), geo, in, out, t, 0, s)) return rc;
+  return taylor_finish(geo, t, znormg, ratios_blk, s);
+}
+
+// Host arrays: the chunked pipeline (inputs up, three sweeps, NL outputs back, per chunk), then the norms.
 int csc2_taylor_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
                          double znormg[10], double *ratios_blk) {
   if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
-  DevProblem dp;
-  if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks_of(ngptot, nproma), dp)) return rc;
-  int rc = cloudsc2_gpu_tl_taylor_dev(nproma, klev, ngptot, ptsphy, &dp.f, znormg, ratios_blk);
-  int rc2 = download_outputs(h, dp, true);
-  return rc ? rc : rc2;
+  if (!znormg) return csc2_fail(3, "znormg is NULL");
+  HostPipe P;
+  if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
+  P.derive = false;
+  P.driver_level = true;
+  const Geom whole{nproma, klev, ngptot, (int)P.nb};
+  TaylorScratch t;
+  if (int rc = taylor_reserve(whole, t)) return rc;
+  const KConst kc = make_kconst(ptsphy);
+  if (int rc = scratch_begin(G.stream)) return rc;     // the pipe streams start behind the main stream
+  if (int rc = run_pipeline(P, false,
+                            [&](size_t b0, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
+                              return taylor_enqueue(kc, geo, in, out, t, (long long)b0 * nproma, s);
+                            },
+                            nullptr, nullptr))
+    return rc;
+  return taylor_finish(whole, t, znormg, ratios_blk, G.stream);
 }
 
 /* ---- adjoint test ------------------------------------------------------------------------ */
+
+struct AdTestScratch {
+  double *y = nullptr, *n1 = nullptr, *n2 = nullptr;   // TL outputs (6 n2b + 4 n2hb), <y,y>, <dx,dx*> per column
+  double *d_z = nullptr, *d_norms = nullptr;
+  size_t n2b = 0, n2hb = 0;
+  long long ncp = 0;
+};
+static int adtest_reserve(const Geom &whole, AdTestScratch &a) {
+  a.n2b = (size_t)whole.nproma * whole.klev * whole.nblocks;
+  a.n2hb = (size_t)whole.nproma * (whole.klev + 1) * whole.nblocks;
+  a.ncp = pad_cols((long long)whole.nblocks * whole.nproma);
+  const size_t ny = 6 * a.n2b + 4 * a.n2hb;
+  if (int rc = G.work.reserve((ny + 2 * (size_t)a.ncp) * sizeof(double))) return rc;
+  if (int rc = G.res.reserve((size_t)(16 + 3 * (size_t)a.ncp) * sizeof(double))) return rc;
+  a.y = G.work.d();
+  a.n1 = a.y + ny;
+  a.n2 = a.n1 + a.ncp;
+  a.d_z = G.res.d();
+  a.d_norms = a.d_z + 16;
+  return 0;
+}
+// TL and AD over the blocks of `geo`, which start at block b0 of the shard; `out` must carry loc_last
+static int adtest_enqueue(const KConst &kc, const Geom &geo, const TrajIn &in, TrajOut out, const AdTestScratch &a,
+                          size_t b0, cudaStream_t s) {
+  const size_t n2 = (size_t)geo.nproma * geo.klev, n2h = n2 + geo.nproma;
+  const size_t nb = a.n2b / n2;
+  double *y = a.y;
+  IncOut dout;
+  dout.tent = y + n2 * b0; dout.tenq = y + a.n2b + n2 * b0; dout.tenl = y + 2 * a.n2b + n2 * b0;
+  dout.teni = y + 3 * a.n2b + n2 * b0; dout.pclc = y + 4 * a.n2b + n2 * b0; dout.pcovptot = y + 5 * a.n2b + n2 * b0;
+  double *yh = y + 6 * a.n2b;
+  dout.pfplsl = yh + n2h * b0; dout.pfplsn = yh + a.n2hb + n2h * b0; dout.pfhpsl = yh + 2 * a.n2hb + n2h * b0;
+  dout.pfhpsn = yh + 3 * a.n2hb + n2h * b0;
+  (void)nb;
+  // the driver zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV) of every block (:112-113)
+  CK(cudaMemsetAsync(out.pcovptot, 0, n2 * geo.nblocks * sizeof(double), s));
+  CK(cudaMemset2DAsync(out.loc_last, out.bs_loc * sizeof(double), 0, n2 * sizeof(double), geo.nblocks, s));
+  out.loc_last = nullptr;
+  IncIn din{};
+  const long long col0 = (long long)b0 * geo.nproma;
+  // TL: y = M' (0.01 x), ZSUPSAT = 0 ; N1 = <y,y> per column (:160-195)
+  TLOpts topt{0.01, 1, nullptr, a.n1 + col0, a.ncp};
+  CK(csc2_launch_tl(kc, geo, in, out, din, dout, topt, s));
+  // AD applied to y with zero-initialised input adjoints; N2 = <0.01 x, M'^T y> (:198-256)
+  // the TL launch above has just written the trajectory outputs of these very inputs (cloudsc2tl.F90:
+  // 1079-1111), so the adjoint restarts from PFPLSL5 / PFPLSN5 and needs no forward sweep of its own
+  ADOpts aopt{0.01, 1, a.n2 + col0, nullptr, a.ncp, 1, 1};
+  CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
+  G.launches += 2;
+  return 0;
+}
+static int adtest_finish(const Geom &whole, const AdTestScratch &a, double *znormg, double *norms_col, cudaStream_t s) {
+  CK(csc2_launch_ad_finalize(whole, a.n1, a.n2, a.d_norms, a.d_z, s));
+  G.launches += 1;
+  // reduction(max:znormg) over the ranks (cloudsc_driver_ad_mod.F90:107); k_ad_finalize has already
+  // mapped non-finite norms to a huge value
+  if (int rc = csc2_allreduce(G, a.d_z, 1, 0, s)) return rc;
+  double hz;
+  CK(cudaMemcpyAsync(&hz, a.d_z, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (norms_col)
+    CK(cudaMemcpyAsync(norms_col, a.d_norms, (size_t)3 * whole.ngptot * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (int rc = scratch_end(s)) return rc;
+  CK(cudaStreamSynchronize(s));
+  *znormg = hz;
+  return 0;
+}
 
 int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
                              const cloudsc2_fields *dev, double *znormg, double *norms_col) {
@@ -796,53 +922,14 @@ int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
   if (int rc = check_fields(dev)) return rc;
   if (!znormg) return csc2_fail(3, "znormg is NULL");
   Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
-  const size_t n2b = (size_t)nproma * klev * geo.nblocks, n2hb = (size_t)nproma * (klev + 1) * geo.nblocks;
-  const long long ncp = pad_cols((long long)geo.nblocks * nproma);
-  // scratch: y (6 n2b + 4 n2hb) | ckpt 2*klev*ncp | n1[ncp] | n2[ncp]
-  const size_t ny = 6 * n2b + 4 * n2hb;
-  if (int rc = G.work.reserve((ny + (size_t)2 * klev * ncp + 2 * ncp) * sizeof(double))) return rc;
-  if (int rc = G.res.reserve((size_t)(16 + 3 * (size_t)ncp) * sizeof(double))) return rc;
-  double *y = G.work.d();
-  IncOut dout;
-  dout.tent = y; dout.tenq = y + n2b; dout.tenl = y + 2 * n2b; dout.teni = y + 3 * n2b;
-  dout.pclc = y + 4 * n2b; dout.pcovptot = y + 5 * n2b; dout.pfplsl = y + 6 * n2b;
-  dout.pfplsn = dout.pfplsl + n2hb; dout.pfhpsl = dout.pfplsn + n2hb; dout.pfhpsn = dout.pfhpsl + n2hb;
-  double *ckpt = y + ny, *n1 = ckpt + (size_t)2 * klev * ncp, *n2 = n1 + ncp;
-  double *d_z = G.res.d(), *d_norms = d_z + 16;
-  const KConst kc = make_kconst(ptsphy);
+  AdTestScratch a;
+  if (int rc = adtest_reserve(geo, a)) return rc;
   TrajIn in; TrajOut out;
   views_from_fields(*dev, nproma, klev, in, out);
   cudaStream_t s = G.stream;
   if (int rc = scratch_begin(s)) return rc;
-  // the driver zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV) of every block (:112-113)
-  CK(cudaMemsetAsync(out.pcovptot, 0, n2b * sizeof(double), s));
-  {
-    const size_t n2 = (size_t)nproma * klev;
-    CK(cudaMemset2DAsync(out.loc_last, CLOUDSC2_NSTATE * n2 * sizeof(double), 0, n2 * sizeof(double), geo.nblocks, s));
-  }
-  out.loc_last = nullptr;
-  IncIn din{};
-  // TL: y = M' (0.01 x), ZSUPSAT = 0 ; N1 = <y,y> per column (:160-195)
-  TLOpts topt{0.01, 1, nullptr, n1, ncp};
-  CK(csc2_launch_tl(kc, geo, in, out, din, dout, topt, s));
-  // AD applied to y with zero-initialised input adjoints; N2 = <0.01 x, M'^T y> (:198-256)
-  // the TL launch above has just written the trajectory outputs of these very inputs (cloudsc2tl.F90:
-  // 1079-1111), so the adjoint restarts from PFPLSL5 / PFPLSN5 and needs no forward sweep of its own
-  ADOpts aopt{0.01, 1, n2, ckpt, ncp, 1, 1};
-  CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
-  CK(csc2_launch_ad_finalize(geo, n1, n2, d_norms, d_z, s));
-  G.launches += 3;      // TL, AD reverse sweep, finalize
-  // reduction(max:znormg) over the ranks (cloudsc_driver_ad_mod.F90:107); k_ad_finalize has already
-  // mapped non-finite norms to a huge value
-  if (int rc = csc2_allreduce(G, d_z, 1, 0, s)) return rc;
-  double hz;
-  CK(cudaMemcpyAsync(&hz, d_z, sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (norms_col)
-    CK(cudaMemcpyAsync(norms_col, d_norms, (size_t)3 * ngptot * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (int rc = scratch_end(s)) return rc;
-  CK(cudaStreamSynchronize(s));
-  *znormg = hz;
-  return 0;
+  if (int rc = adtest_enqueue(make_kconst(ptsphy), geo, in, out, a, 0, s)) return rc;
+  return adtest_finish(geo, a, znormg, norms_col, s);
 }
 
 int csc2_adtest_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
@@ -850,11 +937,23 @@ int csc2_adtest_host_one(int nproma, int klev, int ngptot, double ptsphy, const 
   if (int rc = csc2_require_init()) return rc;
   if (int rc = check_dims(nproma, klev, ngptot)) return rc;
   if (int rc = check_fields(h)) return rc;
-  DevProblem dp;
-  if (int rc = upload_problem(h, nproma, klev, ngptot, nblocks_of(ngptot, nproma), dp)) return rc;
-  int rc = cloudsc2_gpu_ad_test_dev(nproma, klev, ngptot, ptsphy, &dp.f, znormg, norms_col);
-  int rc2 = download_outputs(h, dp, true);
-  return rc ? rc : rc2;
+  if (!znormg) return csc2_fail(3, "znormg is NULL");
+  HostPipe P;
+  if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
+  P.derive = false;
+  P.driver_level = true;
+  const Geom whole{nproma, klev, ngptot, (int)P.nb};
+  AdTestScratch a;
+  if (int rc = adtest_reserve(whole, a)) return rc;
+  const KConst kc = make_kconst(ptsphy);
+  if (int rc = scratch_begin(G.stream)) return rc;
+  if (int rc = run_pipeline(P, false,
+                            [&](size_t b0, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
+                              return adtest_enqueue(kc, geo, in, out, a, b0, s);
+                            },
+                            nullptr, nullptr))
+    return rc;
+  return adtest_finish(whole, a, znormg, norms_col, G.stream);
 }
 
 /* ---- verdicts (host, pure) ---------------------------------------------------------------- */
