@@ -54,7 +54,7 @@ TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
 # DRAM traffic per column measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over
 # 163 840 columns) and FP64-pipe utilisation of the same capture.  Every entry names the capture it comes
 # from (kernel instantiation + profiles/ file); tools/profile_r2*.sh regenerate them.
-NCU = {"nl": {"dram_bytes_per_column": 4.739e9 / 163840, "fp64_pipe_pct": 60.5, "profile": "profiles/r1c_nl_ncu.md",
+NCU = {"nl": {"dram_bytes_per_column": 4.741e9 / 163840, "fp64_pipe_pct": 60.5, "profile": "profiles/r2e_nl_ncu.md",
               "kernel": "k_cloudsc2_nl<0,2,128,128,0,0,0>"},
        "tl": {"dram_bytes_per_column": 9.236e9 / 163840, "fp64_pipe_pct": 55.9, "profile": "profiles/r2a_tl_ncu.md",
               "kernel": "k_cloudsc2_tl<0,2,0,0,2,128>"},
@@ -677,7 +677,7 @@ def main():
                              "frac": nl_gbs / peak,
                              "traffic": NCU["nl"]["dram_bytes_per_column"] * ngp,
                              "traffic_note": "bytes per launch; ncu dram__bytes_read+write of one launch at "
-                                             "163 840 columns scaled by NGPTOT (profiles/r1c_nl_ncu.md)",
+                                             "163 840 columns scaled by NGPTOT (profiles/r2e_nl_ncu.md)",
                              "peak_source": peak_src, "kernel": "k_cloudsc2_nl",
                              "algorithmic_bytes_per_column": NL_BYTES_PER_COL,
                              "algorithmic_bytes_per_launch": NL_BYTES_PER_COL * ngp,

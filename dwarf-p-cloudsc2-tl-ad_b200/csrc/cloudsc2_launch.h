@@ -75,6 +75,11 @@ cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *
                                  long long rows, long long blk_stride, int ngptot, int nblocks,
                                  long long gcol0, void *scratch, double *out5, cudaStream_t s);
 
+cudaError_t csc2_launch_validate_split(const double *ref_src, int nlon, const double *field, int nproma,
+                                       long long rows, long long blk_stride, int ngptot, int nblocks,
+                                       long long gcol0, void *scratch, double *o_min, double *o_max2,
+                                       double *o_sum2, cudaStream_t s);
+
 // Cross-rank reductions of the test norms (cloudsc2_validate_kernel.cu): see k_norms_prepare / k_fill.
 cudaError_t csc2_launch_norms_prepare(double *z, int n, const int *deg, double *deg_as_double, cudaStream_t s);
 cudaError_t csc2_launch_fill(double *z, int n, double v, cudaStream_t s);

@@ -641,6 +641,7 @@ static int load_job(int idx, void *p) {
   cudaStream_t q = c.stream;
   // FIELD_INIT of the outputs (cloudsc2_array_state_mod.F90:100-127; B_LOC zeroed for determinism)
   CK(cudaMemsetAsync(out0, 0, (size_t)(p0 - out0) * sizeof(double), q));
+  (void)out0;
   // the un-expanded columns go up once (about 4 MB), the expansion happens on the device
   const size_t k2 = (size_t)s.klon * s.klev, k2h = (size_t)s.klon * (s.klev + 1);
   const size_t src_total = 10 * k2 + k2h + CLOUDSC2_NCLV * k2 + CLOUDSC2_NSTATE * k2;
@@ -802,18 +803,16 @@ static int val_job(int idx, void *p) {
       {r_loc + 0 * n, st.f.b_loc + 0 * slab, klev, 1, bstride},
       {r_loc + 3 * n, st.f.b_loc + 3 * slab, klev, CLOUDSC2_NCLV, bstride}};
   // device layout for the collectives: mins [0..10) | maxs [16..36): vmax, maxerr | sums [48..68)
-  double *d_min = d_out, *d_max = d_out + 16, *d_sum = d_out + 48, *d_tmp = d_out + 80;
+  double *d_min = d_out, *d_max = d_out + 16, *d_sum = d_out + 48;
   CK(csc2_launch_fill(d_min, 10, 1.7976931348623157e308, q));
   CK(csc2_launch_fill(d_max, 20, -1.7976931348623157e308, q));
   CK(csc2_launch_fill(d_sum, 20, 0.0, q));
   for (int i = 0; i < CLOUDSC2_NVALIDATED && st.nblocks; ++i) {
     const long long bs = v[i].bs ? v[i].bs : (long long)nproma * v[i].nlev * v[i].ndim;
-    CK(csc2_launch_validate(v[i].ref, klon, v[i].field, nproma, (long long)v[i].nlev * v[i].ndim, bs, st.ngptot,
-                            st.nblocks, st.gcol0, scratch, d_tmp, q));
+    // results land where the collectives want them (stream order keeps the shared scratch safe)
+    CK(csc2_launch_validate_split(v[i].ref, klon, v[i].field, nproma, (long long)v[i].nlev * v[i].ndim, bs, st.ngptot,
+                                  st.nblocks, st.gcol0, scratch, d_min + i, d_max + 2 * i, d_sum + 2 * i, q));
     c.launches += 2;
-    CK(cudaMemcpyAsync(d_min + i, d_tmp + 0, sizeof(double), cudaMemcpyDeviceToDevice, q));
-    CK(cudaMemcpyAsync(d_max + 2 * i, d_tmp + 1, 2 * sizeof(double), cudaMemcpyDeviceToDevice, q));
-    CK(cudaMemcpyAsync(d_sum + 2 * i, d_tmp + 3, 2 * sizeof(double), cudaMemcpyDeviceToDevice, q));
   }
   // CLOUDSC_MPI_REDUCE_MIN / MAX / SUM (validate_mod.F90:197-199) over NVLink, on the device
   if (int rc = csc2_allreduce(c, d_min, 10, 1, q)) return rc;

@@ -139,19 +139,19 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
 #endif
 
 // expand_mod.F90:270-302 on the device: dst(nproma, rows, nblocks) <- src(nlon, rows), local
-// column j <- source column (gcol0 + j) mod nlon, zero beyond ngptot.
-__global__ void k_expand(const double *__restrict__ src, int nlon, long long rows,
-                         double *__restrict__ dst, int nproma, int ngptot, long long gcol0,
-                         long long total) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; idx < total; idx += stride) {
-    const int jl = (int)(idx % nproma);
-    const long long t = idx / nproma;
-    const long long r = t % rows;
-    const long long b = t / rows;
-    const long long gcol = b * nproma + jl;
-    dst[idx] = (gcol < ngptot) ? __ldg(src + r * nlon + ((gcol0 + gcol) % nlon)) : 0.0;
+// column j <- source column (gcol0 + j) mod nlon, zero beyond ngptot.  A thread owns one column of the
+// blocked array (its block / lane / source column are computed once) and walks the rows with the grid's
+// y stride: no per-element division, stores coalesced along NPROMA, the 100 source columns stay in L1/L2.
+__global__ void __launch_bounds__(256)
+k_expand(const double *__restrict__ src, int nlon, int rows, double *__restrict__ dst, int nproma,
+         int ngptot, long long gcol0, int ncol) {
+  for (int gcol = blockIdx.x * blockDim.x + threadIdx.x; gcol < ncol; gcol += gridDim.x * blockDim.x) {
+    const int b = gcol / nproma, jl = gcol - b * nproma;
+    const bool valid = gcol < ngptot;
+    const double *sp = src + (int)((gcol0 + gcol) % nlon);
+    double *dp = dst + (size_t)b * rows * nproma + jl;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y)
+      __stcs(dp + (size_t)r * nproma, valid ? __ldg(sp + (size_t)r * nlon) : 0.0);
   }
 }
 
@@ -255,10 +255,15 @@ cudaError_t csc2_launch_nl_ckpt(const KConst &c, const Geom &g, const TrajIn &in
 
 cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,
                                int ngptot, int nblocks, long long gcol0, cudaStream_t s) {
-  const long long total = (long long)nproma * rows * nblocks;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
-  k_expand<<<(int)blocks, 256, 0, s>>>(src, nlon, rows, dst, nproma, ngptot, gcol0, total);
+  const long long ncol = (long long)nproma * nblocks;
+  if (ncol > 0x7fffffffLL || rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+  long long gx = (ncol + 255) / 256;
+  if (gx > 148LL * 8) gx = 148LL * 8;
+  // enough CTAs to fill the machine a few times over, never more rows than there are
+  long long gy = (148LL * 16 + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  k_expand<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(src, nlon, (int)rows, dst, nproma, ngptot, gcol0, (int)ncol);
   return cudaGetLastError();
 }
 

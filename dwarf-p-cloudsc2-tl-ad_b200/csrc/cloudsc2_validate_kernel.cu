@@ -51,42 +51,45 @@ __device__ Stats block_fold(Stats s) {
 // field: (nproma, rows, nblocks) with rows = nlev*ndim, consecutive blocks blk_stride doubles apart
 // (= nproma*rows for a plain array; larger for a slab range of an AOSOA buffer such as
 // TENDENCY_LOC%T = B_LOC(:,:,1,:), cloudsc2_array_state_mod.F90:248-251); ref_src: (nlon, rows)
+// A thread owns one column of the blocked array (block / lane / reference column computed once) and walks
+// the rows with the grid's y stride: no per-element division, loads coalesced along NPROMA.
 __global__ void __launch_bounds__(256)
 k_validate_partial(const double *__restrict__ ref_src, int nlon, const double *__restrict__ field,
-                   int nproma, long long rows, long long blk_stride, int ngptot, long long gcol0,
-                   long long total, Stats *__restrict__ partial) {
+                   int nproma, int rows, long long blk_stride, int ngptot, long long gcol0,
+                   int ncol, Stats *__restrict__ partial) {
   Stats s = identity();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int jl = (int)(idx % nproma);
-    const long long t = idx / nproma;
-    const long long r = t % rows;
-    const long long b = t / rows;
-    const long long col = b * nproma + jl;
-    const double v = __ldcs(field + b * blk_stride + r * nproma + jl);
-    s.vmin = fmin(s.vmin, v);
-    s.vmax = fmax(s.vmax, v);
-    if (col < ngptot) {
-      const double ref = __ldg(ref_src + r * nlon + (gcol0 + col) % nlon);
-      // a NaN result must fail the validation: fmax / fmin drop NaN, so give it the largest error
-      const double d0 = fabs(v - ref);
-      const double d = (d0 == d0) ? d0 : 1.7976931348623157e308;
-      s.maxerr = fmax(s.maxerr, d);
-      s.sumerr += d;
-      s.sumref += fabs(ref);
+  for (int gcol = blockIdx.x * blockDim.x + threadIdx.x; gcol < ncol; gcol += gridDim.x * blockDim.x) {
+    const int b = gcol / nproma, jl = gcol - b * nproma;
+    const bool valid = gcol < ngptot;
+    const double *rp = ref_src + (int)((gcol0 + gcol) % nlon);
+    const double *fp = field + (size_t)b * blk_stride + jl;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+      const double v = __ldcs(fp + (size_t)r * nproma);
+      s.vmin = fmin(s.vmin, v);
+      s.vmax = fmax(s.vmax, v);
+      if (valid) {
+        const double ref = __ldg(rp + (size_t)r * nlon);
+        // a NaN result must fail the validation: fmax / fmin drop NaN, so give it the largest error
+        const double d0 = fabs(v - ref);
+        const double d = (d0 == d0) ? d0 : 1.7976931348623157e308;
+        s.maxerr = fmax(s.maxerr, d);
+        s.sumerr += d;
+        s.sumref += fabs(ref);
+      }
     }
   }
   s = block_fold(s);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = s;
 }
 
 __global__ void __launch_bounds__(256)
-k_validate_final(const Stats *__restrict__ partial, int n, double *__restrict__ out) {
+k_validate_final(const Stats *__restrict__ partial, int n, double *__restrict__ o_min,
+                 double *__restrict__ o_max2, double *__restrict__ o_sum2) {
   Stats s = identity();
   for (int i = threadIdx.x; i < n; i += blockDim.x) fold(s, partial[i]);
   s = block_fold(s);
   if (threadIdx.x == 0) {
-    out[0] = s.vmin; out[1] = s.vmax; out[2] = s.maxerr; out[3] = s.sumerr; out[4] = s.sumref;
+    o_min[0] = s.vmin; o_max2[0] = s.vmax; o_max2[1] = s.maxerr; o_sum2[0] = s.sumerr; o_sum2[1] = s.sumref;
   }
 }
 
@@ -125,14 +128,27 @@ size_t csc2_validate_scratch_bytes() { return (size_t)CSC2_VALIDATE_MAX_CTAS * s
 cudaError_t csc2_launch_validate(const double *ref_src, int nlon, const double *field, int nproma,
                                  long long rows, long long blk_stride, int ngptot, int nblocks,
                                  long long gcol0, void *scratch, double *out5, cudaStream_t s) {
-  const long long total = (long long)nproma * rows * nblocks;
-  long long ctas = (total + 255) / 256;
-  if (ctas > CSC2_VALIDATE_MAX_CTAS) ctas = CSC2_VALIDATE_MAX_CTAS;
-  if (ctas < 1) ctas = 1;
-  k_validate_partial<<<(int)ctas, 256, 0, s>>>(ref_src, nlon, field, nproma, rows, blk_stride, ngptot, gcol0,
-                                               total, static_cast<Stats *>(scratch));
+  return csc2_launch_validate_split(ref_src, nlon, field, nproma, rows, blk_stride, ngptot, nblocks, gcol0, scratch,
+                                    out5, out5 + 1, out5 + 3, s);
+}
+// the same with the results written where the cross-device reductions want them: min | max, max|err| | sums
+cudaError_t csc2_launch_validate_split(const double *ref_src, int nlon, const double *field, int nproma,
+                                       long long rows, long long blk_stride, int ngptot, int nblocks,
+                                       long long gcol0, void *scratch, double *o_min, double *o_max2,
+                                       double *o_sum2, cudaStream_t s) {
+  const long long ncol = (long long)nproma * nblocks;
+  if (ncol > 0x7fffffffLL || rows > 0x7fffffffLL) return cudaErrorInvalidValue;
+  // gx * gy <= CSC2_VALIDATE_MAX_CTAS partials
+  long long gx = (ncol + 255) / 256;
+  if (gx > 148) gx = 148;
+  if (gx < 1) gx = 1;
+  long long gy = CSC2_VALIDATE_MAX_CTAS / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  k_validate_partial<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(ref_src, nlon, field, nproma, (int)rows, blk_stride,
+                                                                     ngptot, gcol0, (int)ncol, static_cast<Stats *>(scratch));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_validate_final<<<1, 256, 0, s>>>(static_cast<const Stats *>(scratch), (int)ctas, out5);
+  k_validate_final<<<1, 256, 0, s>>>(static_cast<const Stats *>(scratch), (int)(gx * gy), o_min, o_max2, o_sum2);
   return cudaGetLastError();
 }
