@@ -41,9 +41,14 @@ def allreduce_norms(values, op: str = "max", device=None):
     """All-reduce a handful of FP64 scalars over the default process group (no-op without one)."""
     import torch
     import torch.distributed as dist
-    v = np.atleast_1d(np.asarray(values, dtype=np.float64))
+    v = np.atleast_1d(np.asarray(values, dtype=np.float64)).copy()
+    if op == "max":
+        # MAX over ranks drops NaN (std::max in gloo, no guarantee in NCCL): a rank whose kernels produced
+        # non-finite norms must fail the test for everybody, so it contributes a huge sentinel instead --
+        # the same mapping the library applies on the device before its own all-reduce (k_norms_prepare)
+        v[~np.isfinite(v)] = 1.0e300
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return v.copy()
+        return v
     t = torch.from_numpy(v.copy())
     if device is not None:
         t = t.to(device)

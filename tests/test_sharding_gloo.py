@@ -121,3 +121,37 @@ def test_shard_expansion_offset(pkg, src100):
     for n in ("pt", "paph", "pclv", "b_cml"):
         assert np.array_equal(part.a[n], whole.a[n][sh.block0:sh.block0 + sh.nblocks]), n
     assert np.allclose(pkg.allreduce_norms([1.0, 2.0]), [1.0, 2.0])   # no process group: identity
+
+
+def _nan_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import oracle_binding as ob
+        z = np.ones(10)
+        if rank == 1:
+            z[3] = np.nan          # a rank whose kernels produced NaN ratios
+            z[7] = np.inf
+        q.put((rank, ob.pkg.allreduce_norms(z, "max")))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_max_allreduce_does_not_drop_a_nan_rank(pkg):
+    """ADVICE r1: std::max(z, NaN) returns z, so a plain MAX over ranks would print TEST PASSED from rank 0
+    alone.  Non-finite norms travel as a huge sentinel and fail the verdict on every rank."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nan_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, z in res:
+        assert z[3] >= 1e300 and z[7] >= 1e300 and z[0] == 1.0
+        pen, _ = pkg.taylor_verdict(z)
+        assert not (0 <= pen <= 5)
