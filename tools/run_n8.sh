@@ -1,30 +1,43 @@
 #!/bin/bash
-# 8-GPU evidence (BASELINE config 5): the C++ programs with 8 ranks, strong scaling of bench.py at
-# NGPTOT = 1 310 720 and 5 242 880.  Run as: gpurun --gpus 8 -- bash tools/run_n8.sh
+# 8-GPU evidence (BASELINE config 5).  Run as: gpurun --gpus 8 -- bash tools/run_n8.sh
+#  1. the device-set tests (tests/test_gpu_multi.py, tests/test_programs.py) with 8 GPUs in ONE process
+#  2. the C++ programs: ONE process drives 8 GPUs through the library (cloudsc2_gpu_init_multi: worker thread
+#     and stream set per device, NCCL all-reduce of the norms / validation statistics) -- no fork, no pipes
+#  3. bench.py under torchrun at N = 8 (the driver's launch): weak line + strong_1310720 / strong_5242880 blocks
 set -u
 out=gpurun_out; mkdir -p $out
+export LD_LIBRARY_PATH=$(python -c "import nvidia.nccl, os; print(os.path.join(list(nvidia.nccl.__path__)[0], 'lib'))" 2>/dev/null):${LD_LIBRARY_PATH:-}
+python -m pytest tests/test_gpu_multi.py tests/test_programs.py -q -m gpu > $out/pytest_gpu_n8.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu_n8.log
 B=dwarf-p-cloudsc2-tl-ad_b200/bin
 {
   for prog in nl tl ad; do
-    echo "== CLOUDSC2_NUMPROC=8 dwarf-cloudsc2-$prog 1 1310720 128"
-    CLOUDSC2_NUMPROC=8 CLOUDSC2_REPEAT=3 $B/dwarf-cloudsc2-$prog 1 1310720 128 2>&1; echo "rc=$?"
+    echo "== CLOUDSC2_NGPUS=8 dwarf-cloudsc2-$prog 1 1310720 128"
+    CLOUDSC2_NGPUS=8 CLOUDSC2_REPEAT=3 $B/dwarf-cloudsc2-$prog 1 1310720 128 2>&1; echo "rc=$?"
   done
-  echo "== CLOUDSC2_NUMPROC=8 dwarf-cloudsc2-nl 1 5242880 128"
-  CLOUDSC2_NUMPROC=8 CLOUDSC2_REPEAT=3 $B/dwarf-cloudsc2-nl 1 5242880 128 2>&1; echo "rc=$?"
+  echo "== CLOUDSC2_NGPUS=8 dwarf-cloudsc2-nl 1 5242880 128"
+  CLOUDSC2_NGPUS=8 CLOUDSC2_REPEAT=3 $B/dwarf-cloudsc2-nl 1 5242880 128 2>&1; echo "rc=$?"
+  echo "== CLOUDSC2_NGPUS=1 dwarf-cloudsc2-nl 1 1310720 128"
+  CLOUDSC2_NGPUS=1 CLOUDSC2_REPEAT=3 $B/dwarf-cloudsc2-nl 1 1310720 128 2>&1; echo "rc=$?"
+  echo "== CLOUDSC2_NGPUS=8 CLOUDSC2_HOST_ARRAYS=3 dwarf-cloudsc2-nl 1 1310720 128   (host arrays, registered, sharded by the library)"
+  CLOUDSC2_NGPUS=8 CLOUDSC2_HOST_ARRAYS=3 CLOUDSC2_REPEAT=2 $B/dwarf-cloudsc2-nl 1 1310720 128 2>&1; echo "rc=$?"
+  echo "== NCCL_DEBUG=INFO CLOUDSC2_NGPUS=8 dwarf-cloudsc2-tl 1 800 1  (communicator evidence)"
+  NCCL_DEBUG=INFO CLOUDSC2_NGPUS=8 $B/dwarf-cloudsc2-tl 1 800 1 2>&1 | grep -E "NCCL INFO (ncclCommInitAll|comm 0x|Connected|NVLS|Channel 00/|Init COMPLETE)|TEST|GPU:" | head -40
 } > $out/programs_n8.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541"
-$TR bench.py --gpus 8 --steps 10 --warmup 3 --ngptot-total 5242880 --no-cpu --no-e2e 2>$out/b8s5.err | tail -1 > $out/bench_n8_strong5m.json
-$TR bench.py --gpus 8 --steps 10 --warmup 3 --ngptot-total 1310720 --no-cpu --e2e-steps 2 2>$out/b8s1.err | tail -1 > $out/bench_n8_strong1m.json
+( time $TR bench.py --gpus 8 --steps 20 --warmup 3 ) > $out/bench_n8.json 2> $out/b8.err
 python - <<'PY'
 import json
-for f in ("bench_n8_strong5m", "bench_n8_strong1m"):
-    try:
-        d = json.load(open(f"gpurun_out/{f}.json"))
-        print(f, d["scaling"], d["config"]["ngptot_total"], round(d["value"] / 1e6, 1), "M col/s", round(d["ms_per_step"], 3), "ms",
-              {k: round(v["ms_per_step"], 3) for k, v in d["modes"].items()}, "e2e", d["e2e"] and round(d["e2e"]["value"] / 1e6, 2),
-              d["selftests"].get("taylor_passed"), d["selftests"].get("adjoint_passed"), d["selftests"].get("allreduce_us_per_call"))
-    except Exception as e:
-        print(f, "failed", e)
+try:
+    d = json.loads(open("gpurun_out/bench_n8.json").read().strip().splitlines()[-1])
+    print("N=8", d["scaling"], d["config"]["ngptot_total"], round(d["value"] / 1e6, 1), "M col/s", round(d["ms_per_step"], 4), "ms")
+    print(" modes", {k: round(v["ms_per_step"], 3) for k, v in d["modes"].items()})
+    print(" e2e", d["e2e"]["ms_per_step"], d["e2e"]["h2d_gbs_per_gpu"], d["e2e"]["numa"], "source", d["e2e_source"]["ms_per_step"])
+    for k in d:
+        if k.startswith("strong"): print(" ", k, d[k])
+    print(" selftests", d["selftests"])
+except Exception as e:
+    print("bench_n8 failed", e)
 PY
-grep -E "GPU:|TEST|rc=|^==" $out/programs_n8.log
+tail -4 $out/pytest_gpu_n8.log
+grep -E "GPU:|TEST|rc=|^==|validation:" $out/programs_n8.log
 free -g | head -2; nproc
