@@ -4,23 +4,29 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * Parity status: the NL restatement is pinned against the reference's own importable Python
- * kernel (src/cloudsc2_nl_gt4py/cloudsc2_py.py) through the golden vectors in tests/golden/
- * (made by make_golden.py on two synthetic atmospheres and by make_golden_edge.py on edge-case
- * columns sitting on the scheme's branch thresholds, KLEV = 60).  TL and AD are pinned against central
- * finite differences of that same reference kernel (tests/golden/tl_fd_pyref*.npz, made by
- * make_golden_tl.py on two atmospheres: TL to 1e-7, AD through <D,y> = <dx, AD y> to 1e-6) and by the
- * reference's own known-answer properties
- * (Taylor test, adjoint dot-product test).  Against the reference
- * FORTRAN BINARIES on the real input.h5: PARITY UNPINNED (no Fortran compiler, no HDF5, and
- * config-files/input.h5 is absent in this environment).
+ * Parity status: PINNED.
+ *  (1) Against the reference's own FORTRAN TEXT: `make -C oracle ref` transliterates satur.F90, cuadjtqs.F90,
+ *      cloudsc2.F90, cuadjtqstl.F90, cloudsc2tl.F90, cuadjtqsad.F90, cloudsc2ad.F90 from /root/reference/src,
+ *      where they lie, into oracle/_ref/libcloudsc2_ref.so (oracle/f90toc.py; statement-by-statement C, same
+ *      expression trees, same flags); tests/test_oracle_ref.py asserts this restatement == that library to
+ *      1e-13 max|field| (measured: exactly 0) for NL, TL and AD, LREGCL off and on, RVTMP2 zero and
+ *      non-zero, two atmospheres, and identical Taylor / adjoint self-test numbers.
+ *  (2) Against the reference's own importable Python kernel (src/cloudsc2_nl_gt4py/cloudsc2_py.py) through
+ *      the golden vectors in tests/golden/: NL values on two synthetic atmospheres and on edge-case columns
+ *      sitting on the scheme's branch thresholds (make_golden.py, make_golden_edge.py); TL and AD against
+ *      central finite differences of that kernel along the drivers' direction (make_golden_tl.py) and along
+ *      16 single-input + 2 random directions (make_golden_tl_dirs.py).
+ *  (3) By the reference's own known-answer properties (Taylor test, adjoint dot-product test).
+ * Not available here: the reference's Fortran BINARIES on the real input.h5 (no Fortran compiler, no HDF5,
+ * config-files/input.h5 absent) -- what a compiler could change relative to the source text (last bits).
  *
  * Statically dead code of the reference that is NOT restated: the precipitation-evaporation
  * branch guarded by LLO2 = ... .AND. (LEVAPLS2 .OR. LDRAIN1D) (cloudsc2.F90:556-591,
  * cloudsc2tl.F90:845-943, cloudsc2ad.F90:724-773,1152-1267): LEVAPLS2 is forced .FALSE. by all
  * three programs (cloudsc2_{nl,tl,ad}/dwarf_cloudsc.F90:105) and LDRAIN1D is a hard-coded .FALSE. in
- * all three drivers (cloudsc_driver*_mod.F90 "LOGICAL :: LDRAIN1D = .FALSE.").  The oracle
- * refuses (returns -1) if either switch is set.  Likewise only LPHYLIN=.TRUE. (forced at
+ * all three drivers (cloudsc_driver*_mod.F90 "LOGICAL :: LDRAIN1D = .FALSE.").  This hand
+ * restatement refuses (returns -1) if either switch is set; the transliterated reference in
+ * oracle/_ref runs the branch (tests/test_oracle_ref.py::test_transliterated_reference_covers_...).  Likewise only LPHYLIN=.TRUE. (forced at
  * dwarf_cloudsc.F90:107) and KCALL==0 of CUADJTQS* are restated.
  */
 #ifndef CLOUDSC2_ORACLE_H
