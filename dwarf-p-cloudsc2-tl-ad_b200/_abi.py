@@ -93,6 +93,8 @@ def _declare(lib):
         "cloudsc2_gpu_init_devices": (i, [P, i, c_double_p, i, C.POINTER(i)]),
         "cloudsc2_gpu_finalize": (i, []),
         "cloudsc2_gpu_num_devices": (i, []),
+        "cloudsc2_shard_blocks": (i, [i, i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i),
+                                      C.POINTER(C.c_longlong)]),
         "cloudsc2_gpu_select_device": (i, [i]),
         "cloudsc2_gpu_comm_unique_id": (i, [vp, i]),
         "cloudsc2_gpu_comm_init_rank": (i, [i, i, vp, i]),

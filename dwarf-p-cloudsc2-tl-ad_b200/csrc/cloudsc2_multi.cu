@@ -112,6 +112,22 @@ struct DeviceSet {
   std::unique_ptr<Worker> worker[CSC2_MAX_DEVICES];
   bool inproc_comm = false;     // communicator made by ncclCommInitAll over the set
   std::mutex call_mu;           // one multi-device call at a time
+  void stop_workers() {
+    for (int i = 0; i < CSC2_MAX_DEVICES; ++i) {
+      if (!worker[i]) continue;
+      Worker &w = *worker[i];
+      {
+        std::lock_guard<std::mutex> lk(w.m);
+        w.quit = true;
+      }
+      w.cv.notify_all();
+      if (w.th.joinable()) w.th.join();
+      worker[i].reset();
+    }
+  }
+  // A host that exits without cloudsc2_gpu_finalize must not die in ~thread (joinable): stop the workers;
+  // device memory and streams go with the process (the CUDA runtime may already be unloading here).
+  ~DeviceSet() { stop_workers(); }
 };
 DeviceSet set_;
 Ctx no_ctx;                      // what csc2_ctx() returns before any init (init == false)
@@ -198,18 +214,7 @@ void destroy_ctx(Ctx &c) {
 }
 
 void teardown() {
-  for (int i = 0; i < set_.n; ++i) {
-    if (set_.worker[i]) {
-      Worker &w = *set_.worker[i];
-      {
-        std::lock_guard<std::mutex> lk(w.m);
-        w.quit = true;
-      }
-      w.cv.notify_all();
-      if (w.th.joinable()) w.th.join();
-      set_.worker[i].reset();
-    }
-  }
+  set_.stop_workers();
   for (int i = 0; i < set_.n; ++i) {
     if (set_.ctx[i]) destroy_ctx(*set_.ctx[i]);
     set_.ctx[i].reset();
@@ -426,6 +431,18 @@ int cloudsc2_gpu_finalize(void) {
 }
 
 int cloudsc2_gpu_num_devices(void) { return set_.n; }
+
+int cloudsc2_shard_blocks(int index, int nshards, int nproma, int ngptot, int *block0, int *nblocks,
+                          int *ngptot_local, long long *gcol0) {
+  if (nshards < 1 || index < 0 || index >= nshards || nproma < 1 || ngptot < 1)
+    return csc2_fail(3, "bad arguments to cloudsc2_shard_blocks");
+  const Shard s = csc2_shard(index, nshards, nproma, ngptot);
+  if (block0) *block0 = s.b0;
+  if (nblocks) *nblocks = s.nb;
+  if (ngptot_local) *ngptot_local = s.ngptot;
+  if (gcol0) *gcol0 = s.gcol0;
+  return 0;
+}
 
 int cloudsc2_gpu_select_device(int index) {
   if (index < 0) { tl_ctx = nullptr; return 0; }

@@ -98,6 +98,13 @@ int cloudsc2_gpu_init_multi(const cloudsc2_params *params, int klev, const doubl
 int cloudsc2_gpu_init_devices(const cloudsc2_params *params, int klev, const double *ceta, int ngpus,
                               const int *devices);
 int cloudsc2_gpu_finalize(void);
+/* The block shard of device / rank `index` of `nshards` (pure function, no GPU needed): per = (NB-1)/R + 1,
+ * shard r owns blocks [r*per, min(NB,(r+1)*per)) -- the arithmetic of cloudsc2_nl/dwarf_cloudsc.F90:65-69
+ * (NGPTOT = (NGPTOTG-1)/NUMPROC+1, the last rank takes the rest) applied to NPROMA blocks, so that a shard is
+ * one contiguous byte range of every blocked array.  Outputs (any may be NULL): first block, number of
+ * blocks, valid columns, first global column.  Returns 0, or 3 for bad arguments. */
+int cloudsc2_shard_blocks(int index, int nshards, int nproma, int ngptot, int *block0, int *nblocks,
+                          int *ngptot_local, long long *gcol0);
 /* Number of devices in the set (0 before init). */
 int cloudsc2_gpu_num_devices(void);
 /* Make device `index` of the set the calling thread's current context for the _dev entry points and

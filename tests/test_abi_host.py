@@ -167,3 +167,25 @@ def test_mini_hdf5_reader_on_reference_file(pkg):
     nz = fn > 0
     assert np.allclose(-hn[nz] / fn[nz], 2.8345e6, rtol=1e-12)      # RLSTT
     assert pkg.read_h5_f8(ref, "TENDENCY_LOC_CLD").shape == (5, 137, 100)
+
+
+def test_library_block_sharding_is_the_reference_arithmetic(pkg):
+    """cloudsc2_shard_blocks (what cloudsc2_gpu_init_multi shards with) == dwarf_cloudsc.F90:65-69 applied to
+    NPROMA blocks == the Python helper the torchrun harness uses; shards tile the problem exactly."""
+    lib = pkg.load_library()
+    for ngptot, nproma, r in [(100, 1, 8), (100, 100, 8), (160000, 32, 8), (163840, 128, 3), (1000, 32, 5),
+                              (7, 8, 4), (1310720, 128, 8), (4133, 128, 2), (65, 64, 2)]:
+        nb = ngptot // nproma + min(ngptot % nproma, 1)
+        per = (nb - 1) // r + 1                                   # NGPTOT = (NGPTOTG-1)/NUMPROC + 1 (:65)
+        cols = 0
+        for k in range(r):
+            b0, n, ng, g0 = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+            assert lib.cloudsc2_shard_blocks(k, r, nproma, ngptot, C.byref(b0), C.byref(n), C.byref(ng), C.byref(g0)) == 0
+            want_b0 = min(k * per, nb)
+            want_n = min(nb, want_b0 + per) - want_b0             # the last ranks take the rest (:66-68)
+            assert (b0.value, n.value, g0.value) == (want_b0, want_n, want_b0 * nproma)
+            sh = pkg.shard_blocks(ngptot, nproma, k, r)
+            assert (sh.block0, sh.nblocks, sh.gcol0, sh.ngptot) == (b0.value, n.value, g0.value, ng.value)
+            cols += ng.value
+        assert cols == ngptot
+    assert lib.cloudsc2_shard_blocks(2, 2, 32, 100, None, None, None, None) == 3
