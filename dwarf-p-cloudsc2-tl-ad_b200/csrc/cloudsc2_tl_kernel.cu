@@ -362,6 +362,12 @@ static cudaError_t launch_tl_variant(const KConst &c, const Geom &g, const TrajI
   }
 #ifdef CSC2_EXPERIMENTS   // occupancy variants measured in DESIGN.md 3.3 (CSC2_TL_MINB); the product has one shape
   static const int minb = [] { const char *e = getenv("CSC2_TL_MINB"); return e ? atoi(e) : 2; }();
+  if (minb == 93)  // 96-thread CTAs, 3 per SM = 9 warps at 224 registers (no spills), 147 kB of ring per SM
+    return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 3, 96>(c, g, in, out, din, dout, opt, grid, s)
+                : launch_tl_k<ONFLY, STAGES, false, false, 3, 96>(c, g, in, out, din, dout, opt, grid, s);
+  if (minb == 9)   // 32-thread CTAs, 9 per SM = 9 warps at 224 registers
+    return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 9, 32>(c, g, in, out, din, dout, opt, grid, s)
+                : launch_tl_k<ONFLY, STAGES, false, false, 9, 32>(c, g, in, out, din, dout, opt, grid, s);
   if (minb == 8)   // 32-thread CTAs, 8 per SM = 8 warps at 255 registers (finer tail)
     return lreg ? launch_tl_k<ONFLY, STAGES, false, true, 8, 32>(c, g, in, out, din, dout, opt, grid, s)
                 : launch_tl_k<ONFLY, STAGES, false, false, 8, 32>(c, g, in, out, din, dout, opt, grid, s);
