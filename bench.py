@@ -163,6 +163,31 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def load_cpu_arm():
+    """The CPU implementation the reference arm / cpu_baseline time: oracle/_ref -- the reference's OWN Fortran
+    kernels (satur.F90, cloudsc2.F90, ...), transliterated statement by statement to C by oracle/f90toc.py from
+    /root/reference/src in the build container and compiled by gcc (the .so travels to the GPU box; there is no
+    Fortran compiler in this image) -- when it is there, kind "reference"; else the hand-written C restatement
+    (oracle/), kind "port".  Both run the same OpenMP block loop (oracle/cloudsc2_drivers.c, the mirror of
+    cloudsc_driver_mod.F90:73-119)."""
+    from tests import oracle_binding as ob
+    ref_lib = ROOT / "oracle" / "_ref" / "libcloudsc2_ref.so"
+    if ref_lib.exists() and os.environ.get("BENCH_CPU_ARM", "ref") != "port":
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("oracle_binding_ref", ROOT / "tests" / "oracle_binding.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.ORACLE_LIB = ref_lib
+        try:
+            if b"f90toc" in mod.flavour():
+                return mod, "reference", ("the reference's Fortran kernels transliterated to C (oracle/f90toc.py) and "
+                                          "compiled with gcc -O2 -ffp-contract=off; OpenMP block loop as in "
+                                          "cloudsc_driver_mod.F90:73-119")
+        except Exception:
+            pass
+    return ob, "port", "C restatement of the reference (oracle/); Fortran reference not buildable here"
+
+
 def cpu_reference_run(pkg, ob, src, prm, nproma: int, ngptot: int, threads: int, repeats: int):
     """The reference CPU path (oracle restatement of CLOUDSC_DRIVER) on `ngptot` columns.
     Returns best columns/s over `repeats` (the reference times the block loop only)."""
@@ -220,12 +245,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # The reference's own CPU implementation of the path: the C restatement of CLOUDSC_DRIVER's block loop
-        # (oracle/, OpenMP over blocks like cloudsc_driver_mod.F90:73-81) -- the Fortran itself cannot be built
-        # in this image.  None of the repo's kernels run here: libcloudsc2_b200.so is mapped by this process
+        # The reference's own CPU implementation of the path (load_cpu_arm: its Fortran kernels transliterated to C
+        # and compiled by gcc, oracle/_ref, when that library travelled here; else the hand-written C restatement)
+        # under an OpenMP block loop like cloudsc_driver_mod.F90:73-81 -- the Fortran itself cannot be built in
+        # this image.  None of the repo's kernels run here: libcloudsc2_b200.so is mapped by this process
         # ONLY because the synthetic input generator and the host-side expansion (pkg.synth_source,
         # pkg.ArrayState) live in that library; no cloudsc2_gpu_* compute entry is called.
-        from tests import oracle_binding as ob
+        ob, cpu_kind, cpu_desc = load_cpu_arm()
         threads = host_threads()
         sample = min(ngp, 32768)
         t_steps = []
@@ -247,10 +273,9 @@ def main():
                 "cores": threads, "sample_columns": sample, "ms_per_sample": ms_sample,
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": cpu_kind,
                                  "sample": f"{sample} of the {ngp} columns per step (NPROMA={nproma}), "
-                                           "block loop only, C restatement of the reference "
-                                           "(Fortran reference not buildable here)"},
+                                           f"block loop only; {cpu_desc}"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -661,14 +686,13 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from tests import oracle_binding as ob
+        ob, cpu_kind, cpu_desc = load_cpu_arm()
         threads = host_threads()
         sample = min(ngp, 65536)
         cps, _ = cpu_reference_run(pkg, ob, src, prm, nproma, sample, threads, repeats=3)
         cps4, _ = cpu_reference_run(pkg, ob, src, prm, 32, min(sample, 32768), min(4, threads), repeats=2)
-        cpu = {"value": cps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{sample} columns, NPROMA={nproma}, best of 3, block loop only "
-                         "(C restatement of the reference; Fortran not buildable in this image)",
+        cpu = {"value": cps, "unit": UNIT, "cores": threads, "kind": cpu_kind,
+               "sample": f"{sample} columns, NPROMA={nproma}, best of 3, block loop only; {cpu_desc}",
                "readme_config_4threads_nproma32": cps4}
         # TL / AD kernels of the CPU port on the same cores (CLOUDSC2TL / CLOUDSC2AD block loops,
         # increments = 1 % of the inputs), for the "modes" lines: a small sample, they are slow

@@ -41,12 +41,12 @@ def test_reference_arm_line(built):
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
 
 
 @pytest.mark.gpu
 def test_b200_arm_line(built):
-    d = _line("--steps", "3", "--warmup", "3", "--no-cpu", "--no-sweep", "--e2e-steps", "1",
+    d = _line("--steps", "3", "--warmup", "3", "--no-cpu", "--no-sweep", "--no-strong", "--e2e-steps", "1",
               "--ngptot-per-gpu", "32768")
     _check_base(d)
     assert d["impl"] == "b200" and d["n_gpus"] == 1 and d["scaling"] == "weak"
@@ -57,6 +57,13 @@ def test_b200_arm_line(built):
     assert rf["traffic"] > 0 and rf["algorithmic_bytes_per_column"] == 27440
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert 0 < d["e2e"]["value"] < d["value"]                        # copies inside the timed region
+    # round 2: the default e2e runs on caller-allocated arrays registered once; the other host situations beside it
+    assert d["e2e"]["host_registered"] is True and d["e2e"]["host_register_ms_once"] > 0
+    assert 0 < d["e2e"]["pageable"]["value"] <= d["e2e"]["value"] * 1.2
+    assert d["e2e"]["host_alloc"]["value"] > 0
+    es = d["e2e_source"]                                             # the dwarf's LOAD -> DRIVER -> VALIDATE in one call
+    assert es["value"] > d["e2e"]["value"] and es["h2d_bytes_per_step"] < 1e7 and es["d2h_bytes_per_step"] == 400
+    assert es["max_abs_err_vs_unexpanded_columns"] == 0.0 and es["stats_finite"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     for m in ("nl", "tl", "ad", "ad_have_trajectory", "tl_taylor_driver", "ad_test_driver"):
         assert d["modes"][m]["columns_per_s"] > 0, m
