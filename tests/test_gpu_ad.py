@@ -211,3 +211,37 @@ def test_ad_kernel_is_the_transpose_of_the_reference_derivative(pkg, golden_fd):
     assert abs(lhs) > 1.0 and abs(lhs - rhs) <= 1e-6 * abs(lhs), (lhs, rhs)
     for n in out10:
         assert not incr[n].any(), n                      # output adjoints consumed and zeroed
+
+
+def test_host_ad_with_precomputed_trajectory_equals_as_written(pkg, src100):
+    """The same through the HOST-pointer entry (chunked pipeline): with ad_have_trajectory the caller's
+    PFPLSL5 / PFPLSN5 arrays (left by a cloudsc2_gpu_nl call on the same inputs) travel up with every chunk
+    and the forward sweep is skipped; ragged NGPTOT, several chunks."""
+    prm = pkg.default_params(lregcl=False)
+    nproma, ngptot = 32, 1000                               # 32 blocks, last one ragged (8 columns)
+    rng = np.random.default_rng(9)
+    outs = []
+    with pkg.Cloudsc2(prm, 137, src100.ceta) as gpu:
+        for have in (0, 1):
+            st = pkg.ArrayState(src100, nproma, ngptot)
+            din, dout = pkg.driver.alloc_increments(st.nblocks, 137, nproma)
+            r = np.random.default_rng(9)
+            for k in din:
+                din[k][...] = 1e-3 * r.standard_normal(din[k].shape)
+            for k in dout:
+                dout[k][...] = r.standard_normal(dout[k].shape)
+            dout0 = {k: v.copy() for k, v in dout.items()}
+            if have:
+                gpu.nl(st)                                   # trajectory fluxes now in st.a["pfplsl"/"pfplsn"]
+            gpu.set_option("ad_have_trajectory", have)
+            try:
+                gpu.ad(st, din, dout)
+            finally:
+                gpu.set_option("ad_have_trajectory", 0)
+            outs.append(({k: v.copy() for k, v in din.items()}, {k: v.copy() for k, v in dout.items()}, dout0))
+    for k in outs[0][0]:
+        assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
+    for k, v in outs[1][1].items():                          # consumed and zeroed; padding columns untouched
+        assert not v[:-1].any() and not v[-1][:, :8].any(), k
+        assert np.array_equal(v[-1][:, 8:], outs[1][2][k][-1][:, 8:]), k
+    del rng

@@ -222,3 +222,54 @@ def test_tl_and_ad_kernels_match_reference_derivative_input_by_input(pkg):
         rhs += float((dx["psupsat"] * adj["psupsat"]).sum()) / ptsphy      # cloudsc2ad.F90:1733
         scale = sum(float(np.abs(fd[f"d{i:02d}_{n}"] * y[n]).sum()) for n in OUT7)
         assert scale > 0 and abs(lhs - rhs) <= 2e-6 * scale, (NAMES[i], lhs, rhs)
+
+
+def test_host_tl_and_ad_pipeline_equals_device_entries_many_chunks(pkg, src100, gpu_nl):
+    """The host-pointer TL / AD entries run the caller's blocks through the chunked three-stream pipeline
+    (compact device layout, ramped chunk plan, increments travelling with their chunk).  On a problem large
+    enough for the ramp (101 blocks of 128 columns, ragged tail) the results must equal the device-pointer
+    entries on the reference layout bit for bit."""
+    nproma, ngptot = 128, 100 * 128 + 57
+    gpu = gpu_nl
+    st = pkg.ArrayState(src100, nproma, ngptot)
+    nb = st.nblocks
+    r = np.random.default_rng(21)
+    din, dout = pkg.driver.alloc_increments(nb, 137, nproma)
+    for k in din:
+        din[k][...] = 1e-3 * r.standard_normal(din[k].shape)
+    for k in dout:
+        dout[k][...] = 5.0                                   # must survive in the padding columns
+    # device-pointer path (reference layout on the device)
+    ds = pkg.DeviceState(gpu, st)
+    ds.zero()
+    d_in = {k: gpu.malloc(v.nbytes) for k, v in din.items()}
+    d_out = {k: gpu.malloc(v.nbytes) for k, v in dout.items()}
+    want_tl = {k: np.empty_like(v) for k, v in dout.items()}
+    want_ad = {k: np.empty_like(v) for k, v in din.items()}
+    try:
+        for k, v in din.items():
+            gpu.h2d(d_in[k], v)
+        for k, v in dout.items():
+            gpu.h2d(d_out[k], v)
+        gpu.tl_dev(ds, st.ptsphy, d_in, d_out)
+        gpu.sync()
+        for k, v in want_tl.items():
+            gpu.d2h(v, d_out[k])
+        gpu.ad_dev(ds, st.ptsphy, d_in, d_out)              # adjoint of the TL outputs, accumulated into din
+        gpu.sync()
+        for k, v in want_ad.items():
+            gpu.d2h(v, d_in[k])
+    finally:
+        for p in list(d_in.values()) + list(d_out.values()):
+            gpu.free(p)
+        ds.free()
+    # host-pointer path
+    gpu.tl(st, din, dout)
+    for k in dout:
+        assert np.array_equal(dout[k], want_tl[k]), k
+        assert (dout[k][-1][:, 57:] == 5.0).all(), k         # padding of the ragged last block untouched
+    gpu.ad(st, din, dout)
+    for k in din:
+        assert np.array_equal(din[k], want_ad[k]), k
+    for k in dout:
+        assert not dout[k][:-1].any() and not dout[k][-1][:, :57].any(), k
