@@ -873,7 +873,6 @@ static int adtest_reserve(const Geom &whole, AdTestScratch &a) {
 static int adtest_enqueue(const KConst &kc, const Geom &geo, const TrajIn &in, TrajOut out, const AdTestScratch &a,
                           size_t b0, cudaStream_t s) {
   const size_t n2 = (size_t)geo.nproma * geo.klev, n2h = n2 + geo.nproma;
-  const size_t nb = a.n2b / n2;
   double *y = a.y;
   IncOut dout;
   dout.tent = y + n2 * b0; dout.tenq = y + a.n2b + n2 * b0; dout.tenl = y + 2 * a.n2b + n2 * b0;
@@ -881,7 +880,6 @@ static int adtest_enqueue(const KConst &kc, const Geom &geo, const TrajIn &in, T
   double *yh = y + 6 * a.n2b;
   dout.pfplsl = yh + n2h * b0; dout.pfplsn = yh + a.n2hb + n2h * b0; dout.pfhpsl = yh + 2 * a.n2hb + n2h * b0;
   dout.pfhpsn = yh + 3 * a.n2hb + n2h * b0;
-  (void)nb;
   // the driver zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV) of every block (:112-113)
   CK(cudaMemsetAsync(out.pcovptot, 0, n2 * geo.nblocks * sizeof(double), s));
   CK(cudaMemset2DAsync(out.loc_last, out.bs_loc * sizeof(double), 0, n2 * sizeof(double), geo.nblocks, s));

@@ -658,7 +658,6 @@ static int load_job(int idx, void *p) {
   cudaStream_t q = c.stream;
   // FIELD_INIT of the outputs (cloudsc2_array_state_mod.F90:100-127; B_LOC zeroed for determinism)
   CK(cudaMemsetAsync(out0, 0, (size_t)(p0 - out0) * sizeof(double), q));
-  (void)out0;
   // the un-expanded columns go up once (about 4 MB), the expansion happens on the device
   const size_t k2 = (size_t)s.klon * s.klev, k2h = (size_t)s.klon * (s.klev + 1);
   const size_t src_total = 10 * k2 + k2h + CLOUDSC2_NCLV * k2 + CLOUDSC2_NSTATE * k2;
