@@ -63,6 +63,7 @@ k_validate_partial(const double *__restrict__ ref_src, int nlon, const double *_
     const bool valid = gcol < ngptot;
     const double *rp = ref_src + (int)((gcol0 + gcol) % nlon);
     const double *fp = field + (size_t)b * blk_stride + jl;
+#pragma unroll 4
     for (int r = blockIdx.y; r < rows; r += gridDim.y) {
       const double v = __ldcs(fp + (size_t)r * nproma);
       s.vmin = fmin(s.vmin, v);
