@@ -3,11 +3,11 @@
 // (cloudsc_driver_ad_mod.F90:184-267).
 //
 // One thread per column, two sweeps in two launches:
-//   forward  JK = 1..KLEV : the NL kernel itself (cloudsc2_nl_kernel.cu, csc2_launch_nl_ckpt: fused
+//   forward  JK = 1..KLEV : the NL kernel itself (cloudsc2_nl_kernel.cu, csc2_launch_nl_traj: fused
 //            SATUR + nonlinear level at the NL kernel's occupancy), writing the trajectory outputs
-//            like the reference (:842-864) and check-pointing ONLY the rain/snow flux entering
-//            each level (2 doubles per level, instead of the reference's 116 stored (KLON,KLEV)
-//            arrays);
+//            like the reference (:842-864); the ONLY state the reverse sweep takes from it is the
+//            rain/snow flux entering each level = the outputs PFPLSL5 / PFPLSN5 themselves (2 doubles
+//            per level, instead of the reference's 116 stored (KLON,KLEV) arrays);
 //   reverse  JK = KLEV..1 : k_cloudsc2_ad below -- reload the level's inputs, recompute its local
 //            trajectory, run the adjoint statements (ad_level), and finish the level's 16 input
 //            adjoints at once -- either accumulated into the caller's arrays (X = X + ..., PSUPSAT
@@ -49,15 +49,16 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const int jl = gcol - ibl * g.nproma;
   const int klev = g.klev, nproma = g.nproma;
   const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
-  // Flux entering level JK (the only state the reverse sweep needs from the forward sweep):
-  // when the forward sweep wrote the trajectory outputs, it IS PFPLSL5(JK) / PFPLSN5(JK)
-  // (cloudsc2ad.F90:847-848), so no separate check-point array is written or read; otherwise
-  // it comes from the [2][klev][ncol_pad] check-point buffer.
-  const bool from_traj = opt.write_traj != 0 || opt.have_traj != 0;
-  const double *ck_r = from_traj ? out.pfplsl + o.oh : opt.ckpt + gcol;
-  const double *ck_s = from_traj ? out.pfplsn + o.oh : opt.ckpt + (size_t)klev * opt.ncol_pad + gcol;
-  const size_t cks = from_traj ? (size_t)nproma : (size_t)opt.ncol_pad;
+  // Flux entering level JK (the only state the reverse sweep needs from the forward sweep): it IS
+  // PFPLSL5(JK) / PFPLSN5(JK) of the trajectory outputs (cloudsc2ad.F90:847-848), written by the forward
+  // sweep of this call or by the CLOUDSC2 / CLOUDSC2TL call the caller vouches for (have_traj) -- no
+  // separate check-point array is written or read.
   constexpr int SLOT = AD_NF * NT;
+  // level pitch of the trajectory flux arrays: NPROMA in the blocked layout (flux_pitch = 0).  Kept a run-time
+  // value on purpose: folded into the shared level offset jk*NPROMA, ptxas spills a loop-carried value of the
+  // 255-register adjoint level (24 B, an STL/LDL pair in the level loop) and the sweep is 3.5 % slower
+  // (2.147 vs 2.073 ms, tools/ad_ab.sh); with its own multiply the spill is the two loop invariants (16 B).
+  const size_t cks = opt.flux_pitch > 0 ? (size_t)opt.flux_pitch : (size_t)nproma;
 
   const CritRH crh = make_critrh(tropopause_eta(c, in.pt, in.gt, o.o1, o.ocml, nproma));
 
@@ -67,8 +68,8 @@ k_cloudsc2_ad(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   auto stage_rev = [&](double *d, int jk) {
     const size_t l = (size_t)jk * nproma;
     csc2_stage_traj<NT, true>(d, in, o, jk, klev, nproma);
-    csc2_cp_async8(d + 16 * NT, ck_r + (size_t)jk * cks);
-    csc2_cp_async8(d + 17 * NT, ck_s + (size_t)jk * cks);
+    csc2_cp_async8(d + 16 * NT, out.pfplsl + o.oh + (size_t)jk * cks);
+    csc2_cp_async8(d + 17 * NT, out.pfplsn + o.oh + (size_t)jk * cks);
     csc2_cp_async8(d + 18 * NT, dout.tent + o.o1 + l);
     csc2_cp_async8(d + 19 * NT, dout.tenq + o.o1 + l);
     csc2_cp_async8(d + 20 * NT, dout.tenl + o.o1 + l);
@@ -203,7 +204,7 @@ static cudaError_t launch_ad_k(const KConst &c, const Geom &g, const TrajIn &in,
   // forward (trajectory) sweep: its own launch at the NL kernel's occupancy (12 warps/SM instead of
   // the 8 the adjoint level allows), check-pointing the fluxes the reverse sweep restarts from
   if (!opt.have_traj) {
-    cudaError_t e = csc2_launch_nl_ckpt(c, g, in, out, opt.ckpt, opt.ncol_pad, opt.write_traj, s);
+    cudaError_t e = csc2_launch_nl_traj(c, g, in, out, s);
     if (e != cudaSuccess) return e;
   }
   kern<<<grid, CSC2_AD_THREADS, smem, s>>>(c, g, in, out, din, dout, opt);

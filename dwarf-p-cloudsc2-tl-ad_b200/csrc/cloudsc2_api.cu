@@ -654,16 +654,12 @@ int cloudsc2_gpu_ad_dev(int nproma, int klev, int ngptot, double ptsphy, const c
   views_from_fields(*dev, nproma, klev, in, out);
   out.loc_last = nullptr;
   inc_views(din_, dout_, din, dout);
-  const long long ncp = pad_cols((long long)geo.nblocks * nproma);
-  if (int rc = G.work.reserve((size_t)2 * klev * ncp * sizeof(double))) return rc;
   opts.load();
   // option "ad_have_trajectory": dev->pfplsl / pfplsn already hold the trajectory of these inputs
-  ADOpts opt{0.0, 0, nullptr, G.work.d(), ncp, 1, opts.ad_have_trajectory};
+  ADOpts opt{0.0, 0, nullptr, 0, opts.ad_have_trajectory};
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : G.stream;
-  if (int rc = scratch_begin(s)) return rc;
   CK(csc2_launch_ad(make_kconst(ptsphy), geo, in, out, din, dout, opt, s));
-  if (int rc = scratch_end(s)) return rc;
-  G.launches += opt.have_traj ? 1 : 2;      // forward (NL + check-points) and reverse sweep
+  G.launches += opt.have_traj ? 1 : 2;      // forward (the NL kernel) and reverse sweep
   return 0;
 }
 
@@ -723,8 +719,8 @@ int csc2_tlad_host_one(bool is_ad, int nproma, int klev, int ngptot, double ptsp
     for (int i = 0; i < 10; ++i) *pb[i] = items[16 + i].dev + items[16 + i].per_blk * b0;
     inc_views(&da, &db, din, dout);
     if (is_ad) {
-      // trajectory fluxes written by the forward sweep ARE the check-points (write_traj = 1): no scratch
-      ADOpts opt{0.0, 0, nullptr, nullptr, 0, 1, have_traj ? 1 : 0};
+      // the trajectory fluxes written by the forward sweep ARE the check-points: no scratch
+      ADOpts opt{0.0, 0, nullptr, 0, have_traj ? 1 : 0};
       CK(csc2_launch_ad(kc, geo, in, out, din, dout, opt, s));
       G.launches += have_traj ? 1 : 2;
     } else {
@@ -892,7 +888,7 @@ static int adtest_enqueue(const KConst &kc, const Geom &geo, const TrajIn &in, T
   // AD applied to y with zero-initialised input adjoints; N2 = <0.01 x, M'^T y> (:198-256)
   // the TL launch above has just written the trajectory outputs of these very inputs (cloudsc2tl.F90:
   // 1079-1111), so the adjoint restarts from PFPLSL5 / PFPLSN5 and needs no forward sweep of its own
-  ADOpts aopt{0.01, 1, a.n2 + col0, nullptr, a.ncp, 1, 1};
+  ADOpts aopt{0.01, 1, a.n2 + col0, a.ncp, 1};
   CK(csc2_launch_ad(kc, geo, in, out, din, dout, aopt, s));
   G.launches += 2;
   return 0;

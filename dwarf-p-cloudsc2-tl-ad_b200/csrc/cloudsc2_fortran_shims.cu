@@ -169,8 +169,7 @@ static void tlad(bool is_ad, const int *kidia, const int *kfdia, const int *klon
   KConst kc; cudaStream_t s; long long dummy;
   if (csc2_shim_context(&kc, *ptsphy, *klev, &s, &dummy)) abor1("cloudsc2_gpu_init has not been called (or KLEV differs)");
   const size_t n2 = (size_t)*klon * *klev, n2h = (size_t)*klon * (*klev + 1);
-  const size_t ncp = ((size_t)*klon + 127) / 128 * 128;
-  double *base = g_slab.get(2 * (21 * n2 + 5 * n2h) + 2 * (size_t)*klev * ncp);
+  double *base = g_slab.get(2 * (21 * n2 + 5 * n2h));
   Mover m{s, base, {}};
   TrajIn in{};
   in.paph = m.in(paphp15, n2h); in.pap = m.in(papp15, n2); in.pq = m.in(pqm15, n2); in.pqs = m.in(pqs5, n2);
@@ -201,7 +200,7 @@ static void tlad(bool is_ad, const int *kidia, const int *kfdia, const int *klon
   dout.pcovptot = m.inout(pcovptot, n2);
   Geom g{*klon, *klev, *kfdia, 1};
   if (is_ad) {
-    ADOpts opt{0.0, 0, nullptr, m.next, (long long)ncp, 1, 0};
+    ADOpts opt{0.0, 0, nullptr, 0, 0};
     CKA(csc2_launch_ad(kc, g, in, out, din, dout, opt, s));
     csc2_shim_count_launch();      // forward + reverse sweep = two launches
   } else {

@@ -40,20 +40,19 @@ cudaError_t csc2_launch_taylor_finalize(const Geom &g, const double *tlsum, cons
                                         long long ncol_pad, double *ratios_blk, double *znormg,
                                         int *degenerate, cudaStream_t s);
 
-// Adjoint (cloudsc2_ad_kernel.cu): forward sweep storing the rain/snow flux entering every
-// level in `ckpt` ([2][klev][ncol_pad]), reverse sweep recomputing each level's trajectory.
+// Adjoint (cloudsc2_ad_kernel.cu): forward sweep = the NL kernel writing the trajectory outputs (its
+// PFPLSL / PFPLSN are the flux check-points), reverse sweep recomputing each level's trajectory.
 //  dot_scale != 0 : input adjoints are not written; instead <dot_scale * x, x*> is accumulated
 //                   per column into coldot (ZNORM2, cloudsc_driver_ad_mod.F90:240-256).
 struct ADOpts {
   double dot_scale;
   int zero_psupsat_pert;
   double *coldot;
-  double *ckpt;
-  long long ncol_pad;
-  int write_traj;          // write the trajectory outputs (PTENT5...) like the reference (:842-864)
+  long long ncol_pad;      // pitch of coldot
   int have_traj;           // the trajectory fluxes PFPLSL5/PFPLSN5 in `out` are already those of `in`
                            // (a CLOUDSC2 / CLOUDSC2TL call on the same inputs ran before, as in the
                            // adjoint test and in any 4D-Var inner loop): skip the forward sweep
+  long long flux_pitch;    // level pitch (doubles) of out.pfplsl / out.pfplsn as read by the reverse sweep; 0 = NPROMA
 };
 cudaError_t csc2_launch_ad(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
                            const IncIn &din, const IncOut &dout, const ADOpts &opt, cudaStream_t s);
@@ -97,8 +96,8 @@ cudaError_t csc2_upload_levels_tl(const double *ceta, const double *zscalm, cons
 cudaError_t csc2_upload_levels_ad(const double *ceta, const double *zscalm, const double *sq1mceta,
                                   int klev, cudaStream_t s);
 
-// Forward sweep of the adjoint as its own launch (cloudsc2_nl_kernel.cu): NL kernel that also
-// writes the rain/snow flux entering each level to ckpt ([2][klev][ncol_pad]); trajectory outputs
-// are written only if write_traj != 0.  Columns beyond ngptot are not touched.
-cudaError_t csc2_launch_nl_ckpt(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
-                                double *ckpt, long long ncol_pad, int write_traj, cudaStream_t s);
+// Forward (trajectory) sweep of the adjoint as its own launch (cloudsc2_nl_kernel.cu): the NL kernel without the
+// driver-level zeroing; its PFPLSL / PFPLSN outputs are the flux check-points of the reverse sweep.  Columns
+// beyond ngptot are not touched.
+cudaError_t csc2_launch_nl_traj(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                cudaStream_t s);

@@ -24,13 +24,8 @@ constexpr int NL_NF = CSC2_NTRAJ;   // staged fields per level: 15 inputs + opti
 // Template parameters: HAS_PQS (PQS supplied by the caller instead of the fused SATUR), STAGES =
 // depth of the shared-memory ring (levels in flight + the one being computed), NT = threads per
 // CTA, MAXREG = register cap (-> CTAs per SM), RV = (RVTMP2 != 0).
-// CKPT: forward (trajectory) sweep of the adjoint -- additionally check-points the rain / snow flux
-// ENTERING every level ([2][klev][ncol_pad]) and writes the trajectory outputs only on request.
-struct NLCkpt {
-  double *ckpt;
-  long long ncol_pad;
-  int write_traj;
-};
+// The same kernel is the forward (trajectory) sweep of the adjoint: the rain / snow flux entering level
+// JK+1 is its output PFPLSL / PFPLSN(JK+1), which the reverse sweep restarts from -- no check-point array.
 
 // PROBE != 0 exists only in the experiments build (tools/probes): extra dummy instructions per level.
 #ifdef CSC2_EXPERIMENTS
@@ -42,10 +37,9 @@ struct NlProbe {
   __device__ __forceinline__ bool fired() const { return false; }
 };
 #endif
-template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV, bool CKPT, int PROBE = 0>
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV, int PROBE = 0>
 __global__ void __maxnreg__(MAXREG)
-k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out,
-              const NLCkpt ck) {
+k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, const TrajOut out) {
   extern __shared__ double ring_all[];
   double *ring = ring_all + threadIdx.x;
   csc2_math_init();
@@ -56,7 +50,6 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   const int klev = g.klev, nproma = g.nproma;
   const ColOffsets o = csc2_col_offsets(ibl, jl, nproma, klev, in.bs_cld, in.bs_cml, out.bs_loc);
 
-  if (CKPT && gcol >= g.ngptot) return;
   if (gcol >= g.ngptot) {
     // padding column of the last block: the DRIVER zeroes PCOVPTOT and TENDENCY_LOC%CLD(:,:,NCLV)
     // of whole blocks (driver_mod.F90:87-88); CLOUDSC2 itself never touches columns beyond ICEND.
@@ -82,19 +75,11 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
   st.paph0 = ldin(in.paph + o.oh);
   st.rfl = 0.0;
   st.sfl = 0.0;
-  const bool wr = !CKPT || ck.write_traj != 0;
-  double *ck_r = nullptr, *ck_s = nullptr;
-  if (CKPT) {
-    ck_r = ck.ckpt + gcol;
-    ck_s = ck.ckpt + (size_t)klev * ck.ncol_pad + gcol;
-  }
   // flux rows at the model top (cloudsc2.F90:308-309, :732-733 -> -0.0)
-  if (wr) {
-    stout(out.pfplsl + o.oh, 0.0);
-    stout(out.pfplsn + o.oh, 0.0);
-    stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
-    stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
-  }
+  stout(out.pfplsl + o.oh, 0.0);
+  stout(out.pfplsn + o.oh, 0.0);
+  stout(out.pfhpsl + o.oh, -0.0 * c.rlvtt);
+  stout(out.pfhpsn + o.oh, -0.0 * c.rlstt);
 
   int slot = 0, pslot = STAGES - 1;
   NlProbe<PROBE> probe;
@@ -107,27 +92,21 @@ k_cloudsc2_nl(const __grid_constant__ KConst c, const Geom g, const TrajIn in, c
     const LevIn cur = csc2_read_level<NT>(ring + slot * (NL_NF * NT), jk, klev);
     const double pqs = HAS_PQS ? ring[(size_t)slot * (NL_NF * NT) + 15 * NT]
                                : satur_point(c, cur.pt, csc2_rcp(cur.pap));
-    if (CKPT && !wr) {   // with the trajectory outputs written, PFPLSL/PFPLSN are the check-points
-      ck_r[(size_t)jk * ck.ncol_pad] = st.rfl;
-      ck_s[(size_t)jk * ck.ncol_pad] = st.sfl;
-    }
     LevOut y;
     nl_level<RV>(c, crh, jk, cur, pqs, st, y);
 
-    if (wr) {
-      const size_t l = (size_t)jk * nproma;
-      stout(out.tent + o.oloc + l, y.tent);
-      stout(out.tenq + o.oloc + l, y.tenq);
-      stout(out.tenl + o.oloc + l, y.tenl);
-      stout(out.teni + o.oloc + l, y.teni);
-      if (out.loc_last) stout(out.loc_last + o.oloc + l, 0.0);
-      stout(out.pclc + o.o1 + l, y.pclc);
-      stout(out.pcovptot + o.o1 + l, 0.0);
-      stout(out.pfplsl + o.oh + l + nproma, y.rfln);
-      stout(out.pfplsn + o.oh + l + nproma, y.sfln);
-      stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);   // cloudsc2.F90:730-735
-      stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
-    }
+    const size_t l = (size_t)jk * nproma;
+    stout(out.tent + o.oloc + l, y.tent);
+    stout(out.tenq + o.oloc + l, y.tenq);
+    stout(out.tenl + o.oloc + l, y.tenl);
+    stout(out.teni + o.oloc + l, y.teni);
+    if (out.loc_last) stout(out.loc_last + o.oloc + l, 0.0);
+    stout(out.pclc + o.o1 + l, y.pclc);
+    stout(out.pcovptot + o.o1 + l, 0.0);
+    stout(out.pfplsl + o.oh + l + nproma, y.rfln);
+    stout(out.pfplsn + o.oh + l + nproma, y.sfln);
+    stout(out.pfhpsl + o.oh + l + nproma, -y.rfln * c.rlvtt);   // cloudsc2.F90:730-735
+    stout(out.pfhpsn + o.oh + l + nproma, -y.sfln * c.rlstt);
     slot = (slot + 1 == STAGES) ? 0 : slot + 1;
     pslot = (pslot + 1 == STAGES) ? 0 : pslot + 1;
   }
@@ -200,9 +179,9 @@ cudaError_t csc2_launch_math_probe(int fn, const double *x, double *y, int n, cu
 // The product shape: 2-stage ring, CTA of 128 columns, 128 registers -> 4 CTAs = 16 warps per SM
 // (measured at 163 840 columns: 16 warps 0.849 ms, 12 warps 0.885, 14 warps 0.878, 18-20 warps 0.92-0.99:
 // more warps cost registers -> instructions, and the kernel is issue-bound).
-template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV, bool CKPT = false, int PROBE = 0>
+template <bool HAS_PQS, int STAGES, int NT, int MAXREG, bool RV, int PROBE = 0>
 static cudaError_t launch_nl_rv(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
-                                cudaStream_t s, NLCkpt ck = NLCkpt{nullptr, 0, 1}) {
+                                cudaStream_t s) {
   const long long ncol = (long long)g.nblocks * g.nproma;
   const int grid = (int)((ncol + NT - 1) / NT);
 #ifdef CSC2_EXPERIMENTS
@@ -213,10 +192,10 @@ static cudaError_t launch_nl_rv(const KConst &c, const Geom &g, const TrajIn &in
   const size_t extra = 0;
 #endif
   const size_t smem = (size_t)STAGES * NL_NF * NT * sizeof(double) + extra;
-  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV, CKPT, PROBE>;
+  auto kern = k_cloudsc2_nl<HAS_PQS, STAGES, NT, MAXREG, RV, PROBE>;
   static CSC2_SMEM_FLAGS smem_ok{0};
   if (cudaError_t e0 = csc2_allow_smem(kern, smem, smem_ok)) return e0;
-  kern<<<grid, NT, smem, s>>>(c, g, in, out, ck);
+  kern<<<grid, NT, smem, s>>>(c, g, in, out);
   return cudaGetLastError();
 }
 
@@ -241,31 +220,18 @@ cudaError_t csc2_launch_nl(const KConst &c, const Geom &g, const TrajIn &in, con
   return launch_nl_rv<false, 2, 128, 128, false>(c, g, in, out, s);
 }
 
-// Forward (trajectory) sweep of the adjoint: the NL kernel + flux check-points.
-cudaError_t csc2_launch_nl_ckpt(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
-                                double *ckpt, long long ncol_pad, int write_traj, cudaStream_t s) {
-  const NLCkpt ck{ckpt, ncol_pad, write_traj};
+// Forward (trajectory) sweep of the adjoint: the NL kernel itself, without the driver-level zeroing.  Its
+// outputs PFPLSL5 / PFPLSN5 (cloudsc2ad.F90:847-848) are the flux check-points the reverse sweep restarts from.
+cudaError_t csc2_launch_nl_traj(const KConst &c, const Geom &g, const TrajIn &in, const TrajOut &out,
+                                cudaStream_t s) {
   TrajOut o = out;
   o.loc_last = nullptr;
-  // With the trajectory outputs written (what every entry point of the library asks for: CLOUDSC2AD as
-  // written, cloudsc2ad.F90:842-864) the fluxes PFPLSL5 / PFPLSN5 ARE the check-points: the forward sweep is
-  // the plain NL kernel without the driver-level zeroing -- same code, same registers, one kernel shape less
-  // on the adjoint's path (the CKPT instantiation carried the unused check-point pointers: 887 instead of
-  // 869 instructions per level, 0.89 instead of 0.85 ms).
-  if (write_traj) {
-    if (c.rvtmp2 != 0.0) {
-      if (in.pqs) return launch_nl_rv<true, 2, 128, 128, true>(c, g, in, o, s);
-      return launch_nl_rv<false, 2, 128, 128, true>(c, g, in, o, s);
-    }
-    if (in.pqs) return launch_nl_rv<true, 2, 128, 128, false>(c, g, in, o, s);
-    return launch_nl_rv<false, 2, 128, 128, false>(c, g, in, o, s);
-  }
   if (c.rvtmp2 != 0.0) {
-    if (in.pqs) return launch_nl_rv<true, 2, 128, 128, true, true>(c, g, in, o, s, ck);
-    return launch_nl_rv<false, 2, 128, 128, true, true>(c, g, in, o, s, ck);
+    if (in.pqs) return launch_nl_rv<true, 2, 128, 128, true>(c, g, in, o, s);
+    return launch_nl_rv<false, 2, 128, 128, true>(c, g, in, o, s);
   }
-  if (in.pqs) return launch_nl_rv<true, 2, 128, 128, false, true>(c, g, in, o, s, ck);
-  return launch_nl_rv<false, 2, 128, 128, false, true>(c, g, in, o, s, ck);
+  if (in.pqs) return launch_nl_rv<true, 2, 128, 128, false>(c, g, in, o, s);
+  return launch_nl_rv<false, 2, 128, 128, false>(c, g, in, o, s);
 }
 
 cudaError_t csc2_launch_expand(const double *src, int nlon, long long rows, double *dst, int nproma,

@@ -134,9 +134,9 @@ static cudaError_t csc2_launch_nl_experiment(const KConst &c, const Geom &g, con
     case 9: return launch_nl_variant<false, 2, 256, 128>(c, g, in, out, s);   // 16, 2 CTAs of 8 warps
     case 10: return launch_nl_variant<false, 2, 64, 128>(c, g, in, out, s);   // 16, 8 CTAs of 2 warps
     case 14: return launch_nl_variant<false, 2, 32, 128>(c, g, in, out, s);   // 16, 16 CTAs of 1 warp
-    case 11: return launch_nl_rv<false, 2, 128, 128, false, false, 1>(c, g, in, out, s);   // probes
-    case 12: return launch_nl_rv<false, 2, 128, 128, false, false, 2>(c, g, in, out, s);
-    case 13: return launch_nl_rv<false, 2, 128, 128, false, false, 3>(c, g, in, out, s);
+    case 11: return launch_nl_rv<false, 2, 128, 128, false, 1>(c, g, in, out, s);   // probes
+    case 12: return launch_nl_rv<false, 2, 128, 128, false, 2>(c, g, in, out, s);
+    case 13: return launch_nl_rv<false, 2, 128, 128, false, 3>(c, g, in, out, s);
     // measured at 163 840 columns: 16 warps 0.849 ms, 12 warps 0.885, 14 warps 0.878, 18 warps 0.916-0.994,
     // 20 warps 0.995 (more warps than 16 cost registers -> instructions, and the kernel is issue-bound)
     default: return cudaErrorNotSupported;                                    // 16: the product shape
