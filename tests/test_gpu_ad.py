@@ -245,3 +245,12 @@ def test_host_ad_with_precomputed_trajectory_equals_as_written(pkg, src100):
         assert not v[:-1].any() and not v[-1][:, :8].any(), k
         assert np.array_equal(v[-1][:, 8:], outs[1][2][k][-1][:, 8:]), k
     del rng
+
+
+@pytest.mark.parametrize("lregcl", [False, True])
+def test_ad_fields_match_transliterated_fortran(pkg, obref, src100, lregcl):
+    """The CUDA CLOUDSC2AD against the reference's OWN Fortran text (oracle/_ref: cloudsc2ad.F90,
+    cuadjtqs.F90, cuadjtqsad.F90 transliterated by oracle/f90toc.py) directly: LREGCL off and on
+    (cloudsc2ad.F90:1057-1059, 1308-1350, 1460, 1554-1559 -- the AD program's configuration)."""
+    test_ad_fields_match_oracle(pkg, obref, src100, 100, 100, lregcl)
+    test_ad_fields_match_oracle(pkg, obref, src100, 64, 200, lregcl)

@@ -313,3 +313,10 @@ def test_nl_launch_variants_agree(pkg, src100, gpu_nl, variant):
         finally:
             gpu_nl.set_option("nl_variant", 0)
         _cmp(b.outputs(), a.outputs(), rtol=1e-13)
+
+
+def test_nl_matches_transliterated_fortran(pkg, obref, src100, gpu_nl):
+    """The CUDA NL step against the reference's OWN Fortran text (oracle/_ref: satur.F90 + cloudsc2.F90
+    transliterated by oracle/f90toc.py) under the driver loop, all 100 source columns, two blockings."""
+    test_nl_host_entry_matches_oracle(pkg, obref, src100, gpu_nl, 100, 100)
+    test_nl_host_entry_matches_oracle(pkg, obref, src100, gpu_nl, 32, 1000)

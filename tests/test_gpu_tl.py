@@ -273,3 +273,12 @@ def test_host_tl_and_ad_pipeline_equals_device_entries_many_chunks(pkg, src100, 
         assert np.array_equal(din[k], want_ad[k]), k
     for k in dout:
         assert not dout[k][:-1].any() and not dout[k][-1][:, :57].any(), k
+
+
+@pytest.mark.parametrize("lregcl", [False, True])
+def test_tl_fields_match_transliterated_fortran(pkg, obref, src100, lregcl):
+    """The CUDA CLOUDSC2TL against the reference's OWN Fortran text (oracle/_ref, cloudsc2tl.F90 +
+    cuadjtqstl.F90 transliterated by oracle/f90toc.py) directly, not only through the hand oracle:
+    100 columns, LREGCL off and on (the regularised statements :575-580, 657, 754-760, 794-800, 998-1000)."""
+    test_tl_fields_match_oracle(pkg, obref, src100, 100, 100, lregcl)
+    test_tl_fields_match_oracle(pkg, obref, src100, 64, 640, lregcl)
