@@ -40,4 +40,13 @@ except Exception as e:
 PY
 tail -4 $out/pytest_gpu_n8.log
 grep -E "GPU:|TEST|rc=|^==|validation:" $out/programs_n8.log
+{
+  nvidia-smi topo -m 2>&1
+  lscpu 2>&1 | grep -i -E "numa|socket|model name|^cpu\(s\)|thread"
+  for d in /sys/bus/pci/devices/*; do
+    if [ "$(cat $d/class 2>/dev/null)" = "0x030200" ]; then echo "$d numa_node=$(cat $d/numa_node) local_cpulist=$(cat $d/local_cpulist) link=$(cat $d/current_link_speed 2>/dev/null) x$(cat $d/current_link_width 2>/dev/null)"; fi
+  done
+  grep -E "Cpus_allowed_list|Mems_allowed_list" /proc/self/status
+  for n in /sys/devices/system/node/node*; do echo "$n cpulist=$(cat $n/cpulist) $(grep MemTotal $n/meminfo)"; done
+} > $out/topology_n8.log 2>&1
 free -g | head -2; nproc
