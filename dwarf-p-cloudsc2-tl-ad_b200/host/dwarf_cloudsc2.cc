@@ -18,8 +18,10 @@
 //
 // Environment:
 //   CLOUDSC2_INPUT      path of input.h5 (default ./input.h5 if it exists; else synthetic columns)
-//   CLOUDSC2_REFERENCE  path of reference.h5 for the NL validation (default ./reference.h5 if it
-//                       exists; else the un-expanded columns computed as one block are the reference)
+//   CLOUDSC2_REFERENCE  path of reference.h5 for the NL validation (default ./reference.h5 next to an input.h5;
+//                       for the default synthetic columns the shipped config-files/reference_synth_seed0.h5 =
+//                       the CPU restatement's results; else, or with the value "self", the un-expanded columns
+//                       computed as one block on the GPU are the reference: a self-consistency check only)
 //   CLOUDSC2_WRITE_INPUT  path: write the columns and constants in use as an input.h5 (all datasets the
 //                       reference's loaders read) before running -- to run the reference's binaries
 //                       on the synthetic columns elsewhere
@@ -52,6 +54,8 @@
 #include <utility>
 #include <vector>
 
+#include <unistd.h>
+
 #include "cloudsc2_host.h"
 
 namespace {
@@ -66,6 +70,17 @@ enum Mode { NL, TL, AD };
 
 void ck(int rc, const char *what) {
   if (rc) abor1(std::string(what) + ": " + cloudsc2_gpu_last_error());
+}
+
+// directory of this executable (bin/), to find the shipped config-files/ next to it
+std::string exe_dir() {
+  char buf[4096];
+  const ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
+  if (n <= 0) return ".";
+  buf[n] = 0;
+  std::string p(buf);
+  const size_t slash = p.find_last_of('/');
+  return slash == std::string::npos ? "." : p.substr(0, slash);
 }
 
 bool file_exists(const char *p) {
@@ -272,11 +287,25 @@ int main(int argc, char **argv) {
   if (o.mode == NL) {
     const char *ref_env = std::getenv("CLOUDSC2_REFERENCE");
     std::string ref_path = (ref_env && *ref_env) ? ref_env : (file_exists("reference.h5") && !in_path.empty() ? "reference.h5" : "");
+    const bool force_self = ref_path == "self";
+    if (force_self) ref_path.clear();
+    bool shipped = false;
+    if (ref_path.empty() && !force_self && in_path.empty() && src.klon == 100 && src.klev == 137 &&
+        env_int("CLOUDSC2_SYNTH_SEED", 0) == 0) {
+      // the default synthetic columns have a reference of their own: the CPU oracle's results (pinned to the
+      // reference's Fortran text), shipped like the reference ships config-files/reference.h5
+      const std::string cand = exe_dir() + "/../config-files/reference_synth_seed0.h5";
+      if (file_exists(cand.c_str())) { ref_path = cand; shipped = true; }
+    }
     if (!ref_path.empty()) {
       if (cloudsc2_reference_load_h5(&ref, ref_path.c_str()))
         abor1(std::string("cannot load ") + ref_path + ": " + cloudsc2_input_last_error());
       if (ref.klon != src.klon || ref.klev != src.klev) abor1("reference.h5 and the input differ in KLON/KLEV");
-      std::snprintf(ref_line, sizeof ref_line, " reference: %s", ref_path.c_str());
+      if (shipped)
+        std::snprintf(ref_line, sizeof ref_line, " reference: config-files/reference_synth_seed0.h5 (the synthetic columns run by the CPU "
+                      "restatement of the reference, NPROMA=KLON)");
+      else
+        std::snprintf(ref_line, sizeof ref_line, " reference: %s", ref_path.c_str());
       independent_ref = true;
     } else {
       self_reference(src, ref);

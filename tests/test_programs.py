@@ -120,6 +120,23 @@ def test_reference_h5_loader(pkg, tmp_path):
         lib.cloudsc2_reference_free(C.byref(r))
 
 
+def test_shipped_reference_of_the_synthetic_columns_is_the_cpu_oracle(pkg, ob, src100):
+    """config-files/reference_synth_seed0.h5 (what dwarf-cloudsc2-nl validates the default synthetic run against)
+    is exactly what tests/golden/make_reference_h5.py says: the CPU restatement's CLOUDSC_DRIVER on the 100
+    columns of seed 0 as one block, in the reference's reference.h5 format."""
+    path = ROOT / "dwarf-p-cloudsc2-tl-ad_b200" / "config-files" / "reference_synth_seed0.h5"
+    assert path.exists() and path.stat().st_size < 2_000_000
+    st = pkg.ArrayState(src100, nproma=100, ngptot=100)
+    ob.driver_nl(pkg.default_params(lregcl=False), src100.ceta, st, numomp=1)
+    assert pkg.read_h5_i4(path, "KLON")[0] == 100 and pkg.read_h5_i4(path, "KLEV")[0] == 137
+    for name, want in (("PLUDE", st.a["plude"][0]), ("PCOVPTOT", st.a["pcovptot"][0]), ("PFPLSL", st.a["pfplsl"][0]),
+                       ("PFPLSN", st.a["pfplsn"][0]), ("PFHPSL", st.a["pfhpsl"][0]), ("PFHPSN", st.a["pfhpsn"][0]),
+                       ("TENDENCY_LOC_T", st.a["b_loc"][0][0]), ("TENDENCY_LOC_A", st.a["b_loc"][0][1]),
+                       ("TENDENCY_LOC_Q", st.a["b_loc"][0][2]), ("TENDENCY_LOC_CLD", st.a["b_loc"][0][3:])):
+        assert np.array_equal(pkg.read_h5_f8(path, name), want), name
+    assert np.abs(st.a["pfplsn"]).max() > 0
+
+
 # ---- CPU: command line ----------------------------------------------------------------------------
 
 def test_programs_command_line(built, pkg):
@@ -157,14 +174,21 @@ def test_dwarf_nl_baseline_config(built, pkg):
     assert len(tot) == 1
     nums = tot[0].replace("x", " ").replace(":", " ").split()
     assert nums[:6] == ["1", "4", "160000", "160000", "5000", "32"]
-    assert "SELF-CONSISTENCY only" in r.stdout and "UNVERIFIED" in r.stdout   # no reference.h5 in this image
+    # the default synthetic columns are validated against the SHIPPED reference: the CPU restatement's results
+    # (config-files/reference_synth_seed0.h5, made by tests/golden/make_reference_h5.py) -- an independent check
+    assert "reference: config-files/reference_synth_seed0.h5" in r.stdout and "UNVERIFIED" not in r.stdout
     v = _validation_lines(r.stdout)
     want = ["PLUDE", "PCOVPTOT", "PFPLSL", "PFPLSN", "PFHPSL", "PFHPSN", "TENDENCY_LOC%A",
             "TENDENCY_LOC%Q", "TENDENCY_LOC%T", "TENDENCY_LOC%CLD"]
     assert list(v) == want                                            # the reference's order (:239-251)
     for name, (nums5, warn) in v.items():
+        assert nums5[4] < 1e-9, (name, nums5)                         # MaxRelErr-% : GPU vs CPU, last bits only
+    assert v["PFPLSN"][0][1] > 0 and v["TENDENCY_LOC%T"][0][1] > 0 and v["PFPLSN"][0][2] > 0   # not trivially equal
+    # CLOUDSC2_REFERENCE=self: the GPU's own one-block results as reference -- bit-identical, and labelled as what it is
+    r2 = _run(built, "dwarf-cloudsc2-nl", 4, 160000, 32, env={"CLOUDSC2_REFERENCE": "self"})
+    assert r2.returncode == 0 and "SELF-CONSISTENCY only" in r2.stdout and "UNVERIFIED" in r2.stdout
+    for name, (nums5, warn) in _validation_lines(r2.stdout).items():
         assert not warn and nums5[2] == 0.0 and nums5[4] == 0.0, (name, nums5)   # bit-identical to 1 block
-    assert v["PFPLSN"][0][1] > 0 and v["TENDENCY_LOC%T"][0][1] > 0    # and not trivially zero
     m = re.search(r"GPU: ([0-9.]+) ms per driver call", r.stderr)
     assert m and float(m.group(1)) < 50.0
 
@@ -178,8 +202,8 @@ def test_dwarf_gpus_do_not_change_results(built, pkg):
     if ndev < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     n = min(ndev, 4)
-    one = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64)
-    many = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NGPUS": str(n)})
+    one = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_REFERENCE": "self"})
+    many = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NGPUS": str(n), "CLOUDSC2_REFERENCE": "self"})
     assert one.returncode == 0 and many.returncode == 0, many.stderr
     assert f"NUMPROC=1, NUMOMP=1, NGPTOTG=10000, NPROMA=64, NGPBLKS=157   (GPUs: {n})" in many.stderr
     per_gpu = [l for l in many.stderr.splitlines() if re.search(r": GPU \d+$", l)]
@@ -189,7 +213,8 @@ def test_dwarf_gpus_do_not_change_results(built, pkg):
     assert list(v1) == list(vn) and len(vn) == 10
     for name in v1:
         assert v1[name][0][:3] == vn[name][0][:3] and vn[name][0][2] == 0.0 and not vn[name][1], name
-    hosted = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NGPUS": str(n), "CLOUDSC2_HOST_ARRAYS": "1"})
+    hosted = _run(built, "dwarf-cloudsc2-nl", 1, 10000, 64, env={"CLOUDSC2_NGPUS": str(n), "CLOUDSC2_HOST_ARRAYS": "1",
+                                                                   "CLOUDSC2_REFERENCE": "self"})
     assert hosted.returncode == 0 and _validation_lines(hosted.stdout) == vn
     a1 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50)
     a2 = _run(built, "dwarf-cloudsc2-ad", 1, 1000, 50, env={"CLOUDSC2_NGPUS": "2"})
