@@ -291,7 +291,11 @@ double cloudsc2_error_rel(const double stats[5], int *flag_out) {
   if (zerrsum < zeps) zrelerr = 0.0;
   else if (zsum < zeps) zrelerr = zerrsum / (1.0 + zsum);
   else zrelerr = zerrsum / zsum;
-  if (flag_out) *flag_out = zrelerr > 10.0 * zeps;
+  // the "!!!!" warning; a non-finite statistic (NaN results or NaN reference values) is always flagged --
+  // `NaN > x` is false, which would otherwise let it pass silently
+  bool finite = true;
+  for (int i = 0; i < 5; ++i) finite = finite && std::isfinite(stats[i]) && std::fabs(stats[i]) < 1.0e300;
+  if (flag_out) *flag_out = !finite || zrelerr > 10.0 * zeps;
   return 100.0 * zrelerr;
 }
 

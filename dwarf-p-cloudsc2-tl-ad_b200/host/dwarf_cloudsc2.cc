@@ -132,7 +132,9 @@ int error_print(const char *name, int ndim, const double st[5], long long ngptot
   if (st[3] < zeps) { rel = 0.0; iopt = 1; }
   else if (st[4] < zeps) { rel = st[3] / (1.0 + st[4]); iopt = 2; }
   else { rel = st[3] / st[4]; iopt = 3; }
-  const bool warn = rel > 10.0 * zeps;
+  bool finite = true;
+  for (int i = 0; i < 5; ++i) finite = finite && std::isfinite(st[i]) && std::fabs(st[i]) < 1.0e300;
+  const bool warn = !finite || rel > 10.0 * zeps;   // NaN > x is false: a non-finite statistic is always marked
   std::printf(" %-20s %1dD%1d %s %s %s %s %s%s\n", name, ndim, iopt, fortran_e(st[0]).c_str(),
               fortran_e(st[1]).c_str(), fortran_e(st[2]).c_str(),
               fortran_e(st[3] / (double)ngptotg).c_str(), fortran_e(100.0 * rel).c_str(), warn ? " !!!!" : "");
