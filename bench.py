@@ -55,15 +55,15 @@ TL_BYTES_MOVED = (2056 + 2193 + 1374 + 1374) * 8
 # 163 840 columns) and FP64-pipe utilisation of the same capture.  Every entry names the capture it comes
 # from (kernel instantiation + profiles/ file); tools/profile_r2*.sh regenerate them.
 NCU = {"nl": {"dram_bytes_per_column": 4.741e9 / 163840, "fp64_pipe_pct": 60.5, "profile": "profiles/r2e_nl_ncu.md",
-              "kernel": "k_cloudsc2_nl<0,2,128,128,0,0,0>"},
-       "tl": {"dram_bytes_per_column": 9.236e9 / 163840, "fp64_pipe_pct": 55.9, "profile": "profiles/r2a_tl_ncu.md",
+              "kernel": "k_cloudsc2_nl<0,2,128,128,0,0>"},
+       "tl": {"dram_bytes_per_column": 9.237e9 / 163840, "fp64_pipe_pct": 55.9, "profile": "profiles/r2r_tl_ncu.md",
               "kernel": "k_cloudsc2_tl<0,2,0,0,2,128>"},
        # AD = forward sweep (the NL kernel without the driver-level zeroing; its PFPLSL/PFPLSN outputs are the
-       # flux check-points: 4.562 GB, profiles/r2a_adfwd_ncu.md -- captured on the former CKPT instantiation,
-       # which moved the same bytes) + reverse sweep kernel (12.107 GB, profiles/r2a_ad_ncu.md)
-       "ad": {"dram_bytes_per_column": (12.107e9 + 4.562e9) / 163840, "fp64_pipe_pct": 43.6,
-              "profile": "profiles/r2a_ad_ncu.md + profiles/r2a_adfwd_ncu.md",
-              "kernel": "k_cloudsc2_nl<0,2,128,128,0,0,0> (loc_last = NULL) + k_cloudsc2_ad<0,0,0,2>"}}
+       # flux check-points: 4.562 GB = the NL launch's 4.741 GB minus the 0.18 GB of zeros for CLD(:,:,NCLV),
+       # profiles/r2e_nl_ncu.md, r2a_adfwd_ncu.md) + reverse sweep kernel (12.108 GB, profiles/r2r_ad_ncu.md)
+       "ad": {"dram_bytes_per_column": (12.108e9 + 4.562e9) / 163840, "fp64_pipe_pct": 43.6,
+              "profile": "profiles/r2r_ad_ncu.md + profiles/r2a_adfwd_ncu.md",
+              "kernel": "k_cloudsc2_nl<0,2,128,128,0,0> (loc_last = NULL) + k_cloudsc2_ad<0,0,0,2>"}}
 METRIC = "NL columns/s (KLEV=137)"
 UNIT = "columns/s"
 
