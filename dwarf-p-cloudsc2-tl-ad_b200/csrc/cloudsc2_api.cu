@@ -803,43 +803,50 @@ static int taylor_finish(const Geom &whole, const TaylorScratch &t, double znorm
 
 int cloudsc2_gpu_tl_taylor_dev(int nproma, int klev, int ngptot, double ptsphy,
                                const cloudsc2_fields *dev, double znormg[10], double *ratios_blk) {
-  if (int rc = csc2_require_init()) return rc;
-  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
-  if (int rc = check_fields(dev)) return rc;
-  if (!znormg) return csc2_fail(3, "znormg is NULL");
-  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  Geom geo{};
   TaylorScratch t;
-  if (int rc = taylor_reserve(geo, t)) return rc;
-  TrajIn in; TrajOut out;
-  views_from_fields(*dev, nproma, klev, in, out);
-  cudaStream_t s = G.stream;
-  if (int rc = scratch_begin(s)) return rc;
-  if (int rc = taylor_enqueue(make_kconst(ptsphy), geo, in, out, t, 0, s)) return rc;
-  return taylor_finish(geo, t, znormg, ratios_blk, s);
+  // (every device of a set agrees on the status of its local work before anyone enters the all-reduce)
+  auto local_part = [&]() -> int {
+    if (int rc = csc2_require_init()) return rc;
+    if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+    if (int rc = check_fields(dev)) return rc;
+    if (!znormg) return csc2_fail(3, "znormg is NULL");
+    geo = Geom{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+    if (int rc = taylor_reserve(geo, t)) return rc;
+    TrajIn in; TrajOut out;
+    views_from_fields(*dev, nproma, klev, in, out);
+    if (int rc = scratch_begin(G.stream)) return rc;
+    return taylor_enqueue(make_kconst(ptsphy), geo, in, out, t, 0, G.stream);
+  };
+  if (int rc = csc2_agree(local_part())) return rc;
+  return taylor_finish(geo, t, znormg, ratios_blk, G.stream);
 }
 
 // Host arrays: the chunked pipeline (inputs up, three sweeps, NL outputs back, per chunk), then the norms.
 int csc2_taylor_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
                          double znormg[10], double *ratios_blk) {
-  if (int rc = csc2_require_init()) return rc;
-  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
-  if (int rc = check_fields(h)) return rc;
-  if (!znormg) return csc2_fail(3, "znormg is NULL");
-  HostPipe P;
-  if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
-  P.derive = false;
-  P.driver_level = true;
-  const Geom whole{nproma, klev, ngptot, (int)P.nb};
+  Geom whole{};
   TaylorScratch t;
-  if (int rc = taylor_reserve(whole, t)) return rc;
-  const KConst kc = make_kconst(ptsphy);
-  if (int rc = scratch_begin(G.stream)) return rc;     // the pipe streams start behind the main stream
-  if (int rc = run_pipeline(P, false,
-                            [&](size_t b0, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
-                              return taylor_enqueue(kc, geo, in, out, t, (long long)b0 * nproma, s);
-                            },
-                            nullptr, nullptr))
-    return rc;
+  auto local_part = [&]() -> int {
+    if (int rc = csc2_require_init()) return rc;
+    if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+    if (int rc = check_fields(h)) return rc;
+    if (!znormg) return csc2_fail(3, "znormg is NULL");
+    HostPipe P;
+    if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
+    P.derive = false;
+    P.driver_level = true;
+    whole = Geom{nproma, klev, ngptot, (int)P.nb};
+    if (int rc = taylor_reserve(whole, t)) return rc;
+    const KConst kc = make_kconst(ptsphy);
+    if (int rc = scratch_begin(G.stream)) return rc;     // the pipe streams start behind the main stream
+    return run_pipeline(P, false,
+                        [&](size_t b0, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
+                          return taylor_enqueue(kc, geo, in, out, t, (long long)b0 * nproma, s);
+                        },
+                        nullptr, nullptr);
+  };
+  if (int rc = csc2_agree(local_part())) return rc;
   return taylor_finish(whole, t, znormg, ratios_blk, G.stream);
 }
 
@@ -911,42 +918,48 @@ static int adtest_finish(const Geom &whole, const AdTestScratch &a, double *znor
 
 int cloudsc2_gpu_ad_test_dev(int nproma, int klev, int ngptot, double ptsphy,
                              const cloudsc2_fields *dev, double *znormg, double *norms_col) {
-  if (int rc = csc2_require_init()) return rc;
-  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
-  if (int rc = check_fields(dev)) return rc;
-  if (!znormg) return csc2_fail(3, "znormg is NULL");
-  Geom geo{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+  Geom geo{};
   AdTestScratch a;
-  if (int rc = adtest_reserve(geo, a)) return rc;
-  TrajIn in; TrajOut out;
-  views_from_fields(*dev, nproma, klev, in, out);
-  cudaStream_t s = G.stream;
-  if (int rc = scratch_begin(s)) return rc;
-  if (int rc = adtest_enqueue(make_kconst(ptsphy), geo, in, out, a, 0, s)) return rc;
-  return adtest_finish(geo, a, znormg, norms_col, s);
+  auto local_part = [&]() -> int {
+    if (int rc = csc2_require_init()) return rc;
+    if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+    if (int rc = check_fields(dev)) return rc;
+    if (!znormg) return csc2_fail(3, "znormg is NULL");
+    geo = Geom{nproma, klev, ngptot, nblocks_of(ngptot, nproma)};
+    if (int rc = adtest_reserve(geo, a)) return rc;
+    TrajIn in; TrajOut out;
+    views_from_fields(*dev, nproma, klev, in, out);
+    if (int rc = scratch_begin(G.stream)) return rc;
+    return adtest_enqueue(make_kconst(ptsphy), geo, in, out, a, 0, G.stream);
+  };
+  if (int rc = csc2_agree(local_part())) return rc;
+  return adtest_finish(geo, a, znormg, norms_col, G.stream);
 }
 
 int csc2_adtest_host_one(int nproma, int klev, int ngptot, double ptsphy, const cloudsc2_fields *h,
                          double *znormg, double *norms_col) {
-  if (int rc = csc2_require_init()) return rc;
-  if (int rc = check_dims(nproma, klev, ngptot)) return rc;
-  if (int rc = check_fields(h)) return rc;
-  if (!znormg) return csc2_fail(3, "znormg is NULL");
-  HostPipe P;
-  if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
-  P.derive = false;
-  P.driver_level = true;
-  const Geom whole{nproma, klev, ngptot, (int)P.nb};
+  Geom whole{};
   AdTestScratch a;
-  if (int rc = adtest_reserve(whole, a)) return rc;
-  const KConst kc = make_kconst(ptsphy);
-  if (int rc = scratch_begin(G.stream)) return rc;
-  if (int rc = run_pipeline(P, false,
-                            [&](size_t b0, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
-                              return adtest_enqueue(kc, geo, in, out, a, b0, s);
-                            },
-                            nullptr, nullptr))
-    return rc;
+  auto local_part = [&]() -> int {
+    if (int rc = csc2_require_init()) return rc;
+    if (int rc = check_dims(nproma, klev, ngptot)) return rc;
+    if (int rc = check_fields(h)) return rc;
+    if (!znormg) return csc2_fail(3, "znormg is NULL");
+    HostPipe P;
+    if (int rc = P.init(nproma, klev, ngptot, h, 0)) return rc;
+    P.derive = false;
+    P.driver_level = true;
+    whole = Geom{nproma, klev, ngptot, (int)P.nb};
+    if (int rc = adtest_reserve(whole, a)) return rc;
+    const KConst kc = make_kconst(ptsphy);
+    if (int rc = scratch_begin(G.stream)) return rc;
+    return run_pipeline(P, false,
+                        [&](size_t b0, size_t, const Geom &geo, const TrajIn &in, const TrajOut &out, cudaStream_t s) -> int {
+                          return adtest_enqueue(kc, geo, in, out, a, b0, s);
+                        },
+                        nullptr, nullptr);
+  };
+  if (int rc = csc2_agree(local_part())) return rc;
   return adtest_finish(whole, a, znormg, norms_col, G.stream);
 }
 

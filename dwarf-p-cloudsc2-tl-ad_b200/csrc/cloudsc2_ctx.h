@@ -104,6 +104,12 @@ struct Shard {
 };
 Shard csc2_shard(int index, int ndev, int nproma, int ngptot);
 
+// Called by every device's worker exactly once per multi-device job, BEFORE the job's first collective, with
+// the status of its work so far: returns rc if it is non-zero, 8 if another device of the set failed, else 0 --
+// and then nobody enters the collective (an all-reduce entered by only some ranks never returns).  Outside a
+// worker thread (single device, process-per-GPU jobs) it returns rc unchanged.
+int csc2_agree(int rc);
+
 // MAX / MIN / SUM all-reduce of n device-resident doubles over the context's communicator, in
 // place, enqueued on `s` (no-op without a communicator).  op: 0 max, 1 min, 2 sum.
 int csc2_allreduce(Ctx &c, double *dev, int n, int op, cudaStream_t s);

@@ -46,6 +46,7 @@ namespace {
 
 thread_local char tl_err[1024] = "";
 thread_local Ctx *tl_ctx = nullptr;
+thread_local bool tl_is_worker = false;
 
 // ---- NCCL, bound at run time ---------------------------------------------------------------------
 struct NcclApi {
@@ -112,6 +113,11 @@ struct DeviceSet {
   std::unique_ptr<Worker> worker[CSC2_MAX_DEVICES];
   bool inproc_comm = false;     // communicator made by ncclCommInitAll over the set
   std::mutex call_mu;           // one multi-device call at a time
+  // host barrier of csc2_agree
+  std::mutex bar_mu;
+  std::condition_variable bar_cv;
+  int bar_count = 0, bar_any = 0, bar_result = 0;
+  unsigned long long bar_gen = 0;
   void stop_workers() {
     for (int i = 0; i < CSC2_MAX_DEVICES; ++i) {
       if (!worker[i]) continue;
@@ -136,6 +142,7 @@ void worker_main(int index) {
   Worker &w = *set_.worker[index];
   Ctx &c = *set_.ctx[index];
   tl_ctx = &c;
+  tl_is_worker = true;
   cudaSetDevice(c.device);
   std::unique_lock<std::mutex> lk(w.m);
   for (;;) {
@@ -296,7 +303,7 @@ int check_host_call(int nproma, int klev, int ngptot, const cloudsc2_fields *h) 
 
 // A rank that owns no block still takes part in the collectives, with the identities.
 int reduce_identity(Ctx &c, int nmax, int nsum) {
-  if (int rc = c.res.reserve(32 * sizeof(double))) return rc;
+  if (int rc = csc2_agree(c.res.reserve(32 * sizeof(double)))) return rc;
   double *d = c.res.d();
   CK(csc2_launch_fill(d, nmax, -1.7976931348623157e308, c.stream));
   if (int rc = csc2_allreduce(c, d, nmax, 0, c.stream)) return rc;
@@ -371,8 +378,30 @@ Shard csc2_shard(int index, int ndev, int nproma, int ngptot) {
   return s;
 }
 
+int csc2_agree(int rc) {
+  if (!tl_is_worker || set_.n <= 1) return rc;
+  std::unique_lock<std::mutex> lk(set_.bar_mu);
+  if (rc) set_.bar_any = 1;
+  const unsigned long long gen = set_.bar_gen;
+  if (++set_.bar_count == set_.n) {
+    set_.bar_result = set_.bar_any;
+    set_.bar_any = 0;
+    set_.bar_count = 0;
+    ++set_.bar_gen;
+    set_.bar_cv.notify_all();
+  } else {
+    set_.bar_cv.wait(lk, [&] { return set_.bar_gen != gen; });
+  }
+  if (rc) return rc;
+  if (set_.bar_result) return csc2_fail(8, "another device of the set failed before the all-reduce; collective skipped");
+  return 0;
+}
+
 int csc2_allreduce(Ctx &c, double *dev, int n, int op, cudaStream_t s) {
   if (!c.comm || c.comm_size <= 1) return 0;
+  // the in-process communicator spans the device set: only the set's workers, all together, may enter it; a
+  // user thread working on one selected device (cloudsc2_gpu_select_device) gets that device's own values
+  if (set_.inproc_comm && !tl_is_worker) return 0;
   NcclApi *api = nccl_api();
   if (!api) return csc2_fail(7, "NCCL is not available");
   const ncclRedOp_t ops[3] = {ncclMax, ncclMin, ncclSum};
@@ -786,54 +815,60 @@ static int val_job(int idx, void *p) {
   ValJob &j = *static_cast<ValJob *>(p);
   Ctx &c = csc2_ctx();
   DevState &st = c.state;
-  if (!st.loaded) return csc2_fail(2, "cloudsc2_gpu_state_load has not been called");
-  const cloudsc2_reference &r = *j.ref;
-  const int klon = r.klon, klev = st.klev, nproma = st.nproma;
-  const size_t n = (size_t)klon * klev, nh = n + klon;
-  // result layout on the device: [10][8] doubles (5 used), reduced in place
-  const size_t ref_total = 2 * n + 4 * nh + CLOUDSC2_NSTATE * n;
-  if (int rc = c.work2.reserve(ref_total * sizeof(double))) return rc;
-  if (int rc = c.res.reserve(csc2_validate_scratch_bytes() + 128 * sizeof(double))) return rc;
-  double *d_out = c.res.d();
-  void *scratch = d_out + 128;
   cudaStream_t q = c.stream;
-  double *d = c.work2.d();
-  auto up = [&](const double *h, size_t cnt) -> double * {
-    double *dst = d;
-    cudaMemcpyAsync(dst, h, cnt * sizeof(double), cudaMemcpyHostToDevice, q);
-    d += cnt;
-    return dst;
+  double *d_out = nullptr;
+  // everything before the collectives; its status is agreed between the devices first
+  auto local_part = [&]() -> int {
+    if (!st.loaded) return csc2_fail(2, "cloudsc2_gpu_state_load has not been called");
+    const cloudsc2_reference &r = *j.ref;
+    const int klon = r.klon, klev = st.klev, nproma = st.nproma;
+    const size_t n = (size_t)klon * klev, nh = n + klon;
+    // result layout on the device: [10][8] doubles (5 used), reduced in place
+    const size_t ref_total = 2 * n + 4 * nh + CLOUDSC2_NSTATE * n;
+    if (int rc = c.work2.reserve(ref_total * sizeof(double))) return rc;
+    if (int rc = c.res.reserve(csc2_validate_scratch_bytes() + 128 * sizeof(double))) return rc;
+    d_out = c.res.d();
+    void *scratch = d_out + 128;
+    double *d = c.work2.d();
+    auto up = [&](const double *h, size_t cnt) -> double * {
+      double *dst = d;
+      cudaMemcpyAsync(dst, h, cnt * sizeof(double), cudaMemcpyHostToDevice, q);
+      d += cnt;
+      return dst;
+    };
+    const double *r_plude = up(r.plude, n), *r_pcov = up(r.pcovptot, n), *r_fl = up(r.pfplsl, nh),
+                 *r_fn = up(r.pfplsn, nh), *r_hl = up(r.pfhpsl, nh), *r_hn = up(r.pfhpsn, nh),
+                 *r_loc = up(r.tend_loc, CLOUDSC2_NSTATE * n);
+    CK(cudaGetLastError());
+    const long long bstride = (long long)CLOUDSC2_NSTATE * nproma * klev;
+    const size_t slab = (size_t)nproma * klev;
+    struct V { const double *ref, *field; int nlev, ndim; long long bs; };
+    // TENDENCY_LOC%A/%Q/%T/%CLD = B_LOC(:,:,2,:), (:,:,3,:), (:,:,1,:), (:,:,4:,:)  (:248-251)
+    const V v[CLOUDSC2_NVALIDATED] = {
+        {r_plude, st.f.plude, klev, 1, 0}, {r_pcov, st.f.pcovptot, klev, 1, 0}, {r_fl, st.f.pfplsl, klev + 1, 1, 0},
+        {r_fn, st.f.pfplsn, klev + 1, 1, 0}, {r_hl, st.f.pfhpsl, klev + 1, 1, 0}, {r_hn, st.f.pfhpsn, klev + 1, 1, 0},
+        {r_loc + 1 * n, st.f.b_loc + 1 * slab, klev, 1, bstride}, {r_loc + 2 * n, st.f.b_loc + 2 * slab, klev, 1, bstride},
+        {r_loc + 0 * n, st.f.b_loc + 0 * slab, klev, 1, bstride},
+        {r_loc + 3 * n, st.f.b_loc + 3 * slab, klev, CLOUDSC2_NCLV, bstride}};
+    // device layout for the collectives: mins [0..10) | maxs [16..36): vmax, maxerr | sums [48..68)
+    double *d_min = d_out, *d_max = d_out + 16, *d_sum = d_out + 48;
+    CK(csc2_launch_fill(d_min, 10, 1.7976931348623157e308, q));
+    CK(csc2_launch_fill(d_max, 20, -1.7976931348623157e308, q));
+    CK(csc2_launch_fill(d_sum, 20, 0.0, q));
+    for (int i = 0; i < CLOUDSC2_NVALIDATED && st.nblocks; ++i) {
+      const long long bs = v[i].bs ? v[i].bs : (long long)nproma * v[i].nlev * v[i].ndim;
+      // results land where the collectives want them (stream order keeps the shared scratch safe)
+      CK(csc2_launch_validate_split(v[i].ref, klon, v[i].field, nproma, (long long)v[i].nlev * v[i].ndim, bs, st.ngptot,
+                                    st.nblocks, st.gcol0, scratch, d_min + i, d_max + 2 * i, d_sum + 2 * i, q));
+      c.launches += 2;
+    }
+    return 0;
   };
-  const double *r_plude = up(r.plude, n), *r_pcov = up(r.pcovptot, n), *r_fl = up(r.pfplsl, nh),
-               *r_fn = up(r.pfplsn, nh), *r_hl = up(r.pfhpsl, nh), *r_hn = up(r.pfhpsn, nh),
-               *r_loc = up(r.tend_loc, CLOUDSC2_NSTATE * n);
-  CK(cudaGetLastError());
-  const long long bstride = (long long)CLOUDSC2_NSTATE * nproma * klev;
-  const size_t slab = (size_t)nproma * klev;
-  struct V { const double *ref, *field; int nlev, ndim; long long bs; };
-  // TENDENCY_LOC%A/%Q/%T/%CLD = B_LOC(:,:,2,:), (:,:,3,:), (:,:,1,:), (:,:,4:,:)  (:248-251)
-  const V v[CLOUDSC2_NVALIDATED] = {
-      {r_plude, st.f.plude, klev, 1, 0}, {r_pcov, st.f.pcovptot, klev, 1, 0}, {r_fl, st.f.pfplsl, klev + 1, 1, 0},
-      {r_fn, st.f.pfplsn, klev + 1, 1, 0}, {r_hl, st.f.pfhpsl, klev + 1, 1, 0}, {r_hn, st.f.pfhpsn, klev + 1, 1, 0},
-      {r_loc + 1 * n, st.f.b_loc + 1 * slab, klev, 1, bstride}, {r_loc + 2 * n, st.f.b_loc + 2 * slab, klev, 1, bstride},
-      {r_loc + 0 * n, st.f.b_loc + 0 * slab, klev, 1, bstride},
-      {r_loc + 3 * n, st.f.b_loc + 3 * slab, klev, CLOUDSC2_NCLV, bstride}};
-  // device layout for the collectives: mins [0..10) | maxs [16..36): vmax, maxerr | sums [48..68)
-  double *d_min = d_out, *d_max = d_out + 16, *d_sum = d_out + 48;
-  CK(csc2_launch_fill(d_min, 10, 1.7976931348623157e308, q));
-  CK(csc2_launch_fill(d_max, 20, -1.7976931348623157e308, q));
-  CK(csc2_launch_fill(d_sum, 20, 0.0, q));
-  for (int i = 0; i < CLOUDSC2_NVALIDATED && st.nblocks; ++i) {
-    const long long bs = v[i].bs ? v[i].bs : (long long)nproma * v[i].nlev * v[i].ndim;
-    // results land where the collectives want them (stream order keeps the shared scratch safe)
-    CK(csc2_launch_validate_split(v[i].ref, klon, v[i].field, nproma, (long long)v[i].nlev * v[i].ndim, bs, st.ngptot,
-                                  st.nblocks, st.gcol0, scratch, d_min + i, d_max + 2 * i, d_sum + 2 * i, q));
-    c.launches += 2;
-  }
+  if (int rc = csc2_agree(local_part())) return rc;
   // CLOUDSC_MPI_REDUCE_MIN / MAX / SUM (validate_mod.F90:197-199) over NVLink, on the device
-  if (int rc = csc2_allreduce(c, d_min, 10, 1, q)) return rc;
-  if (int rc = csc2_allreduce(c, d_max, 20, 0, q)) return rc;
-  if (int rc = csc2_allreduce(c, d_sum, 20, 2, q)) return rc;
+  if (int rc = csc2_allreduce(c, d_out, 10, 1, q)) return rc;
+  if (int rc = csc2_allreduce(c, d_out + 16, 20, 0, q)) return rc;
+  if (int rc = csc2_allreduce(c, d_out + 48, 20, 2, q)) return rc;
   double h[80];
   CK(cudaMemcpyAsync(h, d_out, sizeof h, cudaMemcpyDeviceToHost, q));
   CK(cudaStreamSynchronize(q));
