@@ -189,11 +189,12 @@ class DeviceState:
 
 
 class Cloudsc2:
-    """One set of constants/switches bound to the library's (single, global) GPU context
-    (cloudsc2_gpu_init ... cloudsc2_gpu_finalize).  The library is not re-entrant, so
-    when several Cloudsc2 objects exist the one being used re-initialises the context with its own
-    constants first -- like the reference, where the switches are module variables set before the
-    driver call (dwarf_cloudsc.F90:105-107)."""
+    """One set of constants/switches bound to the library's device set (one context per GPU, created by
+    cloudsc2_gpu_init / _init_multi / _init_devices, released by cloudsc2_gpu_finalize).  A process has ONE
+    device set at a time, so when several Cloudsc2 objects exist the one being used re-initialises
+    the set with its own constants first -- like the reference, where the constants are module variables set
+    before the driver call (dwarf_cloudsc.F90:105-107); only YRNCL%LREGCL can be switched without that
+    (set_option("lregcl", ...))."""
 
     _owner = None     # the object whose constants are currently loaded in the library
 
